@@ -1,0 +1,311 @@
+// mmn_api.cu — the C ABI of libmmn.so (include/mmn.h): plan construction, launch configuration and
+// argument marshalling around the kernels in mmn_kernels.cuh.  No torch types, no hidden syncs.
+#include "mmn_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+using namespace mmn;
+
+struct mmn_plan {
+  DevPlan host;
+  DevPlan* dev = nullptr;
+  int n_sms = 0;
+  int max_smem = 0;
+};
+
+namespace {
+thread_local std::string g_err;
+
+int fail(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+#define MMN_CUDA(call)                                                            \
+  do {                                                                            \
+    cudaError_t e_ = (call);                                                      \
+    if (e_ != cudaSuccess) return fail("%s: %s", #call, cudaGetErrorString(e_));  \
+  } while (0)
+
+int round32(int v) { return (v + 31) & ~31; }
+
+// largest row tile (32*RM rows) whose shared-memory footprint fits
+int pick_rm(const mmn_plan* p, bool train) {
+  for (int rm : {4, 2, 1})
+    if (step_smem_bytes(p->host, rm, train) <= (size_t)p->max_smem) return rm;
+  return 0;
+}
+int grid_for(const mmn_plan* p, int rm, int64_t n_rows) {
+  const int64_t tiles = (n_rows + 32 * rm - 1) / (32 * rm);
+  return (int)std::max<int64_t>(1, std::min<int64_t>(tiles, p->n_sms));
+}
+
+int check_layer(const mmn_layer_desc& l, int S, int64_t n_params, const char* what, int idx, int j) {
+  if (l.in_dim < 0 || l.out_dim <= 0) return fail("%s %d layer %d: bad dims", what, idx, j);
+  if (l.act < MMN_ACT_IDENTITY || l.act > MMN_ACT_TANH) return fail("%s %d layer %d: unsupported activation", what, idx, j);
+  const int64_t ktot = l.in_dim + (l.has_state ? S : 0);
+  if (ktot <= 0) return fail("%s %d layer %d: empty input", what, idx, j);
+  if (l.w_off < 0 || l.b_off < 0 || l.w_off + ktot * l.out_dim > n_params || l.b_off + l.out_dim > n_params)
+    return fail("%s %d layer %d: parameter offsets out of range", what, idx, j);
+  if ((l.w_off & 3) || (l.b_off & 3)) return fail("%s %d layer %d: offsets must be multiples of 4 floats", what, idx, j);
+  return 0;
+}
+}  // namespace
+
+extern "C" const char* mmn_last_error(void) { return g_err.c_str(); }
+extern "C" int mmn_abi_version(void) { return MMN_ABI_VERSION; }
+
+extern "C" int mmn_plan_create(const mmn_model_desc* desc, mmn_plan** out) {
+  if (!desc || !out) return fail("mmn_plan_create: null argument");
+  const int S = desc->state_size, E = desc->n_encoders, D = desc->n_decoders;
+  if (S <= 0) return fail("state_size must be positive");
+  if (E <= 0 || E > MMN_MAX_ENCODERS) return fail("n_encoders must be in [1, %d]", MMN_MAX_ENCODERS);
+  if (D <= 0 || D > MMN_MAX_DECODERS) return fail("n_decoders must be in [1, %d]", MMN_MAX_DECODERS);
+  if (desc->init_off < 0 || desc->init_off + S > desc->n_params || (desc->init_off & 3))
+    return fail("init_off out of range or not a multiple of 4");
+  if (desc->n_params >= (1ll << 31)) return fail("n_params too large");
+
+  mmn_plan* p = new mmn_plan();
+  DevPlan& P = p->host;
+  memset(&P, 0, sizeof P);
+  P.S = S; P.E = E; P.D = D;
+  P.init_off = desc->init_off;
+  P.n_params = desc->n_params;
+  int maxH = 1;
+  P.enc_stash = 0;
+  for (int e = 0; e < E; ++e) {
+    const mmn_encoder_desc& src = desc->encoders[e];
+    DevEncoder& dst = P.enc[e];
+    if (src.n_layers < 1 || src.n_layers > MMN_MAX_LAYERS) { delete p; return fail("encoder %d: n_layers must be in [1, %d]", e, MMN_MAX_LAYERS); }
+    if (!(src.dropout_p >= 0.f && src.dropout_p < 1.f)) { delete p; return fail("encoder %d: dropout must be in [0, 1)", e); }
+    dst.F = src.n_features; dst.n_layers = src.n_layers; dst.p_drop = src.dropout_p;
+    int n_state = 0, off = 0;
+    long long lo = desc->n_params, hi = 0;
+    for (int j = 0; j < src.n_layers; ++j) {
+      const mmn_layer_desc& l = src.layers[j];
+      if (check_layer(l, S, desc->n_params, "encoder", e, j)) { delete p; return 1; }
+      DevLayer& d = dst.L[j];
+      d.in_dim = l.in_dim; d.out_dim = l.out_dim; d.act = l.act; d.has_state = l.has_state ? 1 : 0;
+      d.ktot = l.in_dim + (l.has_state ? S : 0);
+      d.w_off = l.w_off; d.b_off = l.b_off;
+      n_state += d.has_state;
+      if (j == 0 && l.in_dim != src.n_features) { delete p; return fail("encoder %d: layer 0 in_dim != n_features", e); }
+      if (j > 0 && l.in_dim != src.layers[j - 1].out_dim) { delete p; return fail("encoder %d: layer %d in_dim mismatch", e, j); }
+      if (j < src.n_layers - 1) { d.stash_off = off; off += l.out_dim; maxH = std::max(maxH, l.out_dim); }
+      lo = std::min<long long>(lo, std::min(l.w_off, l.b_off));
+      hi = std::max<long long>(hi, std::max<long long>(l.w_off + (long long)d.ktot * l.out_dim, l.b_off + l.out_dim));
+    }
+    if (src.layers[src.n_layers - 1].out_dim != S) { delete p; return fail("encoder %d: last layer must produce the state", e); }
+    if (n_state != 1) { delete p; return fail("encoder %d: exactly one layer must take the state", e); }
+    if (src.dropout_p > 0.f && !src.layers[0].has_state) { delete p; return fail("encoder %d: dropout needs the state on layer 0 (MIMIC_MLPEncoder)", e); }
+    dst.param_lo = (int)lo; dst.param_hi = (int)hi;
+    P.enc_stash = std::max(P.enc_stash, off);
+  }
+  for (int a = 0; a < E; ++a)
+    for (int b = a + 1; b < E; ++b)
+      if (P.enc[a].param_lo < P.enc[b].param_hi && P.enc[b].param_lo < P.enc[a].param_hi) {
+        delete p;
+        return fail("encoders %d and %d: parameter ranges overlap", a, b);
+      }
+  P.dec_stash = 0; P.sumC = 0;
+  for (int d = 0; d < D; ++d) {
+    const mmn_decoder_desc& src = desc->decoders[d];
+    DevDecoder& dst = P.dec[d];
+    if (src.n_layers < 1 || src.n_layers > MMN_MAX_LAYERS) { delete p; return fail("decoder %d: n_layers must be in [1, %d]", d, MMN_MAX_LAYERS); }
+    if (src.n_classes < 1 || src.n_classes > MMN_MAX_CLASSES) { delete p; return fail("decoder %d: n_classes must be in [1, %d]", d, MMN_MAX_CLASSES); }
+    dst.C = src.n_classes; dst.n_layers = src.n_layers; dst.out_off = P.sumC; dst.stash_off = P.dec_stash;
+    int off = 0;
+    for (int j = 0; j < src.n_layers; ++j) {
+      const mmn_layer_desc& l = src.layers[j];
+      if (check_layer(l, S, desc->n_params, "decoder", d, j)) { delete p; return 1; }
+      if (l.has_state) { delete p; return fail("decoder %d: has_state is an encoder concept", d); }
+      if (l.in_dim != (j == 0 ? S : src.layers[j - 1].out_dim)) { delete p; return fail("decoder %d: layer %d in_dim mismatch", d, j); }
+      DevLayer& dl = dst.L[j];
+      dl.in_dim = l.in_dim; dl.out_dim = l.out_dim; dl.act = l.act; dl.has_state = 0; dl.ktot = l.in_dim;
+      dl.w_off = l.w_off; dl.b_off = l.b_off; dl.stash_off = off;
+      off += l.out_dim;
+      maxH = std::max(maxH, l.out_dim);
+    }
+    if (src.layers[src.n_layers - 1].out_dim != src.n_classes) { delete p; return fail("decoder %d: last layer must produce n_classes", d); }
+    P.dec_stash += off;
+    P.sumC += src.n_classes;
+  }
+  P.ldS = round32(S) + 4;
+  P.ldH = round32(maxH) + 4;
+  P.stash_row = (E + 1) * S + E * P.enc_stash + (E + 1) * P.dec_stash;
+  P.n_metrics = 6 * (E + 1) * D + (E + 1) + E;
+
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&p->n_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&p->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
+    delete p;
+    return fail("mmn_plan_create: no CUDA device");
+  }
+  if (pick_rm(p, true) == 0) {
+    const size_t need = step_smem_bytes(P, 1, true);
+    delete p;
+    return fail("model too wide for the fused step kernel: needs %zu B of shared memory per 32-row tile", need);
+  }
+  if (cudaMalloc((void**)&p->dev, sizeof(DevPlan)) != cudaSuccess ||
+      cudaMemcpy(p->dev, &P, sizeof(DevPlan), cudaMemcpyHostToDevice) != cudaSuccess) {
+    delete p;
+    return fail("mmn_plan_create: device allocation failed");
+  }
+  *out = p;
+  return 0;
+}
+
+extern "C" void mmn_plan_destroy(mmn_plan* plan) {
+  if (!plan) return;
+  if (plan->dev) cudaFree(plan->dev);
+  delete plan;
+}
+
+extern "C" int64_t mmn_metrics_count(const mmn_plan* plan) { return plan ? plan->host.n_metrics : -1; }
+extern "C" int64_t mmn_grad_count(const mmn_plan* plan) { return plan ? plan->host.n_params + plan->host.E : -1; }
+
+extern "C" int64_t mmn_workspace_bytes(const mmn_plan* plan, int64_t n_rows, int32_t with_backward) {
+  if (!plan || n_rows < 0) return -1;
+  if (!with_backward) return 0;
+  const int rm = pick_rm(plan, true);
+  return (int64_t)grid_for(plan, rm, n_rows) * 32 * rm * plan->host.stash_row * 4;
+}
+
+namespace {
+int fill_args(const mmn_plan* plan, const mmn_batch* b, const float* params, const mmn_outputs* out, StepArgs& a) {
+  const DevPlan& P = plan->host;
+  if (!b || !params) return fail("null batch / params");
+  if (b->n_rows <= 0) return fail("n_rows must be positive");
+  if (b->seq_len < 0 || b->seq_len > P.E) return fail("seq_len must be in [0, E]");
+  memset(&a, 0, sizeof a);
+  a.plan = plan->dev;
+  a.params = params;
+  a.n_rows = b->n_rows;
+  a.row_offset = b->row_offset;
+  const int64_t bg = b->n_rows_global > 0 ? b->n_rows_global : b->n_rows;
+  a.inv_rows_global = 1.0 / (double)bg;
+  a.seq_len = b->seq_len;
+  unsigned seen = 0;
+  for (int k = 0; k < b->seq_len; ++k) {
+    const int e = b->seq_enc[k], pos = b->seq_pos[k];
+    if (e < 0 || e >= P.E) return fail("sequence step %d: encoder id %d out of range", k, e);
+    if (seen & (1u << e)) return fail("sequence step %d: encoder id %d appears twice", k, e);
+    seen |= 1u << e;
+    if (pos < 0 || pos >= MMN_MAX_ENCODERS) return fail("sequence step %d: data position out of range", k);
+    if (!b->x[pos]) return fail("sequence step %d: x[%d] is null", k, pos);
+    if (b->x_ld[pos] < P.enc[e].F) return fail("sequence step %d: x[%d] row stride %lld < n_features %d", k, pos, (long long)b->x_ld[pos], P.enc[e].F);
+    a.seq_enc[k] = e;
+    a.seq_pos[k] = pos;
+    a.x[pos] = b->x[pos];
+    a.x_ld[pos] = b->x_ld[pos];
+  }
+  a.targets = (const long long*)b->targets;
+  a.skip_flags = b->skip_flags;
+  if (out) {
+    a.metrics = out->metrics;
+    a.predictions = out->predictions;
+    a.pred_ld = out->pred_ld;
+    a.last_outputs = out->last_outputs;
+    a.final_state = out->final_state;
+    if (out->predictions && out->pred_ld < b->n_rows) return fail("pred_ld < n_rows");
+  }
+  return 0;
+}
+
+template <bool TRAIN>
+int launch_step(const mmn_plan* plan, int rm, const StepArgs& a, void* stream) {
+  const size_t smem = step_smem_bytes(plan->host, rm, TRAIN);
+  const int grid = grid_for(plan, rm, a.n_rows);
+#define MMN_CASE(RM_)                                                                              \
+  case RM_: {                                                                                      \
+    auto kfn = mmn_step_kernel<RM_, TRAIN>;                                                        \
+    MMN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    MMN_LAUNCH(kfn, dim3(grid), dim3(kThreads), smem, stream, a);                                  \
+    break;                                                                                         \
+  }
+  switch (rm) {
+    MMN_CASE(4)
+    MMN_CASE(2)
+    MMN_CASE(1)
+    default: return fail("no tile configuration fits");
+  }
+#undef MMN_CASE
+  MMN_CUDA(cudaGetLastError());
+  return 0;
+}
+}  // namespace
+
+extern "C" int mmn_scan_missing(const mmn_plan* plan, const mmn_batch* b, int32_t* flags, void* stream) {
+  if (!plan || !b || !flags) return fail("mmn_scan_missing: null argument");
+  const DevPlan& P = plan->host;
+  if (b->seq_len < 0 || b->seq_len > P.E) return fail("seq_len must be in [0, E]");
+  ScanArgs s;
+  memset(&s, 0, sizeof s);
+  s.seq_len = b->seq_len;
+  s.n_rows = b->n_rows;
+  s.flags = flags;
+  for (int k = 0; k < b->seq_len; ++k) {
+    const int e = b->seq_enc[k], pos = b->seq_pos[k];
+    if (e < 0 || e >= P.E || pos < 0 || pos >= MMN_MAX_ENCODERS || !b->x[pos]) return fail("mmn_scan_missing: bad sequence step %d", k);
+    s.F[k] = P.enc[e].F;
+    s.x[k] = b->x[pos];
+    s.x_ld[k] = b->x_ld[pos];
+  }
+  MMN_CUDA(cudaMemsetAsync(flags, 0, sizeof(int32_t) * std::max(1, b->seq_len), (cudaStream_t)stream));
+  const int grid = std::max(1, std::min(plan->n_sms * 4, (int)((b->n_rows + 7) / 8)));
+  MMN_LAUNCH(mmn_scan_missing_kernel, dim3(grid), dim3(256), 0, stream, s);
+  MMN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmn_forward(const mmn_plan* plan, const mmn_batch* batch, const float* params,
+                           const mmn_outputs* out, void* workspace, size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  if (!plan) return fail("mmn_forward: null plan");
+  StepArgs a;
+  if (fill_args(plan, batch, params, out, a)) return 1;
+  return launch_step<false>(plan, pick_rm(plan, false), a, stream);
+}
+
+extern "C" int mmn_train_step(const mmn_plan* plan, const mmn_batch* batch, const float* params,
+                              const mmn_train_args* targs, const mmn_outputs* out, float* grads,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  if (!plan || !targs || !grads) return fail("mmn_train_step: null argument");
+  const DevPlan& P = plan->host;
+  StepArgs a;
+  if (fill_args(plan, batch, params, out, a)) return 1;
+  if (!batch->targets) return fail("mmn_train_step: targets are required");
+  const int64_t need = mmn_workspace_bytes(plan, batch->n_rows, 1);
+  if (!workspace || (int64_t)workspace_bytes < need) return fail("workspace too small: need %lld bytes", (long long)need);
+  const int rm = pick_rm(plan, true);
+  const double bg = 1.0 / a.inv_rows_global;
+  a.grads = grads;
+  a.stash = (float*)workspace;
+  a.slot_floats = (long long)32 * rm * P.stash_row;
+  a.c_err = (float)((double)targs->err_penalty / ((double)P.D * (P.E + 1) * bg));
+  a.c_sc = (float)(2.0 * (double)targs->state_change_penalty_scaled / ((double)P.E * bg * P.S));
+  a.dropout_seed = targs->dropout_seed;
+  a.training = targs->training;
+  MMN_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)(P.n_params + P.E), (cudaStream_t)stream));
+  return launch_step<true>(plan, rm, a, stream);
+}
+
+extern "C" int mmn_adam_step(const mmn_plan* plan, float* params, const float* grads, float* exp_avg,
+                             float* exp_avg_sq, int32_t* step_count, float lr, float beta1, float beta2,
+                             float eps, void* stream) {
+  if (!plan || !params || !grads || !exp_avg || !exp_avg_sq || !step_count) return fail("mmn_adam_step: null argument");
+  MMN_LAUNCH(mmn_adam_tick_kernel, dim3(1), dim3(32), 0, stream, plan->dev, grads, step_count);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((plan->host.n_params + 255) / 256, (int64_t)plan->n_sms * 8));
+  MMN_LAUNCH(mmn_adam_kernel, dim3(grid), dim3(256), 0, stream, plan->dev, params, grads, exp_avg, exp_avg_sq,
+             step_count, lr, beta1, beta2, eps);
+  MMN_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,822 @@
+// mmn_kernels.cuh — the fused sequential-fusion step for sm_100a (fp32 FMA path).
+//
+// One persistent CTA per batch tile of TM = 32*RM rows walks the whole encoding sequence with the
+// running state resident in shared memory (reference loop nest: multimodn/multimodn.py:139-191):
+//
+//   s_0 = init state                                   state.py:29-32
+//   every decoder on s_0: CE, arg-max, counters        multimodn.py:141-157
+//   for each (position, encoder id) in the sequence:   multimodn.py:159-163
+//       stream x tile from HBM, per-row NaN scan       multimodn.py:168 (per row instead of per batch)
+//       s^ = Encoder(s, x)                             mlp_encoder.py:40-47 / 74-80
+//       s  = present ? s^ : s ; state-change sum       multimodn.py:173-174
+//       every decoder on s                             multimodn.py:176-191
+//   (training) replay the sequence in reverse for loss.backward()   multimodn.py:194-203
+//
+// Every Linear layer is a small GEMM over the tile, computed with 4x4 (RM x 4) register tiles by
+// 32 row-threads x 8 column-threads.  Three shapes are needed and each has one routine:
+//   gemm_nt : out[r][n]  = sum_k a[r][k]  W[n][k]   forward
+//   gemm_nn : din[r][j]  = sum_n dz[r][n] W[n][j]   data gradient
+//   gemm_tn : dW[n][k]  += sum_r dz[r][n] a[r][k]   weight gradient (rows split over 4 thread groups,
+//                                                   reduced in shared memory, one red.global per tile)
+// Shared-memory tiles are row-major with leading dimension == 4 (mod 32) and rows / columns are
+// assigned to threads with stride (r = ty + 32 i, n = tx + 8 j) so that every LDS.128 of a warp
+// touches 32 distinct banks.  Invariant: columns [width, roundup32(width)) of every activation tile
+// are zero, so K loops may run in whole float4 steps.
+//
+// The backward pass needs the forward activations of the tile; they are stashed in a per-CTA slot of
+// global memory that is reused tile after tile (it stays L2-resident) and read back with ld.global.cg.
+#pragma once
+
+#include "mmn_common.cuh"
+
+namespace mmn {
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_fwd(int act, float z) {
+  switch (act) {
+    case MMN_ACT_RELU: return z > 0.f ? z : 0.f;
+    case MMN_ACT_SIGMOID: return 1.f / (1.f + expf(-z));
+    case MMN_ACT_TANH: return tanhf(z);
+    default: return z;
+  }
+}
+// derivative through the activation OUTPUT
+__device__ __forceinline__ float act_bwd(int act, float out) {
+  switch (act) {
+    case MMN_ACT_RELU: return out > 0.f ? 1.f : 0.f;
+    case MMN_ACT_SIGMOID: return out * (1.f - out);
+    case MMN_ACT_TANH: return 1.f - out * out;
+    default: return 1.f;
+  }
+}
+
+// dropout keep decision: counter-based hash of (seed, encoder, global row, column).  The oracle
+// (oracle/multimodn_oracle.py: dropout_keep) computes the same bits.
+__device__ __forceinline__ bool mmn_dropout_keep(unsigned seed_mix, unsigned row, unsigned col, unsigned thr) {
+  unsigned x = row * 0x85EBCA6Bu + col * 0xC2B2AE35u + seed_mix;
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  return (x >> 8) >= thr;
+}
+
+struct Drop {
+  int enabled;
+  unsigned seed_mix, thr, row_base;
+  float scale;
+};
+
+struct Smem {
+  float *S, *T, *A, *B, *XB, *WB, *RED;
+  int* ys;
+  int* rownan;
+  int* cnt;          // [E+1] present rows per history row, summed over this CTA's tiles
+  int* tile_any;     // [E+1] does the current tile have a present row at step k
+  double* met;
+  unsigned char* present;   // [(E+1)][TM]
+};
+
+// One K-segment of a GEMM's activation operand.
+enum { SEG_SMEM = 0, SEG_X = 1, SEG_STASH = 2, SEG_SMEM_STAGED = 3 };
+struct ASeg {
+  const float* ptr;   // SEG_SMEM*: tile base in shared memory; SEG_X/SEG_STASH: global, row 0 of the tile
+  long long ld;
+  int width;
+  int kind;
+  int wcol;           // first weight column this segment multiplies (== its column in [a || state])
+};
+
+template <int RM>
+struct Cfg {
+  static constexpr int TM = 32 * RM;
+};
+
+// 32x32 block of a row-major weight matrix -> WB[32][LDX], zero-filled outside (nrows, ncols)
+__device__ __forceinline__ void stage_w_block(float* WB, const float* __restrict__ W, int ldw, int row0,
+                                              int nrows, int col0, int ncols) {
+  const int t = threadIdx.x, c = t & 31, r0 = t >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + 8 * i;
+    float v = 0.f;
+    if (r < nrows && c < ncols) v = __ldg(W + (long long)(row0 + r) * ldw + col0 + c);
+    WB[r * LDX + c] = v;
+  }
+}
+
+// TM x 32 chunk of an activation source -> XB[TM][LDX]; zero-fill, NaN scan + sanitise for x,
+// dropout mask when enabled.
+template <int RM>
+__device__ __forceinline__ void stage_a_chunk(const Smem& sm, const ASeg& sg, int k0, int kw, int rows_valid,
+                                              const Drop& drop, bool scan_nan) {
+  const int t = threadIdx.x, c = t & 31, r0 = t >> 5;
+#pragma unroll 4
+  for (int i = 0; i < 4 * RM; ++i) {
+    const int r = r0 + 8 * i;
+    float v = 0.f;
+    if (c < kw) {
+      if (sg.kind == SEG_SMEM_STAGED) {
+        v = sg.ptr[(long long)r * sg.ld + k0 + c];
+      } else if (r < rows_valid) {
+        const float* p = sg.ptr + (long long)r * sg.ld + k0 + c;
+        if (sg.kind == SEG_X) {
+          v = __ldg(p);
+          if (v != v) {                 // NaN marks the modality missing for this row
+            if (scan_nan) sm.rownan[r] = 1;
+            v = 0.f;                    // never let it reach arithmetic (0 * NaN = NaN)
+          }
+        } else {
+          v = __ldcg(p);                // stash written earlier by this CTA: L2-coherent load
+        }
+      }
+      if (drop.enabled) {
+        v = mmn_dropout_keep(drop.seed_mix, drop.row_base + (unsigned)r, (unsigned)(sg.wcol + k0 + c), drop.thr)
+                ? v * drop.scale : 0.f;
+      }
+    }
+    sm.XB[r * LDX + c] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gemm_nt: out[r][n] = sum over segments sum_k a[r][k] * W[n][wcol + k];  epi(r, n, acc) for every
+// (r, n) of each 32-column pass, including the zero-pad columns n >= N.
+// ------------------------------------------------------------------------------------------------
+template <int RM, class Epi>
+__device__ __forceinline__ void gemm_nt(const Smem& sm, const float* __restrict__ W, int ldw, int N,
+                                        const ASeg* segs, int nseg, const Drop& drop, int rows_valid,
+                                        bool scan_nan, Epi epi) {
+  const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+  for (int n0 = 0; n0 < N; n0 += 32) {
+    float acc[RM][4];
+#pragma unroll
+    for (int i = 0; i < RM; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int s = 0; s < nseg; ++s) {
+      const ASeg sg = segs[s];
+      for (int k0 = 0; k0 < sg.width; k0 += KC) {
+        const int kw = min(KC, sg.width - k0);
+        __syncthreads();
+        stage_w_block(sm.WB, W, ldw, n0, min(32, N - n0), sg.wcol + k0, kw);
+        const float* a;
+        int lda;
+        if (sg.kind == SEG_SMEM) {
+          a = sg.ptr + k0;
+          lda = (int)sg.ld;
+        } else {
+          stage_a_chunk<RM>(sm, sg, k0, kw, rows_valid, drop, scan_nan && n0 == 0);
+          a = sm.XB;
+          lda = LDX;
+        }
+        __syncthreads();
+        const int nq = (kw + 3) >> 2;
+#pragma unroll 2
+        for (int q = 0; q < nq; ++q) {
+          float4 av[RM], bv[4];
+#pragma unroll
+          for (int i = 0; i < RM; ++i) av[i] = *reinterpret_cast<const float4*>(a + (ty + 32 * i) * lda + 4 * q);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bv[j] = *reinterpret_cast<const float4*>(sm.WB + (tx + 8 * j) * LDX + 4 * q);
+#pragma unroll
+          for (int i = 0; i < RM; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              acc[i][j] = fmaf(av[i].x, bv[j].x, acc[i][j]);
+              acc[i][j] = fmaf(av[i].y, bv[j].y, acc[i][j]);
+              acc[i][j] = fmaf(av[i].z, bv[j].z, acc[i][j]);
+              acc[i][j] = fmaf(av[i].w, bv[j].w, acc[i][j]);
+            }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < RM; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) epi(ty + 32 * i, n0 + tx + 8 * j, acc[i][j]);
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// gemm_nn: out[r][j] = sum_n dz[r][n] * W[n][col0 + j], j < J;  epi(r, j, acc) for every (r, j) of
+// each 32-column pass including pad columns j >= J.  dz: shared tile, zero-padded to 32 columns.
+// ------------------------------------------------------------------------------------------------
+template <int RM, class Epi>
+__device__ __forceinline__ void gemm_nn(const Smem& sm, const float* dz, int ldd, int N,
+                                        const float* __restrict__ W, int ldw, int col0, int J, Epi epi) {
+  const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+  for (int j0 = 0; j0 < J; j0 += 32) {
+    float acc[RM][4];
+#pragma unroll
+    for (int i = 0; i < RM; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int n0 = 0; n0 < N; n0 += 32) {
+      const int nw = min(32, N - n0);
+      __syncthreads();
+      stage_w_block(sm.WB, W, ldw, n0, nw, col0 + j0, min(32, J - j0));
+      __syncthreads();
+      const int nq = (nw + 3) >> 2;
+#pragma unroll 2
+      for (int q = 0; q < nq; ++q) {
+        float4 av[RM], bv[4];
+#pragma unroll
+        for (int i = 0; i < RM; ++i) av[i] = *reinterpret_cast<const float4*>(dz + (ty + 32 * i) * ldd + n0 + 4 * q);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) bv[u] = *reinterpret_cast<const float4*>(sm.WB + (4 * q + u) * LDX + 4 * tx);
+#pragma unroll
+        for (int i = 0; i < RM; ++i) {
+          acc[i][0] = fmaf(av[i].x, bv[0].x, acc[i][0]); acc[i][1] = fmaf(av[i].x, bv[0].y, acc[i][1]);
+          acc[i][2] = fmaf(av[i].x, bv[0].z, acc[i][2]); acc[i][3] = fmaf(av[i].x, bv[0].w, acc[i][3]);
+          acc[i][0] = fmaf(av[i].y, bv[1].x, acc[i][0]); acc[i][1] = fmaf(av[i].y, bv[1].y, acc[i][1]);
+          acc[i][2] = fmaf(av[i].y, bv[1].z, acc[i][2]); acc[i][3] = fmaf(av[i].y, bv[1].w, acc[i][3]);
+          acc[i][0] = fmaf(av[i].z, bv[2].x, acc[i][0]); acc[i][1] = fmaf(av[i].z, bv[2].y, acc[i][1]);
+          acc[i][2] = fmaf(av[i].z, bv[2].z, acc[i][2]); acc[i][3] = fmaf(av[i].z, bv[2].w, acc[i][3]);
+          acc[i][0] = fmaf(av[i].w, bv[3].x, acc[i][0]); acc[i][1] = fmaf(av[i].w, bv[3].y, acc[i][1]);
+          acc[i][2] = fmaf(av[i].w, bv[3].z, acc[i][2]); acc[i][3] = fmaf(av[i].w, bv[3].w, acc[i][3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < RM; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) epi(ty + 32 * i, j0 + 4 * tx + c, acc[i][c]);
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// gemm_tn: gW[n][wcol + k] += sum_r dz[r][n] * a[r][k]   (weight gradient of one K-segment).
+// The TM rows are split over kGroups groups of 64 threads; each group owns the whole 32x32 output
+// block for its rows (4x4 outputs per thread), the groups' partial blocks are summed through
+// shared memory and the tile's contribution is added to global memory with one red per element.
+// ------------------------------------------------------------------------------------------------
+template <int RM>
+__device__ __forceinline__ void gemm_tn(const Smem& sm, const float* dz, int ldd, int N, const ASeg& sg,
+                                        const Drop& drop, int rows_valid, float* __restrict__ gW, int ldw) {
+  constexpr int RPG = 8 * RM;     // rows per group
+  const int tid = threadIdx.x, g = tid >> 6, u = tid & 63, nt = u >> 3, kt = u & 7;
+  const bool vec_ok = ((ldw & 3) == 0) && ((sg.wcol & 3) == 0) && ((reinterpret_cast<size_t>(gW) & 15) == 0);
+  for (int k0 = 0; k0 < sg.width; k0 += KC) {
+    const int kw = min(KC, sg.width - k0);
+    const float* a;
+    int lda;
+    __syncthreads();
+    if (sg.kind == SEG_SMEM) {
+      a = sg.ptr + k0;
+      lda = (int)sg.ld;
+    } else {
+      stage_a_chunk<RM>(sm, sg, k0, kw, rows_valid, drop, false);
+      a = sm.XB;
+      lda = LDX;
+    }
+    __syncthreads();
+    for (int n0 = 0; n0 < N; n0 += 32) {
+      float acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+      for (int rr = 0; rr < RPG; ++rr) {
+        const int r = g * RPG + rr;
+        const float4 dv = *reinterpret_cast<const float4*>(dz + r * ldd + n0 + 4 * nt);
+        const float4 iv = *reinterpret_cast<const float4*>(a + r * lda + 4 * kt);
+        acc[0][0] = fmaf(dv.x, iv.x, acc[0][0]); acc[0][1] = fmaf(dv.x, iv.y, acc[0][1]);
+        acc[0][2] = fmaf(dv.x, iv.z, acc[0][2]); acc[0][3] = fmaf(dv.x, iv.w, acc[0][3]);
+        acc[1][0] = fmaf(dv.y, iv.x, acc[1][0]); acc[1][1] = fmaf(dv.y, iv.y, acc[1][1]);
+        acc[1][2] = fmaf(dv.y, iv.z, acc[1][2]); acc[1][3] = fmaf(dv.y, iv.w, acc[1][3]);
+        acc[2][0] = fmaf(dv.z, iv.x, acc[2][0]); acc[2][1] = fmaf(dv.z, iv.y, acc[2][1]);
+        acc[2][2] = fmaf(dv.z, iv.z, acc[2][2]); acc[2][3] = fmaf(dv.z, iv.w, acc[2][3]);
+        acc[3][0] = fmaf(dv.w, iv.x, acc[3][0]); acc[3][1] = fmaf(dv.w, iv.y, acc[3][1]);
+        acc[3][2] = fmaf(dv.w, iv.z, acc[3][2]); acc[3][3] = fmaf(dv.w, iv.w, acc[3][3]);
+      }
+      float* red = sm.RED + g * 1024;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(red + (4 * nt + i) * 32 + 4 * kt) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      __syncthreads();
+      {
+        const int n = tid >> 3, kq = tid & 7;    // 256 threads x 4 outputs = the 32x32 block
+        float4 s = *reinterpret_cast<const float4*>(sm.RED + n * 32 + 4 * kq);
+#pragma unroll
+        for (int gg = 1; gg < kGroups; ++gg) {
+          const float4 o = *reinterpret_cast<const float4*>(sm.RED + gg * 1024 + n * 32 + 4 * kq);
+          s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+        }
+        if (n0 + n < N) {
+          const int kc = k0 + 4 * kq;
+          float* dst = gW + (long long)(n0 + n) * ldw + sg.wcol + kc;
+          if (vec_ok && kc + 3 < sg.width) {
+            atomicAdd(reinterpret_cast<float4*>(dst), s);
+          } else {
+            if (kc + 0 < sg.width) atomicAdd(dst + 0, s.x);
+            if (kc + 1 < sg.width) atomicAdd(dst + 1, s.y);
+            if (kc + 2 < sg.width) atomicAdd(dst + 2, s.z);
+            if (kc + 3 < sg.width) atomicAdd(dst + 3, s.w);
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// bias gradient: gb[n] += sum_r dz[r][n]
+template <int RM>
+__device__ __forceinline__ void colsum_red(const Smem& sm, const float* dz, int ldd, int N, float* __restrict__ gb) {
+  constexpr int TM = Cfg<RM>::TM;
+  const int tid = threadIdx.x, c = tid & 31, part = tid >> 5;
+  for (int n0 = 0; n0 < N; n0 += 32) {
+    float s = 0.f;
+    for (int r = part; r < TM; r += 8) s += dz[r * ldd + n0 + c];
+    __syncthreads();
+    sm.RED[part * 32 + c] = s;
+    __syncthreads();
+    if (tid < 32 && n0 + tid < N) {
+      float tot = 0.f;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) tot += sm.RED[p * 32 + tid];
+      atomicAdd(gb + n0 + tid, tot);
+    }
+  }
+  __syncthreads();
+}
+
+// shared tile [TM x width] -> global row-major [TM x width]
+template <int RM>
+__device__ __forceinline__ void stash_store(float* dst, const float* buf, int ld, int width) {
+  constexpr int TM = Cfg<RM>::TM;
+  for (int idx = threadIdx.x; idx < TM * width; idx += kThreads) {
+    const int r = idx / width, c = idx - r * width;
+    __stcg(dst + idx, buf[r * ld + c]);
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ unsigned warp_sum_u(unsigned v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the step kernel
+// ------------------------------------------------------------------------------------------------
+template <int RM, bool TRAIN>
+__global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs args) {
+  constexpr int TM = Cfg<RM>::TM;
+  const DevPlan& P = *args.plan;
+  const int tid = threadIdx.x;
+  const int S = P.S, E = P.E, D = P.D, ldS = P.ldS, ldH = P.ldH;
+  const int L = args.seq_len;
+  const float* __restrict__ params = args.params;
+
+  MMN_DYN_SMEM(smem_raw);
+  Smem sm;
+  {
+    float* f = reinterpret_cast<float*>(smem_raw);
+    sm.S = f; f += TM * ldS;
+    sm.T = f; f += TM * ldS;
+    sm.A = f; f += TM * ldH;
+    sm.B = f; f += TM * ldH;
+    sm.XB = f; f += TM * LDX;
+    sm.WB = f; f += 32 * LDX;
+    sm.RED = f; f += kGroups * 1024;
+    sm.ys = reinterpret_cast<int*>(f); f += TM * D;
+    sm.rownan = reinterpret_cast<int*>(f); f += TM;
+    sm.cnt = reinterpret_cast<int*>(f); f += (E + 1);
+    sm.tile_any = reinterpret_cast<int*>(f); f += (E + 1);
+    size_t off = (reinterpret_cast<char*>(f) - smem_raw + 7) & ~(size_t)7;
+    sm.met = reinterpret_cast<double*>(smem_raw + off);
+    sm.present = reinterpret_cast<unsigned char*>(sm.met + P.n_metrics);
+  }
+  for (int i = tid; i < P.n_metrics; i += kThreads) sm.met[i] = 0.0;
+  for (int i = tid; i < E + 1; i += kThreads) sm.cnt[i] = 0;
+
+  const long long n_tiles = (args.n_rows + TM - 1) / TM;
+  float* slot = TRAIN ? args.stash + (long long)blockIdx.x * args.slot_floats : nullptr;
+  Drop nodrop;
+  nodrop.enabled = 0; nodrop.seed_mix = 0; nodrop.thr = 0; nodrop.row_base = 0; nodrop.scale = 1.f;
+
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long row0 = tile * TM;
+    const int rows_valid = (int)min((long long)TM, args.n_rows - row0);
+    __syncthreads();
+
+    // ---- tile prologue: targets, initial state (state.py:29-32), masks ----
+    if (args.targets) {
+      for (int idx = tid; idx < TM * D; idx += kThreads) {
+        const int r = idx / D;
+        long long y = 0;
+        if (r < rows_valid) y = args.targets[(row0 + r) * D + (idx - r * D)];
+        sm.ys[idx] = (int)y;
+      }
+    }
+    for (int idx = tid; idx < TM * ldS; idx += kThreads) {
+      const int c = idx % ldS;
+      sm.S[idx] = c < S ? __ldg(params + P.init_off + c) : 0.f;
+    }
+    for (int r = tid; r < TM; r += kThreads) sm.present[r] = r < rows_valid;
+    if (tid == 0) sm.tile_any[0] = 1;
+    if (tid < TM && tid < rows_valid) atomicAdd(&sm.cnt[0], 1);
+    __syncthreads();
+    if (TRAIN) stash_store<RM>(slot + (long long)stash_state_off(P, 0) * TM, sm.S, ldS, S);
+
+    // ---- decoders on the current state (multimodn.py:141-157, 176-191) ----
+    auto decoders_forward = [&](int k, int hist_row, bool is_last_enc) {
+      for (int d = 0; d < D; ++d) {
+        const DevDecoder& dec = P.dec[d];
+        const float* in = sm.S;
+        int ldin = ldS;
+        for (int j = 0; j < dec.n_layers; ++j) {
+          const DevLayer& ly = dec.L[j];
+          float* out = (j & 1) ? sm.B : sm.A;
+          ASeg seg;
+          seg.ptr = in; seg.ld = ldin; seg.width = ly.in_dim; seg.kind = SEG_SMEM; seg.wcol = 0;
+          const float* __restrict__ bias = params + ly.b_off;
+          const int N = ly.out_dim, act = ly.act;
+          gemm_nt<RM>(sm, params + ly.w_off, ly.ktot, N, &seg, 1, nodrop, rows_valid, false,
+                      [&](int r, int n, float acc) {
+                        out[r * ldH + n] = n < N ? act_fwd(act, acc + __ldg(bias + n)) : 0.f;
+                      });
+          if (TRAIN)
+            stash_store<RM>(slot + (long long)(stash_dec_off(P, k) + dec.stash_off + ly.stash_off) * TM, out, ldH, N);
+          in = out;
+          ldin = ldH;
+        }
+        // per-row epilogue: first-max arg-max, CE on the outputs, confusion cells
+        const int C = dec.C;
+        if (tid < TM) {                       // whole warps: TM is a multiple of 32
+          const int r = tid;
+          const float* p = in + r * ldH;
+          const bool m = sm.present[k * TM + r] != 0;
+          float best = p[0];
+          int pred = 0;
+          for (int c = 1; c < C; ++c) {
+            const float v = p[c];
+            if (v > best || (v != v && best == best)) { best = v; pred = c; }   // NaN wins, like torch.max
+          }
+          if (r < rows_valid) {
+            if (args.predictions) args.predictions[((long long)hist_row * D + d) * args.pred_ld + row0 + r] = (unsigned char)pred;
+            if (args.last_outputs && is_last_enc) {
+              float* o = args.last_outputs + (row0 + r) * P.sumC + dec.out_off;
+              for (int c = 0; c < C; ++c) o[c] = p[c];
+            }
+          }
+          if (args.targets) {
+            int y = sm.ys[r * D + d];
+            y = y < 0 ? 0 : (y >= C ? C - 1 : y);
+            float mx = p[0];
+            for (int c = 1; c < C; ++c) mx = fmaxf(mx, p[c]);
+            float se = 0.f;
+            for (int c = 0; c < C; ++c) se += expf(p[c] - mx);
+            float ce = m ? (mx + logf(se) - p[y]) : 0.f;
+            unsigned pk1 = 0, pk2 = 0;
+            if (m) {
+              pk1 = (pred == y ? 1u : 0u);
+              if (C == 2) {
+                pk1 |= (pred == 1 && y == 1 ? 1u << 8 : 0u) | (pred == 0 && y == 0 ? 1u << 16 : 0u) |
+                       (pred == 1 && y == 0 ? 1u << 24 : 0u);
+                pk2 = (pred == 0 && y == 1 ? 1u : 0u);
+              }
+            }
+            ce = warp_sum(ce);
+            pk1 = warp_sum_u(pk1);
+            pk2 = warp_sum_u(pk2);
+            if ((tid & 31) == 0) {
+              atomicAdd(&sm.met[met_mat(P, 0, hist_row, d)], (double)ce);
+              atomicAdd(&sm.met[met_mat(P, 1, hist_row, d)], (double)(pk1 & 0xff));
+              atomicAdd(&sm.met[met_mat(P, 2, hist_row, d)], (double)((pk1 >> 8) & 0xff));
+              atomicAdd(&sm.met[met_mat(P, 3, hist_row, d)], (double)((pk1 >> 16) & 0xff));
+              atomicAdd(&sm.met[met_mat(P, 4, hist_row, d)], (double)((pk1 >> 24) & 0xff));
+              atomicAdd(&sm.met[met_mat(P, 5, hist_row, d)], (double)(pk2 & 0xff));
+            }
+          }
+        }
+        __syncthreads();
+      }
+    };
+    decoders_forward(0, 0, false);
+
+    // ---- walk the encoding sequence (multimodn.py:159-191) ----
+    for (int k = 1; k <= L; ++k) {
+      const int e = args.seq_enc[k - 1], pos = args.seq_pos[k - 1];
+      const DevEncoder& enc = P.enc[e];
+      const bool skip = args.skip_flags && args.skip_flags[k - 1] != 0;   // reference batch-level rule
+      for (int r = tid; r < TM; r += kThreads) sm.rownan[r] = 0;
+      __syncthreads();
+      if (!skip) {
+        Drop drop = nodrop;
+        if (TRAIN && args.training && enc.p_drop > 0.f && enc.L[0].has_state) {
+          drop.enabled = 1;
+          drop.seed_mix = args.dropout_seed ^ ((unsigned)e * 0x9E3779B9u);
+          drop.thr = (unsigned)(enc.p_drop * 16777216.f);
+          drop.row_base = (unsigned)(args.row_offset + row0);
+          drop.scale = 1.f / (1.f - enc.p_drop);
+        }
+        const float* in = nullptr;
+        int ldin = 0;
+        for (int j = 0; j < enc.n_layers; ++j) {
+          const DevLayer& ly = enc.L[j];
+          const bool last = j == enc.n_layers - 1;
+          float* out = last ? sm.T : ((j & 1) ? sm.B : sm.A);
+          const int ldo = last ? ldS : ldH;
+          ASeg segs[2];
+          int nseg = 0;
+          if (j == 0) {
+            segs[0].ptr = args.x[pos] + row0 * args.x_ld[pos];
+            segs[0].ld = args.x_ld[pos]; segs[0].width = ly.in_dim; segs[0].kind = SEG_X; segs[0].wcol = 0;
+          } else {
+            segs[0].ptr = in; segs[0].ld = ldin; segs[0].width = ly.in_dim; segs[0].kind = SEG_SMEM; segs[0].wcol = 0;
+          }
+          nseg = 1;
+          const bool use_drop = drop.enabled && j == 0;
+          if (ly.has_state) {
+            segs[1].ptr = sm.S; segs[1].ld = ldS; segs[1].width = S;
+            segs[1].kind = use_drop ? SEG_SMEM_STAGED : SEG_SMEM;
+            segs[1].wcol = ly.in_dim;
+            nseg = 2;
+          }
+          const float* __restrict__ bias = params + ly.b_off;
+          const int N = ly.out_dim, act = ly.act;
+          gemm_nt<RM>(sm, params + ly.w_off, ly.ktot, N, segs, nseg, use_drop ? drop : nodrop, rows_valid, j == 0,
+                      [&](int r, int n, float acc) {
+                        out[r * ldo + n] = n < N ? act_fwd(act, acc + __ldg(bias + n)) : 0.f;
+                      });
+          if (TRAIN && !last)
+            stash_store<RM>(slot + (long long)(stash_enc_off(P, k) + ly.stash_off) * TM, out, ldH, N);
+          in = out;
+          ldin = ldo;
+        }
+      }
+      // per-row select (missing rows keep their state bit for bit) + state-change sum (multimodn.py:174)
+      int any = 0;
+      if (tid < TM) {
+        const bool pr = !skip && tid < rows_valid && sm.rownan[tid] == 0;
+        sm.present[k * TM + tid] = pr;
+        if (pr) { atomicAdd(&sm.cnt[e + 1], 1); any = 1; }
+      }
+      any = __syncthreads_or(any);
+      if (tid == 0) sm.tile_any[k] = any;
+      if (any) {
+        float sc = 0.f;
+        for (int idx = tid; idx < TM * S; idx += kThreads) {
+          const int r = idx / S, c = idx - r * S;
+          if (sm.present[k * TM + r]) {
+            const float o = sm.S[r * ldS + c], nw = sm.T[r * ldS + c], df = nw - o;
+            sc = fmaf(df, df, sc);
+            sm.S[r * ldS + c] = nw;
+          }
+        }
+        sc = warp_sum(sc);
+        if ((tid & 31) == 0 && TRAIN) atomicAdd(&sm.met[met_sc(P, e)], (double)sc);
+      }
+      __syncthreads();
+      if (TRAIN) stash_store<RM>(slot + (long long)stash_state_off(P, k) * TM, sm.S, ldS, S);
+      decoders_forward(k, e + 1, e == E - 1);
+    }
+    if (args.final_state) {
+      for (int idx = tid; idx < rows_valid * S; idx += kThreads) {
+        const int r = idx / S, c = idx - r * S;
+        args.final_state[(row0 + r) * S + c] = sm.S[r * ldS + c];
+      }
+    }
+
+    // =============================================================================================
+    // backward: replay the sequence in reverse.  G (aliasing the state tile)
+    // holds dLoss/ds_k for the tile.
+    // =============================================================================================
+    if (TRAIN) {
+      __syncthreads();
+      float* G = sm.S;
+      float* grads = args.grads;
+      for (int idx = tid; idx < TM * ldS; idx += kThreads) G[idx] = 0.f;
+      __syncthreads();
+
+      auto decoders_backward = [&](int k) {
+        const float* sk = slot + (long long)stash_state_off(P, k) * TM;
+        for (int d = 0; d < D; ++d) {
+          const DevDecoder& dec = P.dec[d];
+          const int C = dec.C, nl = dec.n_layers;
+          const long long dbase = (long long)(stash_dec_off(P, k) + dec.stash_off) * TM;
+          // dz of the last layer from the stashed outputs p: CE-on-outputs gradient through out_act
+          {
+            const float* pst = slot + dbase + (long long)dec.L[nl - 1].stash_off * TM;
+            const int act = dec.L[nl - 1].act;
+            const int Cpad = (C + 31) & ~31;
+            if (tid < TM) {
+              const int r = tid;
+              const bool m = sm.present[k * TM + r] != 0;
+              float p[MMN_MAX_CLASSES];
+              float mx = -3.4e38f;
+              for (int c = 0; c < C; ++c) { p[c] = __ldcg(pst + r * C + c); mx = fmaxf(mx, p[c]); }
+              float se = 0.f;
+              for (int c = 0; c < C; ++c) se += expf(p[c] - mx);
+              int y = sm.ys[r * D + d];
+              y = y < 0 ? 0 : (y >= C ? C - 1 : y);
+              const float coef = m ? args.c_err : 0.f;
+              const float inv = 1.f / se;
+              for (int c = 0; c < Cpad; ++c) {
+                float v = 0.f;
+                if (c < C) v = coef * (expf(p[c] - mx) * inv - (c == y ? 1.f : 0.f)) * act_bwd(act, p[c]);
+                sm.A[r * ldH + c] = v;
+              }
+            }
+            __syncthreads();
+          }
+          float* cur = sm.A;
+          for (int j = nl - 1; j >= 0; --j) {
+            const DevLayer& ly = dec.L[j];
+            colsum_red<RM>(sm, cur, ldH, ly.out_dim, grads + ly.b_off);
+            ASeg seg;
+            seg.kind = SEG_STASH; seg.wcol = 0; seg.width = ly.in_dim; seg.ld = ly.in_dim;
+            seg.ptr = j == 0 ? sk : slot + dbase + (long long)dec.L[j - 1].stash_off * TM;
+            gemm_tn<RM>(sm, cur, ldH, ly.out_dim, seg, nodrop, TM, grads + ly.w_off, ly.ktot);
+            if (j > 0) {
+              float* other = cur == sm.A ? sm.B : sm.A;
+              const float* ast = slot + dbase + (long long)dec.L[j - 1].stash_off * TM;
+              const int J = ly.in_dim, pact = dec.L[j - 1].act;
+              gemm_nn<RM>(sm, cur, ldH, ly.out_dim, params + ly.w_off, ly.ktot, 0, J,
+                          [&](int r, int jc, float acc) {
+                            other[r * ldH + jc] = jc < J ? acc * act_bwd(pact, __ldcg(ast + r * J + jc)) : 0.f;
+                          });
+              cur = other;
+            } else {
+              gemm_nn<RM>(sm, cur, ldH, ly.out_dim, params + ly.w_off, ly.ktot, 0, S,
+                          [&](int r, int jc, float acc) {
+                            if (jc < S) G[r * ldS + jc] += acc;
+                          });
+            }
+          }
+        }
+      };
+
+      for (int k = L; k >= 1; --k) {
+        if (!sm.tile_any[k]) continue;     // no row of this tile took the step: s_k == s_{k-1}, nothing flows
+        const int e = args.seq_enc[k - 1], pos = args.seq_pos[k - 1];
+        const DevEncoder& enc = P.enc[e];
+        decoders_backward(k);
+        const float* sk = slot + (long long)stash_state_off(P, k) * TM;
+        const float* skm1 = slot + (long long)stash_state_off(P, k - 1) * TM;
+        const int nl = enc.n_layers;
+        // G += u_k ; dz_last = present ? G * act'(s_k) : 0
+        {
+          const int act = enc.L[nl - 1].act;
+          const int Spad = (S + 31) & ~31;
+          for (int idx = tid; idx < TM * Spad; idx += kThreads) {
+            const int r = idx / Spad, c = idx - r * Spad;
+            float dzv = 0.f;
+            if (c < S) {
+              const float a = __ldcg(sk + r * S + c), b = __ldcg(skm1 + r * S + c);
+              const float g = G[r * ldS + c] + args.c_sc * (a - b);
+              G[r * ldS + c] = g;
+              if (sm.present[k * TM + r]) dzv = g * act_bwd(act, a);
+            }
+            sm.T[r * ldS + c] = dzv;
+          }
+          __syncthreads();
+        }
+        Drop drop = nodrop;
+        if (args.training && enc.p_drop > 0.f && enc.L[0].has_state) {
+          drop.enabled = 1;
+          drop.seed_mix = args.dropout_seed ^ ((unsigned)e * 0x9E3779B9u);
+          drop.thr = (unsigned)(enc.p_drop * 16777216.f);
+          drop.row_base = (unsigned)(args.row_offset + row0);
+          drop.scale = 1.f / (1.f - enc.p_drop);
+        }
+        float* cur = sm.T;
+        int ldc = ldS;
+        const long long ebase = (long long)stash_enc_off(P, k) * TM;
+        for (int j = nl - 1; j >= 0; --j) {
+          const DevLayer& ly = enc.L[j];
+          const bool use_drop = drop.enabled && j == 0;
+          colsum_red<RM>(sm, cur, ldc, ly.out_dim, grads + ly.b_off);
+          ASeg seg;
+          seg.wcol = 0; seg.width = ly.in_dim;
+          if (j == 0) {
+            seg.kind = SEG_X; seg.ptr = args.x[pos] + row0 * args.x_ld[pos]; seg.ld = args.x_ld[pos];
+          } else {
+            seg.kind = SEG_STASH; seg.ptr = slot + ebase + (long long)enc.L[j - 1].stash_off * TM; seg.ld = ly.in_dim;
+          }
+          gemm_tn<RM>(sm, cur, ldc, ly.out_dim, seg, use_drop ? drop : nodrop, rows_valid, grads + ly.w_off, ly.ktot);
+          if (ly.has_state) {
+            ASeg s2;
+            s2.kind = SEG_STASH; s2.ptr = skm1; s2.ld = S; s2.width = S; s2.wcol = ly.in_dim;
+            gemm_tn<RM>(sm, cur, ldc, ly.out_dim, s2, use_drop ? drop : nodrop, TM, grads + ly.w_off, ly.ktot);
+          }
+          float* other = nullptr;
+          if (j > 0) {
+            other = cur == sm.A ? sm.B : sm.A;
+            const float* ast = slot + ebase + (long long)enc.L[j - 1].stash_off * TM;
+            const int J = ly.in_dim, pact = enc.L[j - 1].act;
+            gemm_nn<RM>(sm, cur, ldc, ly.out_dim, params + ly.w_off, ly.ktot, 0, J,
+                        [&](int r, int jc, float acc) {
+                          other[r * ldH + jc] = jc < J ? acc * act_bwd(pact, __ldcg(ast + r * J + jc)) : 0.f;
+                        });
+          }
+          if (ly.has_state) {
+            // carry into G: present rows take dz W_s (through the dropout mask), absent rows keep G;
+            // then remove u_k, which belongs to s_{k-1} with the opposite sign (multimodn.py:165,174)
+            const int in_dim = ly.in_dim;
+            gemm_nn<RM>(sm, cur, ldc, ly.out_dim, params + ly.w_off, ly.ktot, in_dim, S,
+                        [&](int r, int jc, float acc) {
+                          if (jc < S) {
+                            float carry = acc;
+                            if (use_drop)
+                              carry = mmn_dropout_keep(drop.seed_mix, drop.row_base + (unsigned)r, (unsigned)(in_dim + jc), drop.thr)
+                                          ? carry * drop.scale : 0.f;
+                            const float u = args.c_sc * (__ldcg(sk + r * S + jc) - __ldcg(skm1 + r * S + jc));
+                            const float g = sm.present[k * TM + r] ? carry : G[r * ldS + jc];
+                            G[r * ldS + jc] = g - u;
+                          }
+                        });
+          }
+          if (j > 0) { cur = other; ldc = ldH; }
+        }
+      }
+      decoders_backward(0);
+      colsum_red<RM>(sm, G, ldS, S, grads + P.init_off);      // tile backward of state.py:30
+    }
+  }
+
+  // ---- flush this CTA's metric partials ----
+  __syncthreads();
+  if (args.metrics) {
+    const int nmat = 6 * (E + 1) * D;
+    for (int i = tid; i < P.n_metrics; i += kThreads) {
+      double v;
+      if (i < (E + 1) * D) v = sm.met[i] * args.inv_rows_global;
+      else if (i < nmat) v = sm.met[i];
+      else if (i < nmat + E + 1) v = (double)sm.cnt[i - nmat];
+      else v = sm.met[i] * args.inv_rows_global / (double)S;
+      if (v != 0.0) atomicAdd(args.metrics + i, v);
+    }
+  }
+  if (TRAIN && args.grads) {
+    for (int e = tid; e < E; e += kThreads)
+      if (sm.cnt[e + 1]) atomicAdd(args.grads + P.n_params + e, (float)sm.cnt[e + 1]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// any(isnan) per modality tensor — the reference's batch-level missingness test (multimodn.py:168)
+// ------------------------------------------------------------------------------------------------
+struct ScanArgs {
+  int seq_len;
+  long long n_rows;
+  int F[MMN_MAX_ENCODERS];
+  const float* x[MMN_MAX_ENCODERS];
+  long long x_ld[MMN_MAX_ENCODERS];
+  int* flags;
+};
+__global__ void __launch_bounds__(256) mmn_scan_missing_kernel(const ScanArgs a) {
+  for (int k = 0; k < a.seq_len; ++k) {
+    const long long n = a.n_rows * a.F[k];
+    int found = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      const long long r = i / a.F[k];
+      const float v = __ldg(a.x[k] + r * a.x_ld[k] + (i - r * a.F[k]));
+      if (v != v) found = 1;
+    }
+    if (__syncthreads_or(found) && threadIdx.x == 0) a.flags[k] = 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam on the packed buffers (torch.optim.Adam defaults; multimodn.py:204)
+// ------------------------------------------------------------------------------------------------
+__global__ void mmn_adam_tick_kernel(const DevPlan* plan, const float* grads, int* step_count) {
+  const int i = threadIdx.x;
+  if (i == 0) step_count[0] += 1;
+  if (i >= 1 && i <= plan->E && grads[plan->n_params + (i - 1)] > 0.f) step_count[i] += 1;
+}
+__global__ void __launch_bounds__(256) mmn_adam_kernel(const DevPlan* plan, float* params, const float* grads,
+                                                        float* m, float* v, const int* step_count, float lr,
+                                                        float b1, float b2, float eps) {
+  const DevPlan& P = *plan;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n_params;
+       i += (long long)gridDim.x * blockDim.x) {
+    int owner = 0;
+    for (int e = 0; e < P.E; ++e)
+      if (i >= P.enc[e].param_lo && i < P.enc[e].param_hi) owner = e + 1;
+    if (owner && !(grads[P.n_params + owner - 1] > 0.f)) continue;    // `.grad is None`: untouched
+    const int t = step_count[owner];
+    const float g = grads[i];
+    const float mi = m[i] + (g - m[i]) * (1.f - b1);
+    const float vi = v[i] * b2 + g * g * (1.f - b2);
+    m[i] = mi;
+    v[i] = vi;
+    const double bc1 = 1.0 - pow((double)b1, (double)t), bc2 = 1.0 - pow((double)b2, (double)t);
+    const float step_size = (float)((double)lr / bc1);
+    const float denom = sqrtf(vi) / (float)sqrt(bc2) + eps;
+    params[i] = params[i] - step_size * (mi / denom);
+  }
+}
+
+}  // namespace mmn

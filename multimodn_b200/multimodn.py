@@ -1,0 +1,461 @@
+"""MultiModN — drop-in driver of the sequential-fusion step on B200 (reference:
+multimodn/multimodn.py:65-531).
+
+Same constructor, same ``train_epoch`` / ``test`` / ``predict`` / ``get_states`` signatures, same
+history matrices; underneath, each batch is ONE launch of the fused sm_100a kernel in libmmn.so
+(include/mmn.h) instead of the reference's Python loop nest over encoders and decoders.
+
+Deliberate, documented deviations from the reference:
+  * ``missing_mode="row"`` (default): a NaN marks the modality missing for THAT ROW (per-row
+    select) — the reference evaluated at batch size 1.  ``missing_mode="batch"`` reproduces the
+    reference rule (one NaN skips the encoder for the whole batch, multimodn.py:167-169).
+  * ``predict`` skips missing rows like ``test`` does (the reference propagates NaN, :449), and
+    accepts numpy / list sequences (the reference needs a tensor, :518).
+  * ``test`` collects, for every row, the decoder outputs at the step of encoder id E-1
+    (the reference drops rows of skipped batches and mis-aligns them with the targets, :354-357).
+  * an encoder id may appear at most once in an encoding sequence.
+Everything else — 0.01 factor (:86), fixed D(E+1) and E divisors (:194-196), ``np.ones``
+sample counters (:105,:270), unweighted batch mean (:222), CE on squashed outputs, first-max
+arg-max, rows indexed by encoder id + 1, ``.grad is None`` for skipped encoders — is kept.
+
+There is no CPU path: a non-CUDA device, a missing library, an unsupported module or criterion
+raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import random
+from typing import Callable, Iterable, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch import Tensor
+from torch.optim import Optimizer
+from torch.utils.data import DataLoader
+
+from . import _lib
+from .decoders.multimod_decoder import MultiModDecoder
+from .encoders.multimod_encoder import MultiModEncoder
+from .history import MultiModNHistory
+from .metrics import get_performance_metrics, performance_metrics  # noqa: F401  (re-exported like the reference)
+from .plan import PackedModel
+from .state import InitState, TrainableInitState
+
+
+def _check_criterion(criterion):
+    """Only the criterion every reference pipeline uses is fused: default CrossEntropyLoss
+    (pipelines/titanic/titanic_mlp_pipeline.py:76)."""
+    ok = (isinstance(criterion, nn.CrossEntropyLoss) and criterion.weight is None
+          and criterion.reduction == "mean" and criterion.ignore_index == -100
+          and getattr(criterion, "label_smoothing", 0.0) == 0.0)
+    if not ok:
+        raise NotImplementedError("the fused step implements torch.nn.CrossEntropyLoss() with default "
+                                  f"arguments only, got {criterion!r}")
+
+
+class _Runtime:
+    """Everything that lives next to the model on the device: plan handle, packed parameters and
+    gradients, workspace, metric buffers."""
+
+    def __init__(self, model: "MultiModN"):
+        self.lib = model._lib_factory()
+        self.device = model.device
+        if self.device.type != "cuda" and not self.lib.host_memory:
+            raise RuntimeError(f"multimodn_b200 runs on CUDA devices only (got device '{self.device}'); "
+                               "there is no CPU path")
+        if not isinstance(model.init_state, TrainableInitState):
+            raise NotImplementedError("the fused step supports TrainableInitState only")
+        self.S = int(model.init_state.state_size)
+        self.packed = PackedModel(model.init_state.state_value, model.encoders, model.decoders, self.S)
+        self.E, self.D = len(self.packed.encoders), len(self.packed.decoders)
+        self.flat = self.packed.pack(self.device)
+        desc, self._keep = self.packed.model_desc()
+        handle = C.c_void_p()
+        self.lib.check(self.lib.dll.mmn_plan_create(C.byref(desc), C.byref(handle)))
+        self.plan = handle
+        self.n_metrics = int(self.lib.dll.mmn_metrics_count(self.plan))
+        self.n_grads = int(self.lib.dll.mmn_grad_count(self.plan))
+        self.gflat = torch.zeros(self.n_grads, dtype=torch.float32, device=self.device)
+        self.sumC = sum(m.n_classes for m in self.packed.decoders)
+        self._ws = None
+        self._flags = torch.zeros(max(self.E, 1), dtype=torch.int32, device=self.device)
+        self.step_counter = 0
+        self.dropout_base_seed = int(torch.initial_seed() & 0x7FFFFFFF)
+
+    def __del__(self):
+        try:
+            if getattr(self, "plan", None):
+                self.lib.dll.mmn_plan_destroy(self.plan)
+                self.plan = None
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def ensure_packed(self):
+        if not self.packed.is_packed(self.flat):
+            self.flat = self.packed.pack(self.device)
+
+    def new_metrics(self) -> Tensor:
+        return torch.zeros(self.n_metrics, dtype=torch.float64, device=self.device)
+
+    def workspace(self, n_rows: int, train: bool):
+        need = int(self.lib.dll.mmn_workspace_bytes(self.plan, n_rows, 1 if train else 0))
+        if need < 0:
+            raise _lib.MMNError("mmn_workspace_bytes failed")
+        if need == 0:
+            return None, 0
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws, need
+
+    def stream(self):
+        if self.device.type == "cuda":
+            return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return C.c_void_p(0)
+
+    def prepare_batch(self, data: List[Tensor], target: Optional[Tensor], seq: List[Tuple[int, int]],
+                      missing_mode: str, dp):
+        """multimodn.py:132-135: move to the device; then fill mmn_batch."""
+        if len(seq) > self.E:
+            raise ValueError(f"encoding sequence has {len(seq)} steps, the model has {self.E} encoders")
+        enc_ids = [e for _, e in seq]
+        if len(set(enc_ids)) != len(enc_ids):
+            raise ValueError("an encoder id may appear at most once in an encoding sequence")
+        xs = []
+        for t in data:
+            t = torch.as_tensor(t)
+            t = t.to(device=self.device, dtype=torch.float32, non_blocking=True)
+            if t.dim() != 2:
+                raise ValueError(f"modality tensors must be (batch, features), got {tuple(t.shape)}")
+            if t.stride(1) != 1 or t.stride(0) < t.shape[1]:
+                t = t.contiguous()
+            xs.append(t)
+        n_rows = xs[0].shape[0] if xs else int(target.shape[0])
+        for pos, e in seq:
+            if not 0 <= e < self.E:
+                raise ValueError(f"encoder id {e} out of range")
+            if not 0 <= pos < len(xs):
+                raise ValueError(f"encoding sequence position {pos} has no data tensor")
+            if xs[pos].shape[1] != self.packed.encoders[e].n_features or xs[pos].shape[0] != n_rows:
+                raise ValueError(f"data[{pos}] has shape {tuple(xs[pos].shape)}, encoder {e} expects "
+                                 f"({n_rows}, {self.packed.encoders[e].n_features})")
+        tgt = None
+        if target is not None:
+            tgt = torch.as_tensor(target).to(device=self.device, dtype=torch.int64, non_blocking=True)   # :134-135
+            if tgt.dim() != 2 or tgt.shape[1] != self.D or tgt.shape[0] != n_rows:
+                raise ValueError(f"target must be ({n_rows}, {self.D}), got {tuple(tgt.shape)}")
+            tgt = tgt.contiguous()
+        npos = max(len(xs), 1)
+        seq_pos = (C.c_int32 * max(len(seq), 1))(*[p for p, _ in seq])
+        seq_enc = (C.c_int32 * max(len(seq), 1))(*enc_ids)
+        xptr = (C.c_void_p * npos)(*[t.data_ptr() for t in xs])
+        xld = (C.c_int64 * npos)(*[t.stride(0) for t in xs])
+        world, rank, group = dp if dp else (1, 0, None)
+        b = _lib.Batch()
+        b.n_rows, b.n_rows_global, b.row_offset = n_rows, n_rows * world, rank * n_rows
+        b.seq_len = len(seq)
+        b.seq_pos = C.cast(seq_pos, C.POINTER(C.c_int32))
+        b.seq_enc = C.cast(seq_enc, C.POINTER(C.c_int32))
+        b.x = C.cast(xptr, C.POINTER(C.c_void_p))
+        b.x_ld = C.cast(xld, C.POINTER(C.c_int64))
+        b.targets = tgt.data_ptr() if tgt is not None else None
+        b.skip_flags = None
+        keep = (xs, tgt, seq_pos, seq_enc, xptr, xld)
+        if missing_mode == "batch" and len(seq):
+            self.lib.check(self.lib.dll.mmn_scan_missing(self.plan, C.byref(b), self._flags.data_ptr(), self.stream()))
+            if group is not None or world > 1:
+                torch.distributed.all_reduce(self._flags, op=torch.distributed.ReduceOp.MAX, group=group)
+            b.skip_flags = self._flags.data_ptr()
+        elif missing_mode != "row" and missing_mode != "batch":
+            raise ValueError(f"missing_mode must be 'row' or 'batch', got {missing_mode!r}")
+        return b, keep, n_rows
+
+    def outputs(self, metrics=None, predictions=None, last_outputs=None, final_state=None):
+        o = _lib.Outputs()
+        o.metrics = metrics.data_ptr() if metrics is not None else None
+        o.predictions = predictions.data_ptr() if predictions is not None else None
+        o.pred_ld = predictions.shape[-1] if predictions is not None else 0
+        o.last_outputs = last_outputs.data_ptr() if last_outputs is not None else None
+        o.final_state = final_state.data_ptr() if final_state is not None else None
+        return o
+
+    def forward(self, batch, n_rows, **outs):
+        self.ensure_packed()
+        o = self.outputs(**outs)
+        self.lib.check(self.lib.dll.mmn_forward(self.plan, C.byref(batch), self.flat.data_ptr(), C.byref(o), None, 0,
+                                                self.stream()))
+
+    def train_step(self, batch, n_rows, err_penalty, scp_scaled, training, metrics):
+        self.ensure_packed()
+        ws, ws_bytes = self.workspace(n_rows, True)
+        self.step_counter += 1
+        seed = (self.dropout_base_seed * 0x9E3779B1 + self.step_counter * 0x85EBCA77) & 0xFFFFFFFF
+        targs = _lib.TrainArgs(err_penalty, scp_scaled, seed, 1 if training else 0)
+        o = self.outputs(metrics=metrics)
+        self.lib.check(self.lib.dll.mmn_train_step(self.plan, C.byref(batch), self.flat.data_ptr(), C.byref(targs),
+                                                   C.byref(o), self.gflat.data_ptr(), ws.data_ptr(), ws_bytes,
+                                                   self.stream()))
+        return seed
+
+    def assign_grads(self):
+        """loss.backward() epilogue (multimodn.py:203): hand each parameter a view of the packed
+        gradient; an encoder that took no row keeps ``.grad = None`` (multimodn.py:168-169)."""
+        touched = self.gflat[self.packed.n_params:].tolist()        # E floats (one small D2H)
+        for p, off, owner in self.packed.slots:
+            if owner >= 0 and touched[owner] <= 0:
+                p.grad = None
+            else:
+                p.grad = self.gflat[off:off + p.numel()].view(p.shape)
+
+    # ------------------------------------------------------------------------------------------
+    def split_metrics(self, host: np.ndarray):
+        E, D = self.E, self.D
+        n = (E + 1) * D
+        mats = [host[i * n:(i + 1) * n].reshape(E + 1, D).copy() for i in range(6)]
+        n_present = host[6 * n:6 * n + E + 1].copy()
+        sc = host[6 * n + E + 1:6 * n + 2 * E + 1].copy()
+        return mats, n_present, sc
+
+
+class MultiModN(nn.Module):
+    _lib_factory = staticmethod(_lib.get_lib)
+
+    def __init__(
+            self,
+            state_size: int,
+            encoders: List[MultiModEncoder],
+            decoders: List[MultiModDecoder],
+            err_penalty: float,
+            state_change_penalty: float,
+            shuffle_mode: Optional[bool] = False,
+            init_state: Optional[InitState] = None,
+            device: Optional[torch.device] = None,
+            missing_mode: str = "row",
+    ):
+        super().__init__()
+        self.shuffle_mode = shuffle_mode
+        self.device = torch.device(device) if device else torch.device(
+            "cuda" if torch.cuda.is_available() else "cpu")
+        self.init_state = TrainableInitState(state_size, self.device) if not init_state else init_state
+        self.encoders = nn.ModuleList(encoders)
+        self.decoders = nn.ModuleList(decoders)
+        self.err_penalty = err_penalty
+        self.state_change_penalty = 0.01 * state_change_penalty      # multimodn.py:86
+        if missing_mode not in ("row", "batch"):
+            raise ValueError(f"missing_mode must be 'row' or 'batch', got {missing_mode!r}")
+        self.missing_mode = missing_mode
+        self.to(self.device)
+        self._rt: Optional[_Runtime] = None
+        self._dp = None                 # (world, rank, group) once data parallelism is enabled
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_rt"] = None             # plan handles and packed buffers are rebuilt on demand
+        state["_dp"] = None
+        return state
+
+    def runtime(self) -> _Runtime:
+        if self._rt is None:
+            self._rt = _Runtime(self)
+        return self._rt
+
+    def enable_data_parallel(self, group=None):
+        """Shard every batch by rows over the ranks of ``group`` (one process per GPU): the loader
+        of rank r yields its own rows; gradients (and the epoch's metric sums) are all-reduced over
+        NCCL.  Parameters must start identical on every rank (same seed)."""
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self._dp = (dist.get_world_size(group), dist.get_rank(group), group)
+        rt = self.runtime()
+        rt.ensure_packed()
+        dist.broadcast(rt.flat, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        return self
+
+    def _allreduce(self, tensor):
+        if self._dp and self._dp[0] > 1:
+            torch.distributed.all_reduce(tensor, group=self._dp[2])
+
+    # -- the encoding sequence (multimodn.py:509-531) --------------------------------------------
+    def get_encoder_iterable(self, encoder_sequence, shuffle_mode: bool, train: bool) -> List[Tuple[int, int]]:
+        if encoder_sequence is None:
+            pairs = list(enumerate(range(len(self.encoders))))
+        else:
+            seq = encoder_sequence.detach().cpu().numpy() if torch.is_tensor(encoder_sequence) \
+                else np.asarray(encoder_sequence)
+            if seq.ndim == 2:
+                if not (seq == seq[0]).all():
+                    raise ValueError("Encoder sequence has different values across the batch. "
+                                     "Hint: set batch size to 1 to avoid this error.")
+                seq = seq[0]
+            elif seq.ndim != 1:
+                raise ValueError("encoder_sequence must be (batch, steps) or (steps,)")
+            pairs = [(i, int(e)) for i, e in enumerate(seq)]
+        if shuffle_mode and train:
+            random.shuffle(pairs)                                   # multimodn.py:527-529
+        return pairs
+
+    # -- epoch bookkeeping (multimodn.py:222-250, 367-409) ---------------------------------------
+    def _finalize(self, rt: _Runtime, metrics: Tensor, n_batches: int):
+        self._allreduce(metrics)
+        mats, n_present, sc = rt.split_metrics(metrics.cpu().numpy())
+        ce, n_correct, tp, tn, fp, fn = mats
+        n_samples = np.ones((rt.E + 1, 1)) + n_present.reshape(-1, 1)      # starts at ONE (:105,:270)
+        nb = max(n_batches, 1)
+        for d, dec in enumerate(rt.packed.decoders):
+            if dec.n_classes != 2:                                         # :60-63: NaN cells once visited
+                for m in (tp, tn, fp, fn):
+                    m[:, d] = np.where(n_present > 0, np.nan, 0.0)
+        tp32, tn32, fp32, fn32 = (m.astype(np.float32) for m in (tp, tn, fp, fn))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            sens = np.where(tp32 + fn32 == 0, np.float32(0), tp32 / (tp32 + fn32))     # :234-236
+            spec = np.where(tn32 + fp32 == 0, np.float32(0), tn32 / (tn32 + fp32))     # :238-240
+        return dict(loss=ce / nb, accuracy=n_correct / n_samples, sensitivity=sens, specificity=spec,
+                    balanced_accuracy=(sens + spec) / 2, state_change=sc / nb)
+
+    # -- training (multimodn.py:89-252) ----------------------------------------------------------
+    def train_epoch(
+            self,
+            train_loader: DataLoader,
+            optimizer: Optimizer,
+            criterion: Union[nn.Module, Callable],
+            history: Optional[MultiModNHistory] = None,
+            log_interval: Optional[int] = None,
+            logger: Optional[Callable] = None,
+            last_epoch: Optional[bool] = False,
+    ):
+        if log_interval and not logger:
+            logger = print
+        _check_criterion(criterion)
+        self.train()
+        rt = self.runtime()
+        fused_opt = getattr(optimizer, "_mmn_fused", False)
+        n_batches = len(train_loader)
+        epoch_metrics = rt.new_metrics()
+        batch_metrics = rt.new_metrics() if log_interval else None
+        E, D = rt.E, rt.D
+
+        for batch_idx, batch in enumerate(train_loader):
+            data, target, encoder_sequence = (list(batch) + [None])[:3]
+            seq = self.get_encoder_iterable(encoder_sequence, shuffle_mode=self.shuffle_mode, train=True)
+            optimizer.zero_grad()
+            mb, keep, n_rows = rt.prepare_batch(list(data), target, seq, self.missing_mode, self._dp)
+            if batch_metrics is not None:
+                batch_metrics.zero_()
+            rt.train_step(mb, n_rows, float(self.err_penalty), float(self.state_change_penalty), True,
+                          batch_metrics if batch_metrics is not None else epoch_metrics)
+            self._allreduce(rt.gflat)
+            if fused_opt:
+                optimizer.step()                # reads the packed gradient on the device: no host sync
+            else:
+                rt.assign_grads()
+                optimizer.step()
+            del keep
+            if batch_metrics is not None:
+                epoch_metrics += batch_metrics
+                if batch_idx % log_interval == log_interval - 1:
+                    bm = batch_metrics.clone()
+                    self._allreduce(bm)
+                    mats, _, sc = rt.split_metrics(bm.cpu().numpy())
+                    err = mats[0].sum() / (D * (E + 1))                      # :194-196
+                    chg = sc.sum() / E
+                    loss = err * self.err_penalty + chg * self.state_change_penalty
+                    logger(f"Batch {batch_idx + 1}/{n_batches}\n"
+                           f"\tLoss: {loss:.4f}\n"
+                           f"\tErr loss: {err:.4f}\n"
+                           f"\tState change: {chg:.4f}")
+
+        if history is not None:
+            fin = self._finalize(rt, epoch_metrics, n_batches)
+            history.state_change_loss.append(fin["state_change"])
+            history.append("train", fin)
+        if last_epoch:
+            return self.test(train_loader, criterion, history=None)
+
+    # -- evaluation (multimodn.py:255-419) -------------------------------------------------------
+    def test(
+            self,
+            test_loader: DataLoader,
+            criterion: Union[nn.Module, Callable],
+            history: Optional[MultiModNHistory] = None,
+            tag: str = 'test',
+            log_results: bool = False,
+            logger: Optional[Callable] = None,
+    ):
+        if log_results and not logger:
+            logger = print
+        _check_criterion(criterion)
+        self.eval()
+        rt = self.runtime()
+        n_batches = len(test_loader)
+        metrics = rt.new_metrics()
+        outs, tgts = [], []
+        for batch in test_loader:
+            data, target, encoder_sequence = (list(batch) + [None])[:3]
+            seq = self.get_encoder_iterable(encoder_sequence, shuffle_mode=self.shuffle_mode, train=False)
+            mb, keep, n_rows = rt.prepare_batch(list(data), target, seq, self.missing_mode, self._dp)
+            last = torch.zeros((n_rows, rt.sumC), dtype=torch.float32, device=rt.device)
+            rt.forward(mb, n_rows, metrics=metrics, last_outputs=last)
+            outs.append(last)
+            tgts.append(keep[1])
+            del keep
+        fin = self._finalize(rt, metrics, n_batches)
+        if log_results:
+            logger(f"{tag.capitalize()} results\n"
+                   f"\tAverage loss: {np.mean(fin['loss']):.4f}\n"
+                   f"\tAccuracy: {np.mean(fin['accuracy']):.4f}\n"
+                   f"\tSensitivity: {np.nanmean(fin['sensitivity']):.4f}\n"
+                   f"\tSpecificity: {np.nanmean(fin['specificity']):.4f}\n"
+                   f"\tBalanced accuracy: {np.nanmean(fin['balanced_accuracy']):.4f}")
+        if history is not None:
+            history.append(tag, fin)
+        # end-of-test metric suite on the last-encoder outputs (multimodn.py:411-419)
+        results = [[] for _ in range(rt.D)]
+        if outs:
+            out_all = torch.cat(outs).cpu()
+            tgt_all = torch.cat(tgts).cpu()
+            col = 0
+            for d, dec in enumerate(rt.packed.decoders):
+                o = out_all[:, col:col + dec.n_classes]
+                col += dec.n_classes
+                o = o / o.sum(dim=1, keepdim=True)                          # :415
+                pred = torch.max(o, dim=1)[1]                               # :416
+                results[d] = get_performance_metrics(tgt_all[:, d], pred, o[:, 1] if dec.n_classes > 1 else o[:, 0])
+        return results
+
+    # -- inference (multimodn.py:422-458) --------------------------------------------------------
+    def predict(self, x: List[Tensor], encoder_sequence=None) -> np.ndarray:
+        self.eval()
+        rt = self.runtime()
+        seq = self.get_encoder_iterable(encoder_sequence, shuffle_mode=self.shuffle_mode, train=False)
+        mb, keep, n_rows = rt.prepare_batch(list(x), None, seq, self.missing_mode, None)
+        preds = torch.zeros((rt.E + 1, rt.D, n_rows), dtype=torch.uint8, device=rt.device)
+        rt.forward(mb, n_rows, predictions=preds)
+        del keep
+        return preds.cpu().numpy().astype(np.float64)
+
+    def get_states(self, data_loader: DataLoader) -> List[Tensor]:
+        """multimodn.py:460-492"""
+        self.eval()
+        rt = self.runtime()
+        states = []
+        for batch in data_loader:
+            data, _, encoder_sequence = (list(batch) + [None])[:3]
+            seq = self.get_encoder_iterable(encoder_sequence, shuffle_mode=self.shuffle_mode, train=False)
+            mb, keep, n_rows = rt.prepare_batch(list(data), None, seq, self.missing_mode, None)
+            st = torch.empty((n_rows, rt.S), dtype=torch.float32, device=rt.device)
+            rt.forward(mb, n_rows, final_state=st)
+            states.append(st)
+            del keep
+        return list(torch.cat(states, dim=0))
+
+    def display_arch(self, input: Optional[np.ndarray] = None):
+        """multimodn.py:494-507 (torchsummary is optional here: the lowered plan is printed)."""
+        rt = self.runtime()
+        for name, mods in (("Encoder", rt.packed.encoders), ("Decoder", rt.packed.decoders)):
+            for i, m in enumerate(mods):
+                print(f"{name} {i}: " + " -> ".join(
+                    f"Linear({l.in_dim}{'+S' if l.has_state else ''}, {l.out_dim}){'/' + l.act if l.act != 'identity' else ''}"
+                    for l in m.layers))

@@ -8,3 +8,17 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+import pytest  # noqa: E402
+
+
+@pytest.fixture
+def emu(monkeypatch):
+    """Route MultiModN through the host-compiled kernel emulator (tests/emu) — CPU tests only."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    from emu_backend import get_emu_lib
+    from multimodn_b200 import MultiModN
+    lib = get_emu_lib()
+    monkeypatch.setattr(MultiModN, "_lib_factory", staticmethod(lambda: lib))
+    return lib
