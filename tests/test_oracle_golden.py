@@ -174,3 +174,21 @@ def test_dropout_fixed_mask():
     check_history(fx, "val", epoch(spec, data, y, len(y)), rtol=1e-5)       # eval: no dropout
     keep = O.dropout_keep(seed, 0, np.arange(4096), 64, 0.25)
     assert abs(keep.mean() - 0.75) < 0.01
+
+
+def test_torch_port_matches_oracle():
+    """the CPU-baseline port (oracle/torch_port.py, timed by bench.py) computes the same step"""
+    import torch
+    from oracle.torch_port import TorchPort
+    from oracle.spec_io import random_spec, synthetic_batch
+    rng = np.random.default_rng(11)
+    feats = [6, 19, 40]
+    spec = random_spec(rng, 16, feats, enc_hidden=(8, 8), n_decoders=2, dec_hidden=(8, 8))
+    data, y = synthetic_batch(rng, feats, 2, 96, mnar=True)
+    fwd, loss, grads, touched = O.train_step(O.cast_spec(spec, np.float32), data, y, 1.0, 0.003, missing_mode="row")
+    port = TorchPort(spec, 1.0, 0.003)
+    ploss, ce, sc, pg = port.grads([torch.from_numpy(x) for x in data], torch.from_numpy(y))
+    assert abs(ploss - loss) <= 1e-5 * abs(loss)
+    assert_close(ce, fwd["ce"], rtol=1e-5, what="ce")
+    assert_close(sc, fwd["state_change"], rtol=1e-5, what="sc")
+    assert_close(np.concatenate([g.ravel() for g in pg]), flat_grads(grads), rtol=1e-5, what="grads")
