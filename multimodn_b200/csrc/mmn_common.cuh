@@ -96,8 +96,8 @@ struct StepArgs {
 // shared-memory footprint of the step kernel for a row tile of 32*RM rows
 inline size_t step_smem_bytes(const DevPlan& p, int RM, bool train) {
   const size_t TM = 32 * (size_t)RM;
-  size_t f = 2 * TM * p.ldS + 2 * TM * p.ldH + TM * LDX + 32 * LDX;   // S/G, T, A, B, XB, WB
-  f += kGroups * 1024;                                                // RED scratch (also column sums)
+  size_t f = 2 * TM * p.ldS + 2 * TM * p.ldH + 2 * (TM * LDX + 32 * LDX);   // S/G, T, A, B, 2x(XB, WB)
+  f += 2 * kGroups * 1024;                                                  // 2x RED scratch (also column sums)
   size_t bytes = f * 4;
   bytes += TM * p.D * 4;                 // targets tile
   bytes += TM * 4;                       // row NaN flags

@@ -52,12 +52,17 @@ __device__ __forceinline__ float act_bwd(int act, float out) {
   }
 }
 
-// dropout keep decision: counter-based hash of (seed, encoder, global row, column).  The oracle
-// (oracle/multimodn_oracle.py: dropout_keep) computes the same bits.
-__device__ __forceinline__ bool mmn_dropout_keep(unsigned seed_mix, unsigned row, unsigned col, unsigned thr) {
-  unsigned x = row * 0x85EBCA6Bu + col * 0xC2B2AE35u + seed_mix;
+// dropout keep decision: counter-based hash of (seed, encoder, global row, column pair); one 32-bit
+// hash serves two adjacent columns (16 bits each).  The oracle (oracle/multimodn_oracle.py:
+// dropout_keep) computes the same bits.
+__device__ __forceinline__ unsigned mmn_dropout_hash(unsigned seed_mix, unsigned row, unsigned colpair) {
+  unsigned x = row * 0x85EBCA6Bu + colpair * 0xC2B2AE35u + seed_mix;
   x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
-  return (x >> 8) >= thr;
+  return x;
+}
+__device__ __forceinline__ bool mmn_dropout_keep(unsigned seed_mix, unsigned row, unsigned col, unsigned thr16) {
+  const unsigned h = mmn_dropout_hash(seed_mix, row, col >> 1);
+  return ((col & 1u) ? (h >> 16) : (h & 0xffffu)) >= thr16;
 }
 
 struct Drop {
@@ -67,7 +72,7 @@ struct Drop {
 };
 
 struct Smem {
-  float *S, *T, *A, *B, *XB, *WB, *RED;
+  float *S, *T, *A, *B, *XB, *WB, *RED;   // XB, WB, RED are double-buffered
   int* ys;
   int* rownan;
   int* cnt;          // [E+1] present rows per history row, summed over this CTA's tiles
@@ -85,137 +90,269 @@ struct ASeg {
   int kind;
   int wcol;           // first weight column this segment multiplies (== its column in [a || state])
 };
+__device__ __forceinline__ bool seg_vec_ok(const ASeg& sg) {
+  return (sg.kind == SEG_X || sg.kind == SEG_STASH) && ((sg.ld & 3) == 0) && ((sg.width & 3) == 0) &&
+         ((reinterpret_cast<size_t>(sg.ptr) & 15) == 0);
+}
 
 template <int RM>
 struct Cfg {
   static constexpr int TM = 32 * RM;
 };
 
-// 32x32 block of a row-major weight matrix -> WB[32][LDX], zero-filled outside (nrows, ncols)
-__device__ __forceinline__ void stage_w_block(float* WB, const float* __restrict__ W, int ldw, int row0,
-                                              int nrows, int col0, int ncols) {
-  const int t = threadIdx.x, c = t & 31, r0 = t >> 5;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = r0 + 8 * i;
-    float v = 0.f;
-    if (r < nrows && c < ncols) v = __ldg(W + (long long)(row0 + r) * ldw + col0 + c);
-    WB[r * LDX + c] = v;
-  }
+// ---- 32x32 block of a row-major weight matrix -> WB[32][LDX], zero-filled outside (nrows, ncols).
+// Split in a load half (global -> registers, issued early) and a store half (registers -> smem).
+__device__ __forceinline__ bool w_vec_ok(const float* W, int ldw, int col0) {
+  return ((ldw & 3) == 0) && ((col0 & 3) == 0) && ((reinterpret_cast<size_t>(W) & 15) == 0);
 }
-
-// TM x 32 chunk of an activation source -> XB[TM][LDX]; zero-fill, NaN scan + sanitise for x,
-// dropout mask when enabled.
-template <int RM>
-__device__ __forceinline__ void stage_a_chunk(const Smem& sm, const ASeg& sg, int k0, int kw, int rows_valid,
-                                              const Drop& drop, bool scan_nan) {
-  const int t = threadIdx.x, c = t & 31, r0 = t >> 5;
-#pragma unroll 4
-  for (int i = 0; i < 4 * RM; ++i) {
-    const int r = r0 + 8 * i;
-    float v = 0.f;
-    if (c < kw) {
-      if (sg.kind == SEG_SMEM_STAGED) {
-        v = sg.ptr[(long long)r * sg.ld + k0 + c];
-      } else if (r < rows_valid) {
-        const float* p = sg.ptr + (long long)r * sg.ld + k0 + c;
-        if (sg.kind == SEG_X) {
-          v = __ldg(p);
-          if (v != v) {                 // NaN marks the modality missing for this row
-            if (scan_nan) sm.rownan[r] = 1;
-            v = 0.f;                    // never let it reach arithmetic (0 * NaN = NaN)
-          }
-        } else {
-          v = __ldcg(p);                // stash written earlier by this CTA: L2-coherent load
-        }
-      }
-      if (drop.enabled) {
-        v = mmn_dropout_keep(drop.seed_mix, drop.row_base + (unsigned)r, (unsigned)(sg.wcol + k0 + c), drop.thr)
-                ? v * drop.scale : 0.f;
+__device__ __forceinline__ void w_block_load(float (&w)[4], const float* __restrict__ W, int ldw, int row0,
+                                             int nrows, int col0, int ncols, bool vec) {
+  const int t = threadIdx.x;
+  if (vec) {
+    const int c4 = (t & 7) * 4, r = t >> 3;
+    w[0] = w[1] = w[2] = w[3] = 0.f;
+    if (r < nrows) {
+      const float* p = W + (long long)(row0 + r) * ldw + col0 + c4;
+      if (c4 + 3 < ncols) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+        w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (c4 + u < ncols) w[u] = __ldg(p + u);
       }
     }
-    sm.XB[r * LDX + c] = v;
+  } else {
+    const int c = t & 31, r0 = t >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + 8 * i;
+      w[i] = (r < nrows && c < ncols) ? __ldg(W + (long long)(row0 + r) * ldw + col0 + c) : 0.f;
+    }
+  }
+}
+__device__ __forceinline__ void w_block_store(float* WB, const float (&w)[4], bool vec) {
+  const int t = threadIdx.x;
+  if (vec) {
+    *reinterpret_cast<float4*>(WB + (t >> 3) * LDX + (t & 7) * 4) = make_float4(w[0], w[1], w[2], w[3]);
+  } else {
+    const int c = t & 31, r0 = t >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) WB[(r0 + 8 * i) * LDX + c] = w[i];
   }
 }
 
+// ---- TM x 32 chunk of an activation source -> XB[TM][LDX]: zero-fill, NaN scan + sanitise for x,
+// dropout mask when enabled.  Load half: 4*RM values per thread in flight (LDG.128 when aligned).
+template <int RM>
+__device__ __forceinline__ void a_chunk_load(float (&v)[4 * RM], const ASeg& sg, int k0, int kw, int rows_valid,
+                                             bool vec) {
+  if (sg.kind != SEG_X && sg.kind != SEG_STASH) return;
+  const int t = threadIdx.x;
+  if (vec) {
+    const int c4 = (t & 7) * 4, r0 = t >> 3;
+#pragma unroll
+    for (int i = 0; i < RM; ++i) {
+      const int r = r0 + 32 * i;
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < rows_valid && c4 < kw) {
+        const float4* p = reinterpret_cast<const float4*>(sg.ptr + (long long)r * sg.ld + k0 + c4);
+        q = sg.kind == SEG_X ? __ldg(p) : __ldcg(p);
+      }
+      v[4 * i + 0] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+    }
+  } else {
+    const int c = t & 31, r0 = t >> 5;
+#pragma unroll
+    for (int i = 0; i < 4 * RM; ++i) {
+      const int r = r0 + 8 * i;
+      float x = 0.f;
+      if (r < rows_valid && c < kw) {
+        const float* p = sg.ptr + (long long)r * sg.ld + k0 + c;
+        x = sg.kind == SEG_X ? __ldg(p) : __ldcg(p);   // stash: written earlier by this CTA, L2-coherent load
+      }
+      v[i] = x;
+    }
+  }
+}
+template <int RM>
+__device__ __forceinline__ void a_chunk_store(float* XB, float (&v)[4 * RM], const Smem& sm, const ASeg& sg, int k0,
+                                              int kw, const Drop& drop, bool scan_nan, bool vec) {
+  const int t = threadIdx.x;
+  if (vec) {
+    const int c4 = (t & 7) * 4, r0 = t >> 3;
+#pragma unroll
+    for (int i = 0; i < RM; ++i) {
+      const int r = r0 + 32 * i;
+      if (sg.kind == SEG_X) {
+        bool bad = false;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (v[4 * i + u] != v[4 * i + u]) { bad = true; v[4 * i + u] = 0.f; }   // never let NaN reach arithmetic
+        if (bad && scan_nan) sm.rownan[r] = 1;              // NaN marks the modality missing for this row
+      }
+      if (drop.enabled) {
+        const unsigned col = (unsigned)(sg.wcol + k0 + c4), row = drop.row_base + (unsigned)r;
+        if ((col & 1u) == 0) {
+          const unsigned h0 = mmn_dropout_hash(drop.seed_mix, row, col >> 1);
+          const unsigned h1 = mmn_dropout_hash(drop.seed_mix, row, (col >> 1) + 1);
+          v[4 * i + 0] = (h0 & 0xffffu) >= drop.thr ? v[4 * i + 0] * drop.scale : 0.f;
+          v[4 * i + 1] = (h0 >> 16) >= drop.thr ? v[4 * i + 1] * drop.scale : 0.f;
+          v[4 * i + 2] = (h1 & 0xffffu) >= drop.thr ? v[4 * i + 2] * drop.scale : 0.f;
+          v[4 * i + 3] = (h1 >> 16) >= drop.thr ? v[4 * i + 3] * drop.scale : 0.f;
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            v[4 * i + u] = mmn_dropout_keep(drop.seed_mix, row, col + u, drop.thr) ? v[4 * i + u] * drop.scale : 0.f;
+        }
+      }
+      *reinterpret_cast<float4*>(XB + r * LDX + c4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+  } else {
+    const int c = t & 31, r0 = t >> 5;
+#pragma unroll
+    for (int i = 0; i < 4 * RM; ++i) {
+      const int r = r0 + 8 * i;
+      float x = v[i];
+      if (sg.kind == SEG_SMEM_STAGED) x = c < kw ? sg.ptr[(long long)r * sg.ld + k0 + c] : 0.f;
+      if (sg.kind == SEG_X && x != x) {
+        if (scan_nan) sm.rownan[r] = 1;
+        x = 0.f;
+      }
+      if (drop.enabled && c < kw)
+        x = mmn_dropout_keep(drop.seed_mix, drop.row_base + (unsigned)r, (unsigned)(sg.wcol + k0 + c), drop.thr)
+                ? x * drop.scale : 0.f;
+      XB[r * LDX + c] = x;
+    }
+  }
+}
+
+// iterator over the (segment, k0) chunks of a GEMM's K dimension
+struct ChunkIt {
+  int s, k0;
+  __device__ __forceinline__ bool valid(int nseg) const { return s < nseg; }
+  __device__ __forceinline__ void next(const ASeg* segs) {
+    k0 += KC;
+    if (k0 >= segs[s].width) { ++s; k0 = 0; }
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
-// gemm_nt: out[r][n] = sum over segments sum_k a[r][k] * W[n][wcol + k];  epi(r, n, acc) for every
-// (r, n) of each 32-column pass, including the zero-pad columns n >= N.
+// gemm_nt: out[r][n] = bias[n] + sum over segments sum_k a[r][k] * W[n][wcol + k];  epi(r, n, value)
+// for every (r, n) of each 32-column pass, including the zero-pad columns n >= N.
+// Chunks are double-buffered: the global loads of chunk c+1 are in flight while chunk c is multiplied
+// (one __syncthreads per chunk).
 // ------------------------------------------------------------------------------------------------
 template <int RM, class Epi>
 __device__ __forceinline__ void gemm_nt(const Smem& sm, const float* __restrict__ W, int ldw, int N,
-                                        const ASeg* segs, int nseg, const Drop& drop, int rows_valid,
-                                        bool scan_nan, Epi epi) {
+                                        const float* __restrict__ bias, const ASeg* segs, int nseg,
+                                        const Drop& drop, int rows_valid, bool scan_nan, Epi epi) {
+  constexpr int TM = Cfg<RM>::TM;
   const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+  bool avec[2];
+  avec[0] = seg_vec_ok(segs[0]);
+  avec[1] = nseg > 1 ? seg_vec_ok(segs[1]) : false;
   for (int n0 = 0; n0 < N; n0 += 32) {
-    float acc[RM][4];
+    const int nrows = min(32, N - n0);
+    float acc[RM][4], bj[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bj[j] = (n0 + tx + 8 * j) < N ? __ldg(bias + n0 + tx + 8 * j) : 0.f;
 #pragma unroll
     for (int i = 0; i < RM; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int s = 0; s < nseg; ++s) {
-      const ASeg sg = segs[s];
-      for (int k0 = 0; k0 < sg.width; k0 += KC) {
-        const int kw = min(KC, sg.width - k0);
-        __syncthreads();
-        stage_w_block(sm.WB, W, ldw, n0, min(32, N - n0), sg.wcol + k0, kw);
-        const float* a;
-        int lda;
-        if (sg.kind == SEG_SMEM) {
-          a = sg.ptr + k0;
-          lda = (int)sg.ld;
-        } else {
-          stage_a_chunk<RM>(sm, sg, k0, kw, rows_valid, drop, scan_nan && n0 == 0);
-          a = sm.XB;
-          lda = LDX;
-        }
-        __syncthreads();
-        const int nq = (kw + 3) >> 2;
-#pragma unroll 2
-        for (int q = 0; q < nq; ++q) {
-          float4 av[RM], bv[4];
-#pragma unroll
-          for (int i = 0; i < RM; ++i) av[i] = *reinterpret_cast<const float4*>(a + (ty + 32 * i) * lda + 4 * q);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) bv[j] = *reinterpret_cast<const float4*>(sm.WB + (tx + 8 * j) * LDX + 4 * q);
-#pragma unroll
-          for (int i = 0; i < RM; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              acc[i][j] = fmaf(av[i].x, bv[j].x, acc[i][j]);
-              acc[i][j] = fmaf(av[i].y, bv[j].y, acc[i][j]);
-              acc[i][j] = fmaf(av[i].z, bv[j].z, acc[i][j]);
-              acc[i][j] = fmaf(av[i].w, bv[j].w, acc[i][j]);
-            }
-        }
+    float wr[4], ar[4 * RM];
+    ChunkIt it{0, 0};
+    bool wv = w_vec_ok(W, ldw, segs[0].wcol);
+    w_block_load(wr, W, ldw, n0, nrows, segs[0].wcol, min(KC, segs[0].width), wv);
+    a_chunk_load<RM>(ar, segs[0], 0, min(KC, segs[0].width), rows_valid, avec[0]);
+    int buf = 0;
+    __syncthreads();                    // previous users of the staging buffers are done
+    while (it.valid(nseg)) {
+      const ASeg sg = segs[it.s];
+      const int kw = min(KC, sg.width - it.k0);
+      float* WBb = sm.WB + buf * (32 * LDX);
+      float* XBb = sm.XB + buf * (TM * LDX);
+      w_block_store(WBb, wr, wv);
+      const float* a;
+      int lda;
+      if (sg.kind == SEG_SMEM) {
+        a = sg.ptr + it.k0;
+        lda = (int)sg.ld;
+      } else {
+        a_chunk_store<RM>(XBb, ar, sm, sg, it.k0, kw, drop, scan_nan && n0 == 0, avec[it.s]);
+        a = XBb;
+        lda = LDX;
       }
+      ChunkIt nx = it;
+      nx.next(segs);
+      if (nx.valid(nseg)) {
+        const ASeg& ns = segs[nx.s];
+        const int nkw = min(KC, ns.width - nx.k0);
+        wv = w_vec_ok(W, ldw, ns.wcol + nx.k0);
+        w_block_load(wr, W, ldw, n0, nrows, ns.wcol + nx.k0, nkw, wv);
+        a_chunk_load<RM>(ar, ns, nx.k0, nkw, rows_valid, avec[nx.s]);
+      }
+      __syncthreads();
+      const int nq = (kw + 3) >> 2;
+#pragma unroll 2
+      for (int q = 0; q < nq; ++q) {
+        float4 av[RM], bv[4];
+#pragma unroll
+        for (int i = 0; i < RM; ++i) av[i] = *reinterpret_cast<const float4*>(a + (ty + 32 * i) * lda + 4 * q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bv[j] = *reinterpret_cast<const float4*>(WBb + (tx + 8 * j) * LDX + 4 * q);
+#pragma unroll
+        for (int i = 0; i < RM; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[i][j] = fmaf(av[i].x, bv[j].x, acc[i][j]);
+            acc[i][j] = fmaf(av[i].y, bv[j].y, acc[i][j]);
+            acc[i][j] = fmaf(av[i].z, bv[j].z, acc[i][j]);
+            acc[i][j] = fmaf(av[i].w, bv[j].w, acc[i][j]);
+          }
+      }
+      it = nx;
+      buf ^= 1;
     }
 #pragma unroll
     for (int i = 0; i < RM; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) epi(ty + 32 * i, n0 + tx + 8 * j, acc[i][j]);
+      for (int j = 0; j < 4; ++j) epi(ty + 32 * i, n0 + tx + 8 * j, acc[i][j] + bj[j]);
   }
   __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
-// gemm_nn: out[r][j] = sum_n dz[r][n] * W[n][col0 + j], j < J;  epi(r, j, acc) for every (r, j) of
-// each 32-column pass including pad columns j >= J.  dz: shared tile, zero-padded to 32 columns.
+// gemm_nn: out[r][j] = sum_n dz[r][n] * W[n][col0 + j], j < J;  epi(r, j, acc, pre(r, j)) for every
+// (r, j) of each 32-column pass including pad columns j >= J.  dz: shared tile, zero-padded to 32
+// columns.  pre(r, j) is evaluated BEFORE the K loop so that its global loads (stashed activations)
+// are hidden behind the multiply.
 // ------------------------------------------------------------------------------------------------
-template <int RM, class Epi>
+template <int RM, class Pre, class Epi>
 __device__ __forceinline__ void gemm_nn(const Smem& sm, const float* dz, int ldd, int N,
-                                        const float* __restrict__ W, int ldw, int col0, int J, Epi epi) {
+                                        const float* __restrict__ W, int ldw, int col0, int J, Pre pre, Epi epi) {
   const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
   for (int j0 = 0; j0 < J; j0 += 32) {
-    float acc[RM][4];
+    const int jw = min(32, J - j0);
+    float acc[RM][4], pv[RM][4];
 #pragma unroll
     for (int i = 0; i < RM; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      for (int c = 0; c < 4; ++c) {
+        acc[i][c] = 0.f;
+        pv[i][c] = pre(ty + 32 * i, j0 + 4 * tx + c);
+      }
+    const bool wv = w_vec_ok(W, ldw, col0 + j0);
+    float wr[4];
+    w_block_load(wr, W, ldw, 0, min(32, N), col0 + j0, jw, wv);
+    int buf = 0;
+    __syncthreads();
     for (int n0 = 0; n0 < N; n0 += 32) {
       const int nw = min(32, N - n0);
-      __syncthreads();
-      stage_w_block(sm.WB, W, ldw, n0, nw, col0 + j0, min(32, J - j0));
+      float* WBb = sm.WB + buf * (32 * LDX);
+      w_block_store(WBb, wr, wv);
+      if (n0 + 32 < N) w_block_load(wr, W, ldw, n0 + 32, min(32, N - n0 - 32), col0 + j0, jw, wv);
       __syncthreads();
       const int nq = (nw + 3) >> 2;
 #pragma unroll 2
@@ -224,7 +361,7 @@ __device__ __forceinline__ void gemm_nn(const Smem& sm, const float* dz, int ldd
 #pragma unroll
         for (int i = 0; i < RM; ++i) av[i] = *reinterpret_cast<const float4*>(dz + (ty + 32 * i) * ldd + n0 + 4 * q);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) bv[u] = *reinterpret_cast<const float4*>(sm.WB + (4 * q + u) * LDX + 4 * tx);
+        for (int u = 0; u < 4; ++u) bv[u] = *reinterpret_cast<const float4*>(WBb + (4 * q + u) * LDX + 4 * tx);
 #pragma unroll
         for (int i = 0; i < RM; ++i) {
           acc[i][0] = fmaf(av[i].x, bv[0].x, acc[i][0]); acc[i][1] = fmaf(av[i].x, bv[0].y, acc[i][1]);
@@ -237,11 +374,12 @@ __device__ __forceinline__ void gemm_nn(const Smem& sm, const float* dz, int ldd
           acc[i][2] = fmaf(av[i].w, bv[3].z, acc[i][2]); acc[i][3] = fmaf(av[i].w, bv[3].w, acc[i][3]);
         }
       }
+      buf ^= 1;
     }
 #pragma unroll
     for (int i = 0; i < RM; ++i)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) epi(ty + 32 * i, j0 + 4 * tx + c, acc[i][c]);
+      for (int c = 0; c < 4; ++c) epi(ty + 32 * i, j0 + 4 * tx + c, acc[i][c], pv[i][c]);
   }
   __syncthreads();
 }
@@ -251,28 +389,64 @@ __device__ __forceinline__ void gemm_nn(const Smem& sm, const float* dz, int ldd
 // The TM rows are split over kGroups groups of 64 threads; each group owns the whole 32x32 output
 // block for its rows (4x4 outputs per thread), the groups' partial blocks are summed through
 // shared memory and the tile's contribution is added to global memory with one red per element.
+// Input chunks and the reduction scratch are double-buffered: one __syncthreads per 32x32 block.
 // ------------------------------------------------------------------------------------------------
 template <int RM>
 __device__ __forceinline__ void gemm_tn(const Smem& sm, const float* dz, int ldd, int N, const ASeg& sg,
                                         const Drop& drop, int rows_valid, float* __restrict__ gW, int ldw) {
+  constexpr int TM = Cfg<RM>::TM;
   constexpr int RPG = 8 * RM;     // rows per group
   const int tid = threadIdx.x, g = tid >> 6, u = tid & 63, nt = u >> 3, kt = u & 7;
   const bool vec_ok = ((ldw & 3) == 0) && ((sg.wcol & 3) == 0) && ((reinterpret_cast<size_t>(gW) & 15) == 0);
+  const bool avec = seg_vec_ok(sg);
+  const int nnb = (N + 31) >> 5;
+  float ar[4 * RM];
+  a_chunk_load<RM>(ar, sg, 0, min(KC, sg.width), rows_valid, avec);
+  __syncthreads();                 // previous users of XB / RED are done
+  int xbuf = 0, rbuf = 0;
+  // software pipeline over (chunk, n-block) items: the reduction of item i-1 runs after the sync of item i
+  int pend_n0 = -1, pend_k0 = 0, pend_rbuf = 0;
+  auto flush = [&](int n0, int k0, int rb) {
+    const int n = tid >> 3, kq = tid & 7;    // 256 threads x 4 outputs = the 32x32 block
+    const float* red = sm.RED + rb * (kGroups * 1024);
+    float4 s = *reinterpret_cast<const float4*>(red + n * 32 + 4 * kq);
+#pragma unroll
+    for (int gg = 1; gg < kGroups; ++gg) {
+      const float4 o = *reinterpret_cast<const float4*>(red + gg * 1024 + n * 32 + 4 * kq);
+      s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+    }
+    if (n0 + n < N) {
+      const int kc = k0 + 4 * kq;
+      float* dst = gW + (long long)(n0 + n) * ldw + sg.wcol + kc;
+      if (vec_ok && kc + 3 < sg.width) {
+        atomicAdd(reinterpret_cast<float4*>(dst), s);
+      } else {
+        if (kc + 0 < sg.width) atomicAdd(dst + 0, s.x);
+        if (kc + 1 < sg.width) atomicAdd(dst + 1, s.y);
+        if (kc + 2 < sg.width) atomicAdd(dst + 2, s.z);
+        if (kc + 3 < sg.width) atomicAdd(dst + 3, s.w);
+      }
+    }
+  };
   for (int k0 = 0; k0 < sg.width; k0 += KC) {
     const int kw = min(KC, sg.width - k0);
     const float* a;
     int lda;
-    __syncthreads();
     if (sg.kind == SEG_SMEM) {
       a = sg.ptr + k0;
       lda = (int)sg.ld;
     } else {
-      stage_a_chunk<RM>(sm, sg, k0, kw, rows_valid, drop, false);
-      a = sm.XB;
+      float* XBb = sm.XB + xbuf * (TM * LDX);
+      a_chunk_store<RM>(XBb, ar, sm, sg, k0, kw, drop, false, avec);
+      a = XBb;
       lda = LDX;
+      xbuf ^= 1;
     }
-    __syncthreads();
-    for (int n0 = 0; n0 < N; n0 += 32) {
+    if (k0 + KC < sg.width) a_chunk_load<RM>(ar, sg, k0 + KC, min(KC, sg.width - k0 - KC), rows_valid, avec);
+    for (int nb = 0; nb < nnb; ++nb) {
+      const int n0 = nb * 32;
+      __syncthreads();             // chunk visible; RED of the pending item complete
+      if (pend_n0 >= 0) flush(pend_n0, pend_k0, pend_rbuf);
       float acc[4][4];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -292,35 +466,16 @@ __device__ __forceinline__ void gemm_tn(const Smem& sm, const float* dz, int ldd
         acc[3][0] = fmaf(dv.w, iv.x, acc[3][0]); acc[3][1] = fmaf(dv.w, iv.y, acc[3][1]);
         acc[3][2] = fmaf(dv.w, iv.z, acc[3][2]); acc[3][3] = fmaf(dv.w, iv.w, acc[3][3]);
       }
-      float* red = sm.RED + g * 1024;
+      float* red = sm.RED + rbuf * (kGroups * 1024) + g * 1024;
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         *reinterpret_cast<float4*>(red + (4 * nt + i) * 32 + 4 * kt) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-      __syncthreads();
-      {
-        const int n = tid >> 3, kq = tid & 7;    // 256 threads x 4 outputs = the 32x32 block
-        float4 s = *reinterpret_cast<const float4*>(sm.RED + n * 32 + 4 * kq);
-#pragma unroll
-        for (int gg = 1; gg < kGroups; ++gg) {
-          const float4 o = *reinterpret_cast<const float4*>(sm.RED + gg * 1024 + n * 32 + 4 * kq);
-          s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
-        }
-        if (n0 + n < N) {
-          const int kc = k0 + 4 * kq;
-          float* dst = gW + (long long)(n0 + n) * ldw + sg.wcol + kc;
-          if (vec_ok && kc + 3 < sg.width) {
-            atomicAdd(reinterpret_cast<float4*>(dst), s);
-          } else {
-            if (kc + 0 < sg.width) atomicAdd(dst + 0, s.x);
-            if (kc + 1 < sg.width) atomicAdd(dst + 1, s.y);
-            if (kc + 2 < sg.width) atomicAdd(dst + 2, s.z);
-            if (kc + 3 < sg.width) atomicAdd(dst + 3, s.w);
-          }
-        }
-      }
-      __syncthreads();
+      pend_n0 = n0; pend_k0 = k0; pend_rbuf = rbuf;
+      rbuf ^= 1;
     }
   }
+  __syncthreads();
+  if (pend_n0 >= 0) flush(pend_n0, pend_k0, pend_rbuf);
 }
 
 // bias gradient: gb[n] += sum_r dz[r][n]
@@ -344,13 +499,30 @@ __device__ __forceinline__ void colsum_red(const Smem& sm, const float* dz, int 
   __syncthreads();
 }
 
-// shared tile [TM x width] -> global row-major [TM x width]
+// walks idx = tid, tid + kThreads, ... of a [rows x w] index space as (r, c) without a division per step
+struct RowCol {
+  int r, c, q, rem, w;
+  __device__ __forceinline__ RowCol(int w_) : w(w_) {
+    r = (int)threadIdx.x / w_; c = (int)threadIdx.x - r * w_;
+    q = kThreads / w_; rem = kThreads - q * w_;
+  }
+  __device__ __forceinline__ void next() {
+    r += q; c += rem;
+    if (c >= w) { c -= w; ++r; }
+  }
+};
+
+// shared tile [TM x width] -> global row-major [TM x width] (float4 when the width allows)
 template <int RM>
 __device__ __forceinline__ void stash_store(float* dst, const float* buf, int ld, int width) {
   constexpr int TM = Cfg<RM>::TM;
-  for (int idx = threadIdx.x; idx < TM * width; idx += kThreads) {
-    const int r = idx / width, c = idx - r * width;
-    __stcg(dst + idx, buf[r * ld + c]);
+  if ((width & 3) == 0) {
+    const int w4 = width >> 2;
+    for (RowCol it(w4); it.r < TM; it.next())
+      __stcg(reinterpret_cast<float4*>(dst) + it.r * w4 + it.c,
+             *reinterpret_cast<const float4*>(buf + it.r * ld + 4 * it.c));
+  } else {
+    for (RowCol it(width); it.r < TM; it.next()) __stcg(dst + it.r * width + it.c, buf[it.r * ld + it.c]);
   }
 }
 
@@ -385,9 +557,9 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
     sm.T = f; f += TM * ldS;
     sm.A = f; f += TM * ldH;
     sm.B = f; f += TM * ldH;
-    sm.XB = f; f += TM * LDX;
-    sm.WB = f; f += 32 * LDX;
-    sm.RED = f; f += kGroups * 1024;
+    sm.XB = f; f += 2 * TM * LDX;
+    sm.WB = f; f += 2 * 32 * LDX;
+    sm.RED = f; f += 2 * kGroups * 1024;
     sm.ys = reinterpret_cast<int*>(f); f += TM * D;
     sm.rownan = reinterpret_cast<int*>(f); f += TM;
     sm.cnt = reinterpret_cast<int*>(f); f += (E + 1);
@@ -439,12 +611,9 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
           float* out = (j & 1) ? sm.B : sm.A;
           ASeg seg;
           seg.ptr = in; seg.ld = ldin; seg.width = ly.in_dim; seg.kind = SEG_SMEM; seg.wcol = 0;
-          const float* __restrict__ bias = params + ly.b_off;
           const int N = ly.out_dim, act = ly.act;
-          gemm_nt<RM>(sm, params + ly.w_off, ly.ktot, N, &seg, 1, nodrop, rows_valid, false,
-                      [&](int r, int n, float acc) {
-                        out[r * ldH + n] = n < N ? act_fwd(act, acc + __ldg(bias + n)) : 0.f;
-                      });
+          gemm_nt<RM>(sm, params + ly.w_off, ly.ktot, N, params + ly.b_off, &seg, 1, nodrop, rows_valid, false,
+                      [&](int r, int n, float z) { out[r * ldH + n] = n < N ? act_fwd(act, z) : 0.f; });
           if (TRAIN)
             stash_store<RM>(slot + (long long)(stash_dec_off(P, k) + dec.stash_off + ly.stash_off) * TM, out, ldH, N);
           in = out;
@@ -516,7 +685,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
         if (TRAIN && args.training && enc.p_drop > 0.f && enc.L[0].has_state) {
           drop.enabled = 1;
           drop.seed_mix = args.dropout_seed ^ ((unsigned)e * 0x9E3779B9u);
-          drop.thr = (unsigned)(enc.p_drop * 16777216.f);
+          drop.thr = (unsigned)(enc.p_drop * 65536.f);
           drop.row_base = (unsigned)(args.row_offset + row0);
           drop.scale = 1.f / (1.f - enc.p_drop);
         }
@@ -543,12 +712,10 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
             segs[1].wcol = ly.in_dim;
             nseg = 2;
           }
-          const float* __restrict__ bias = params + ly.b_off;
           const int N = ly.out_dim, act = ly.act;
-          gemm_nt<RM>(sm, params + ly.w_off, ly.ktot, N, segs, nseg, use_drop ? drop : nodrop, rows_valid, j == 0,
-                      [&](int r, int n, float acc) {
-                        out[r * ldo + n] = n < N ? act_fwd(act, acc + __ldg(bias + n)) : 0.f;
-                      });
+          gemm_nt<RM>(sm, params + ly.w_off, ly.ktot, N, params + ly.b_off, segs, nseg, use_drop ? drop : nodrop,
+                      rows_valid, j == 0,
+                      [&](int r, int n, float z) { out[r * ldo + n] = n < N ? act_fwd(act, z) : 0.f; });
           if (TRAIN && !last)
             stash_store<RM>(slot + (long long)(stash_enc_off(P, k) + ly.stash_off) * TM, out, ldH, N);
           in = out;
@@ -566,8 +733,8 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
       if (tid == 0) sm.tile_any[k] = any;
       if (any) {
         float sc = 0.f;
-        for (int idx = tid; idx < TM * S; idx += kThreads) {
-          const int r = idx / S, c = idx - r * S;
+        for (RowCol it(S); it.r < TM; it.next()) {
+          const int r = it.r, c = it.c;
           if (sm.present[k * TM + r]) {
             const float o = sm.S[r * ldS + c], nw = sm.T[r * ldS + c], df = nw - o;
             sc = fmaf(df, df, sc);
@@ -582,10 +749,8 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
       decoders_forward(k, e + 1, e == E - 1);
     }
     if (args.final_state) {
-      for (int idx = tid; idx < rows_valid * S; idx += kThreads) {
-        const int r = idx / S, c = idx - r * S;
-        args.final_state[(row0 + r) * S + c] = sm.S[r * ldS + c];
-      }
+      for (RowCol it(S); it.r < rows_valid; it.next())
+        args.final_state[(row0 + it.r) * S + it.c] = sm.S[it.r * ldS + it.c];
     }
 
     // =============================================================================================
@@ -643,13 +808,15 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
               const float* ast = slot + dbase + (long long)dec.L[j - 1].stash_off * TM;
               const int J = ly.in_dim, pact = dec.L[j - 1].act;
               gemm_nn<RM>(sm, cur, ldH, ly.out_dim, params + ly.w_off, ly.ktot, 0, J,
-                          [&](int r, int jc, float acc) {
-                            other[r * ldH + jc] = jc < J ? acc * act_bwd(pact, __ldcg(ast + r * J + jc)) : 0.f;
+                          [&](int r, int jc) { return jc < J ? __ldcg(ast + r * J + jc) : 0.f; },
+                          [&](int r, int jc, float acc, float a) {
+                            other[r * ldH + jc] = jc < J ? acc * act_bwd(pact, a) : 0.f;
                           });
               cur = other;
             } else {
               gemm_nn<RM>(sm, cur, ldH, ly.out_dim, params + ly.w_off, ly.ktot, 0, S,
-                          [&](int r, int jc, float acc) {
+                          [&](int, int) { return 0.f; },
+                          [&](int r, int jc, float acc, float) {
                             if (jc < S) G[r * ldS + jc] += acc;
                           });
             }
@@ -669,8 +836,8 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
         {
           const int act = enc.L[nl - 1].act;
           const int Spad = (S + 31) & ~31;
-          for (int idx = tid; idx < TM * Spad; idx += kThreads) {
-            const int r = idx / Spad, c = idx - r * Spad;
+          for (RowCol it(Spad); it.r < TM; it.next()) {
+            const int r = it.r, c = it.c;
             float dzv = 0.f;
             if (c < S) {
               const float a = __ldcg(sk + r * S + c), b = __ldcg(skm1 + r * S + c);
@@ -686,7 +853,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
         if (args.training && enc.p_drop > 0.f && enc.L[0].has_state) {
           drop.enabled = 1;
           drop.seed_mix = args.dropout_seed ^ ((unsigned)e * 0x9E3779B9u);
-          drop.thr = (unsigned)(enc.p_drop * 16777216.f);
+          drop.thr = (unsigned)(enc.p_drop * 65536.f);
           drop.row_base = (unsigned)(args.row_offset + row0);
           drop.scale = 1.f / (1.f - enc.p_drop);
         }
@@ -716,8 +883,9 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
             const float* ast = slot + ebase + (long long)enc.L[j - 1].stash_off * TM;
             const int J = ly.in_dim, pact = enc.L[j - 1].act;
             gemm_nn<RM>(sm, cur, ldc, ly.out_dim, params + ly.w_off, ly.ktot, 0, J,
-                        [&](int r, int jc, float acc) {
-                          other[r * ldH + jc] = jc < J ? acc * act_bwd(pact, __ldcg(ast + r * J + jc)) : 0.f;
+                        [&](int r, int jc) { return jc < J ? __ldcg(ast + r * J + jc) : 0.f; },
+                        [&](int r, int jc, float acc, float a) {
+                          other[r * ldH + jc] = jc < J ? acc * act_bwd(pact, a) : 0.f;
                         });
           }
           if (ly.has_state) {
@@ -725,13 +893,15 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
             // then remove u_k, which belongs to s_{k-1} with the opposite sign (multimodn.py:165,174)
             const int in_dim = ly.in_dim;
             gemm_nn<RM>(sm, cur, ldc, ly.out_dim, params + ly.w_off, ly.ktot, in_dim, S,
-                        [&](int r, int jc, float acc) {
+                        [&](int r, int jc) {      // u_k, loaded before the multiply
+                          return jc < S ? args.c_sc * (__ldcg(sk + r * S + jc) - __ldcg(skm1 + r * S + jc)) : 0.f;
+                        },
+                        [&](int r, int jc, float acc, float u) {
                           if (jc < S) {
                             float carry = acc;
                             if (use_drop)
                               carry = mmn_dropout_keep(drop.seed_mix, drop.row_base + (unsigned)r, (unsigned)(in_dim + jc), drop.thr)
                                           ? carry * drop.scale : 0.f;
-                            const float u = args.c_sc * (__ldcg(sk + r * S + jc) - __ldcg(skm1 + r * S + jc));
                             const float g = sm.present[k * TM + r] ? carry : G[r * ldS + jc];
                             G[r * ldS + jc] = g - u;
                           }

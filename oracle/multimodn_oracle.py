@@ -89,14 +89,16 @@ def dropout_keep(seed, enc_id, rows, n_cols, p):
     cols = np.arange(n_cols, dtype=np.uint32)[None, :]
     with np.errstate(over="ignore"):
         h = np.uint32(seed) ^ (np.uint32(enc_id) * np.uint32(0x9E3779B9))
-        x = rows * np.uint32(0x85EBCA6B) + cols * np.uint32(0xC2B2AE35) + h
+        x = rows * np.uint32(0x85EBCA6B) + (cols >> np.uint32(1)) * np.uint32(0xC2B2AE35) + h
         x ^= x >> np.uint32(16)
         x *= np.uint32(0x7FEB352D)
         x ^= x >> np.uint32(15)
         x *= np.uint32(0x846CA68B)
         x ^= x >> np.uint32(16)
-    thr = np.uint32(int(float(p) * (1 << 24)))
-    return (x >> np.uint32(8)) >= thr
+    # one 32-bit hash serves a pair of adjacent columns: low 16 bits -> even column, high -> odd
+    half = np.where((cols & np.uint32(1)) == 1, x >> np.uint32(16), x & np.uint32(0xFFFF))
+    thr = np.uint32(int(np.float32(p) * np.float32(65536.0)))
+    return half >= thr
 
 
 # --------------------------------------------------------------------------------------
