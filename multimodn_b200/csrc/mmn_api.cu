@@ -1,6 +1,7 @@
 // mmn_api.cu — the C ABI of libmmn.so (include/mmn.h): plan construction, launch configuration and
 // argument marshalling around the kernels in mmn_kernels.cuh.  No torch types, no hidden syncs.
 #include "mmn_kernels.cuh"
+#include "mmn_tc.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -306,6 +307,18 @@ extern "C" int mmn_adam_step(const mmn_plan* plan, float* params, const float* g
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((plan->host.n_params + 255) / 256, (int64_t)plan->n_sms * 8));
   MMN_LAUNCH(mmn_adam_kernel, dim3(grid), dim3(256), 0, stream, plan->dev, params, grads, exp_avg, exp_avg_sq,
              step_count, lr, beta1, beta2, eps);
+  MMN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Diagnostic: one tcgen05 3xTF32 GEMM in each operand configuration of the tensor-core engine
+// (mmn_tc.cuh).  a, b, out: device pointers, see mmn_tc_selftest_kernel.
+extern "C" int mmn_selftest_umma(int mode, int n, const float* a, const float* b, float* out, void* stream) {
+  if (mode < 0 || mode > 2 || (n != 32 && n != 64) || (mode == 2 && n != 32)) return fail("mmn_selftest_umma: bad mode / n");
+  const size_t smem = 1024 + 98304 + 64;
+  auto kfn = mmn_tc_selftest_kernel;
+  MMN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MMN_LAUNCH(kfn, dim3(1), dim3(256), smem, stream, mode, n, a, b, out);
   MMN_CUDA(cudaGetLastError());
   return 0;
 }

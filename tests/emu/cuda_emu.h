@@ -207,8 +207,8 @@ template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) {
   do {                                                                              \
     dim3 g_ = (grid), b_ = (block);                                                 \
     emu::gDim() = g_; emu::bDim() = b_;                                             \
-    std::vector<char> smem_((size_t)(smem) + 16);                                   \
-    emu::st().dyn_smem = (char*)(((uintptr_t)smem_.data() + 15) & ~(uintptr_t)15);  \
+    std::vector<char> smem_((size_t)(smem) + 1024);                                   \
+    emu::st().dyn_smem = (char*)(((uintptr_t)smem_.data() + 1023) & ~(uintptr_t)1023);  \
     emu::st().dyn_smem_bytes = (smem);                                              \
     for (unsigned bx_ = 0; bx_ < g_.x; ++bx_) {                                     \
       emu::bIdx() = dim3(bx_);                                                      \

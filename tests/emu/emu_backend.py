@@ -10,7 +10,8 @@ from multimodn_b200 import _lib
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SO = os.path.join(HERE, "libmmn_emu.so")
-SOURCES = [os.path.join(ROOT, "multimodn_b200", "csrc", f) for f in ("mmn_api.cu", "mmn_kernels.cuh", "mmn_common.cuh")]
+import glob
+SOURCES = glob.glob(os.path.join(ROOT, "multimodn_b200", "csrc", "*.cu*"))
 SOURCES += [os.path.join(ROOT, "include", "mmn.h"), os.path.join(HERE, "cuda_emu.h")]
 
 
