@@ -135,6 +135,12 @@ int mmn_abi_version(void);
 int mmn_plan_create(const mmn_model_desc* desc, mmn_plan** out);
 void mmn_plan_destroy(mmn_plan* plan);
 
+/* Which GEMM engine the plan's step kernel uses: the tcgen05 3xTF32 tensor-core engine when the
+ * model's tiles fit shared memory at 128 rows, else the FP32-FMA engine.  The environment variable
+ * MMN_ENGINE=fma|tc (read by mmn_plan_create) forces one; results agree to fp32 round-off. */
+enum { MMN_ENGINE_FMA = 0, MMN_ENGINE_TC = 1 };
+int32_t mmn_plan_engine(const mmn_plan* plan);
+
 int64_t mmn_metrics_count(const mmn_plan* plan);            /* doubles in mmn_outputs.metrics */
 int64_t mmn_grad_count(const mmn_plan* plan);               /* floats in the gradient buffer:
                                                                n_params + E (tail: per-encoder

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -16,6 +17,8 @@ struct mmn_plan {
   DevPlan* dev = nullptr;
   int n_sms = 0;
   int max_smem = 0;
+  int engine = MMN_ENGINE_FMA;   // MMN_ENGINE_*
+  int rm = 0;                    // FMA engine: rows per tile / 32
 };
 
 namespace {
@@ -38,14 +41,21 @@ int fail(const char* fmt, ...) {
 
 int round32(int v) { return (v + 31) & ~31; }
 
-// largest row tile (32*RM rows) whose shared-memory footprint fits
-int pick_rm(const mmn_plan* p, bool train) {
+size_t fma_smem(const DevPlan& P, int rm) {
+  const size_t stage = rm == 4 ? FmaEngine<4>::stage_bytes() : rm == 2 ? FmaEngine<2>::stage_bytes() : FmaEngine<1>::stage_bytes();
+  return step_smem_bytes(P, 32 * rm, stage);
+}
+size_t tc_smem(const DevPlan& P) { return step_smem_bytes(P, TcEngine::TM, TcEngine::stage_bytes()); }
+// largest FMA row tile (32*RM rows) whose shared-memory footprint fits
+int pick_rm(const mmn_plan* p) {
   for (int rm : {4, 2, 1})
-    if (step_smem_bytes(p->host, rm, train) <= (size_t)p->max_smem) return rm;
+    if (fma_smem(p->host, rm) <= (size_t)p->max_smem) return rm;
   return 0;
 }
-int grid_for(const mmn_plan* p, int rm, int64_t n_rows) {
-  const int64_t tiles = (n_rows + 32 * rm - 1) / (32 * rm);
+int tile_rows(const mmn_plan* p) { return p->engine == MMN_ENGINE_TC ? TcEngine::TM : 32 * p->rm; }
+int grid_for(const mmn_plan* p, int64_t n_rows) {
+  const int tm = tile_rows(p);
+  const int64_t tiles = (n_rows + tm - 1) / tm;
   return (int)std::max<int64_t>(1, std::min<int64_t>(tiles, p->n_sms));
 }
 
@@ -150,8 +160,16 @@ extern "C" int mmn_plan_create(const mmn_model_desc* desc, mmn_plan** out) {
     delete p;
     return fail("mmn_plan_create: no CUDA device");
   }
-  if (pick_rm(p, true) == 0) {
-    const size_t need = step_smem_bytes(P, 1, true);
+  p->rm = pick_rm(p);
+  const bool tc_fits = tc_smem(P) <= (size_t)p->max_smem;
+  const char* want = getenv("MMN_ENGINE");            // "tc" | "fma" | unset = auto
+  if (want && !strcmp(want, "tc") && !tc_fits) {
+    delete p;
+    return fail("MMN_ENGINE=tc: the tensor-core engine needs %zu B of shared memory for this model (limit %d)", tc_smem(P), p->max_smem);
+  }
+  p->engine = (tc_fits && !(want && !strcmp(want, "fma"))) ? MMN_ENGINE_TC : MMN_ENGINE_FMA;
+  if (p->engine == MMN_ENGINE_FMA && p->rm == 0) {
+    const size_t need = fma_smem(P, 1);
     delete p;
     return fail("model too wide for the fused step kernel: needs %zu B of shared memory per 32-row tile", need);
   }
@@ -173,11 +191,12 @@ extern "C" void mmn_plan_destroy(mmn_plan* plan) {
 extern "C" int64_t mmn_metrics_count(const mmn_plan* plan) { return plan ? plan->host.n_metrics : -1; }
 extern "C" int64_t mmn_grad_count(const mmn_plan* plan) { return plan ? plan->host.n_params + plan->host.E : -1; }
 
+extern "C" int32_t mmn_plan_engine(const mmn_plan* plan) { return plan ? plan->engine : -1; }
+
 extern "C" int64_t mmn_workspace_bytes(const mmn_plan* plan, int64_t n_rows, int32_t with_backward) {
   if (!plan || n_rows < 0) return -1;
   if (!with_backward) return 0;
-  const int rm = pick_rm(plan, true);
-  return (int64_t)grid_for(plan, rm, n_rows) * 32 * rm * plan->host.stash_row * 4;
+  return (int64_t)grid_for(plan, n_rows) * tile_rows(plan) * plan->host.stash_row * 4;
 }
 
 namespace {
@@ -221,26 +240,25 @@ int fill_args(const mmn_plan* plan, const mmn_batch* b, const float* params, con
   return 0;
 }
 
-template <bool TRAIN>
-int launch_step(const mmn_plan* plan, int rm, const StepArgs& a, void* stream) {
-  const size_t smem = step_smem_bytes(plan->host, rm, TRAIN);
-  const int grid = grid_for(plan, rm, a.n_rows);
-#define MMN_CASE(RM_)                                                                              \
-  case RM_: {                                                                                      \
-    auto kfn = mmn_step_kernel<RM_, TRAIN>;                                                        \
-    MMN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    MMN_LAUNCH(kfn, dim3(grid), dim3(kThreads), smem, stream, a);                                  \
-    break;                                                                                         \
-  }
-  switch (rm) {
-    MMN_CASE(4)
-    MMN_CASE(2)
-    MMN_CASE(1)
-    default: return fail("no tile configuration fits");
-  }
-#undef MMN_CASE
+template <class ENG, bool TRAIN>
+int launch_engine(const mmn_plan* plan, const StepArgs& a, void* stream) {
+  const size_t smem = step_smem_bytes(plan->host, ENG::TM, ENG::stage_bytes());
+  const int grid = grid_for(plan, a.n_rows);
+  auto kfn = mmn_step_kernel<ENG, TRAIN>;
+  MMN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MMN_LAUNCH(kfn, dim3(grid), dim3(kThreads), smem, stream, a);
   MMN_CUDA(cudaGetLastError());
   return 0;
+}
+template <bool TRAIN>
+int launch_step(const mmn_plan* plan, const StepArgs& a, void* stream) {
+  if (plan->engine == MMN_ENGINE_TC) return launch_engine<TcEngine, TRAIN>(plan, a, stream);
+  switch (plan->rm) {
+    case 4: return launch_engine<FmaEngine<4>, TRAIN>(plan, a, stream);
+    case 2: return launch_engine<FmaEngine<2>, TRAIN>(plan, a, stream);
+    case 1: return launch_engine<FmaEngine<1>, TRAIN>(plan, a, stream);
+    default: return fail("no tile configuration fits");
+  }
 }
 }  // namespace
 
@@ -273,7 +291,7 @@ extern "C" int mmn_forward(const mmn_plan* plan, const mmn_batch* batch, const f
   if (!plan) return fail("mmn_forward: null plan");
   StepArgs a;
   if (fill_args(plan, batch, params, out, a)) return 1;
-  return launch_step<false>(plan, pick_rm(plan, false), a, stream);
+  return launch_step<false>(plan, a, stream);
 }
 
 extern "C" int mmn_train_step(const mmn_plan* plan, const mmn_batch* batch, const float* params,
@@ -286,17 +304,16 @@ extern "C" int mmn_train_step(const mmn_plan* plan, const mmn_batch* batch, cons
   if (!batch->targets) return fail("mmn_train_step: targets are required");
   const int64_t need = mmn_workspace_bytes(plan, batch->n_rows, 1);
   if (!workspace || (int64_t)workspace_bytes < need) return fail("workspace too small: need %lld bytes", (long long)need);
-  const int rm = pick_rm(plan, true);
   const double bg = 1.0 / a.inv_rows_global;
   a.grads = grads;
   a.stash = (float*)workspace;
-  a.slot_floats = (long long)32 * rm * P.stash_row;
+  a.slot_floats = (long long)tile_rows(plan) * P.stash_row;
   a.c_err = (float)((double)targs->err_penalty / ((double)P.D * (P.E + 1) * bg));
   a.c_sc = (float)(2.0 * (double)targs->state_change_penalty_scaled / ((double)P.E * bg * P.S));
   a.dropout_seed = targs->dropout_seed;
   a.training = targs->training;
   MMN_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)(P.n_params + P.E), (cudaStream_t)stream));
-  return launch_step<true>(plan, rm, a, stream);
+  return launch_step<true>(plan, a, stream);
 }
 
 extern "C" int mmn_adam_step(const mmn_plan* plan, float* params, const float* grads, float* exp_avg,

@@ -93,19 +93,16 @@ struct StepArgs {
   unsigned dropout_seed;
 };
 
-// shared-memory footprint of the step kernel for a row tile of 32*RM rows
-inline size_t step_smem_bytes(const DevPlan& p, int RM, bool train) {
-  const size_t TM = 32 * (size_t)RM;
-  size_t f = 2 * TM * p.ldS + 2 * TM * p.ldH + 2 * (TM * LDX + 32 * LDX);   // S/G, T, A, B, 2x(XB, WB)
-  f += 2 * kGroups * 1024;                                                  // 2x RED scratch (also column sums)
-  size_t bytes = f * 4;
+// shared-memory footprint of the step kernel for a row tile of TM rows, given the engine's staging bytes
+inline size_t step_smem_bytes(const DevPlan& p, int TM_, size_t stage_bytes) {
+  const size_t TM = (size_t)TM_;
+  size_t bytes = stage_bytes + (2 * TM * p.ldS + 2 * TM * p.ldH) * 4;   // staging, S/G, T, A, B
   bytes += TM * p.D * 4;                 // targets tile
   bytes += TM * 4;                       // row NaN flags
   bytes += (size_t)(p.E + 1) * 8;        // present-row counters + tile_any (ints)
   bytes = (bytes + 7) & ~(size_t)7;
   bytes += (size_t)p.n_metrics * 8;      // metric accumulators (double)
   bytes += (size_t)(p.E + 1) * TM;       // present masks
-  (void)train;
   return (bytes + 15) & ~(size_t)15;
 }
 

@@ -79,6 +79,8 @@ struct Smem {
   int* tile_any;     // [E+1] does the current tile have a present row at step k
   double* met;
   unsigned char* present;   // [(E+1)][TM]
+  unsigned long long* bar;  // tensor-core engine: two mbarriers
+  unsigned* tslot;          // tensor-core engine: TMEM base address slot
 };
 
 // One K-segment of a GEMM's activation operand.
@@ -244,7 +246,7 @@ struct ChunkIt {
 // (one __syncthreads per chunk).
 // ------------------------------------------------------------------------------------------------
 template <int RM, class Epi>
-__device__ __forceinline__ void gemm_nt(const Smem& sm, const float* __restrict__ W, int ldw, int N,
+__device__ __forceinline__ void fma_gemm_nt(const Smem& sm, const float* __restrict__ W, int ldw, int N,
                                         const float* __restrict__ bias, const ASeg* segs, int nseg,
                                         const Drop& drop, int rows_valid, bool scan_nan, Epi epi) {
   constexpr int TM = Cfg<RM>::TM;
@@ -330,7 +332,7 @@ __device__ __forceinline__ void gemm_nt(const Smem& sm, const float* __restrict_
 // are hidden behind the multiply.
 // ------------------------------------------------------------------------------------------------
 template <int RM, class Pre, class Epi>
-__device__ __forceinline__ void gemm_nn(const Smem& sm, const float* dz, int ldd, int N,
+__device__ __forceinline__ void fma_gemm_nn(const Smem& sm, const float* dz, int ldd, int N,
                                         const float* __restrict__ W, int ldw, int col0, int J, Pre pre, Epi epi) {
   const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
   for (int j0 = 0; j0 < J; j0 += 32) {
@@ -392,7 +394,7 @@ __device__ __forceinline__ void gemm_nn(const Smem& sm, const float* dz, int ldd
 // Input chunks and the reduction scratch are double-buffered: one __syncthreads per 32x32 block.
 // ------------------------------------------------------------------------------------------------
 template <int RM>
-__device__ __forceinline__ void gemm_tn(const Smem& sm, const float* dz, int ldd, int N, const ASeg& sg,
+__device__ __forceinline__ void fma_gemm_tn(const Smem& sm, const float* dz, int ldd, int N, const ASeg& sg,
                                         const Drop& drop, int rows_valid, float* __restrict__ gW, int ldw) {
   constexpr int TM = Cfg<RM>::TM;
   constexpr int RPG = 8 * RM;     // rows per group
@@ -478,6 +480,43 @@ __device__ __forceinline__ void gemm_tn(const Smem& sm, const float* dz, int ldd
   if (pend_n0 >= 0) flush(pend_n0, pend_k0, pend_rbuf);
 }
 
+// ------------------------------------------------------------------------------------------------
+// FMA engine: the three GEMM shapes on the FP32 pipe (any tile height RM in {1, 2, 4})
+// ------------------------------------------------------------------------------------------------
+struct NoState {};
+template <int RM_>
+struct FmaEngine {
+  static constexpr int RM = RM_;
+  static constexpr int TM = 32 * RM_;
+  static constexpr bool kTensor = false;
+  using State = NoState;
+  static size_t stage_bytes() { return (size_t)(2 * (TM * LDX + 32 * LDX) + 2 * kGroups * 1024) * 4; }
+  __device__ static __forceinline__ char* carve(Smem& sm, char* p) {
+    float* f = reinterpret_cast<float*>(p);
+    sm.XB = f; f += 2 * TM * LDX;
+    sm.WB = f; f += 2 * 32 * LDX;
+    sm.RED = f; f += 2 * kGroups * 1024;
+    return reinterpret_cast<char*>(f);
+  }
+  __device__ static __forceinline__ void init(const Smem&, State&) {}
+  __device__ static __forceinline__ void fini(const Smem&, State&) {}
+  template <class Epi>
+  __device__ static __forceinline__ void gemm_nt(const Smem& sm, State&, const float* __restrict__ W, int ldw, int N,
+                                                 const float* __restrict__ bias, const ASeg* segs, int nseg,
+                                                 const Drop& drop, int rows_valid, bool scan_nan, Epi epi) {
+    fma_gemm_nt<RM>(sm, W, ldw, N, bias, segs, nseg, drop, rows_valid, scan_nan, epi);
+  }
+  template <class Pre, class Epi>
+  __device__ static __forceinline__ void gemm_nn(const Smem& sm, State&, const float* dz, int ldd, int N,
+                                                 const float* __restrict__ W, int ldw, int col0, int J, Pre pre, Epi epi) {
+    fma_gemm_nn<RM>(sm, dz, ldd, N, W, ldw, col0, J, pre, epi);
+  }
+  __device__ static __forceinline__ void gemm_tn(const Smem& sm, State&, const float* dz, int ldd, int N, const ASeg& sg,
+                                                 const Drop& drop, int rows_valid, float* __restrict__ gW, int ldw) {
+    fma_gemm_tn<RM>(sm, dz, ldd, N, sg, drop, rows_valid, gW, ldw);
+  }
+};
+
 // bias gradient: gb[n] += sum_r dz[r][n]
 template <int RM>
 __device__ __forceinline__ void colsum_red(const Smem& sm, const float* dz, int ldd, int N, float* __restrict__ gb) {
@@ -540,9 +579,10 @@ __device__ __forceinline__ unsigned warp_sum_u(unsigned v) {
 // ------------------------------------------------------------------------------------------------
 // the step kernel
 // ------------------------------------------------------------------------------------------------
-template <int RM, bool TRAIN>
+template <class ENG, bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs args) {
-  constexpr int TM = Cfg<RM>::TM;
+  constexpr int RM = ENG::RM;
+  constexpr int TM = ENG::TM;
   const DevPlan& P = *args.plan;
   const int tid = threadIdx.x;
   const int S = P.S, E = P.E, D = P.D, ldS = P.ldS, ldH = P.ldH;
@@ -551,15 +591,13 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
 
   MMN_DYN_SMEM(smem_raw);
   Smem sm;
+  typename ENG::State es;
   {
-    float* f = reinterpret_cast<float*>(smem_raw);
+    float* f = reinterpret_cast<float*>(ENG::carve(sm, smem_raw));   // engine staging first (alignment), then tiles
     sm.S = f; f += TM * ldS;
     sm.T = f; f += TM * ldS;
     sm.A = f; f += TM * ldH;
     sm.B = f; f += TM * ldH;
-    sm.XB = f; f += 2 * TM * LDX;
-    sm.WB = f; f += 2 * 32 * LDX;
-    sm.RED = f; f += 2 * kGroups * 1024;
     sm.ys = reinterpret_cast<int*>(f); f += TM * D;
     sm.rownan = reinterpret_cast<int*>(f); f += TM;
     sm.cnt = reinterpret_cast<int*>(f); f += (E + 1);
@@ -570,6 +608,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
   }
   for (int i = tid; i < P.n_metrics; i += kThreads) sm.met[i] = 0.0;
   for (int i = tid; i < E + 1; i += kThreads) sm.cnt[i] = 0;
+  ENG::init(sm, es);
 
   const long long n_tiles = (args.n_rows + TM - 1) / TM;
   float* slot = TRAIN ? args.stash + (long long)blockIdx.x * args.slot_floats : nullptr;
@@ -612,7 +651,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
           ASeg seg;
           seg.ptr = in; seg.ld = ldin; seg.width = ly.in_dim; seg.kind = SEG_SMEM; seg.wcol = 0;
           const int N = ly.out_dim, act = ly.act;
-          gemm_nt<RM>(sm, params + ly.w_off, ly.ktot, N, params + ly.b_off, &seg, 1, nodrop, rows_valid, false,
+          ENG::gemm_nt(sm, es, params + ly.w_off, ly.ktot, N, params + ly.b_off, &seg, 1, nodrop, rows_valid, false,
                       [&](int r, int n, float z) { out[r * ldH + n] = n < N ? act_fwd(act, z) : 0.f; });
           if (TRAIN)
             stash_store<RM>(slot + (long long)(stash_dec_off(P, k) + dec.stash_off + ly.stash_off) * TM, out, ldH, N);
@@ -713,7 +752,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
             nseg = 2;
           }
           const int N = ly.out_dim, act = ly.act;
-          gemm_nt<RM>(sm, params + ly.w_off, ly.ktot, N, params + ly.b_off, segs, nseg, use_drop ? drop : nodrop,
+          ENG::gemm_nt(sm, es, params + ly.w_off, ly.ktot, N, params + ly.b_off, segs, nseg, use_drop ? drop : nodrop,
                       rows_valid, j == 0,
                       [&](int r, int n, float z) { out[r * ldo + n] = n < N ? act_fwd(act, z) : 0.f; });
           if (TRAIN && !last)
@@ -802,19 +841,19 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
             ASeg seg;
             seg.kind = SEG_STASH; seg.wcol = 0; seg.width = ly.in_dim; seg.ld = ly.in_dim;
             seg.ptr = j == 0 ? sk : slot + dbase + (long long)dec.L[j - 1].stash_off * TM;
-            gemm_tn<RM>(sm, cur, ldH, ly.out_dim, seg, nodrop, TM, grads + ly.w_off, ly.ktot);
+            ENG::gemm_tn(sm, es, cur, ldH, ly.out_dim, seg, nodrop, TM, grads + ly.w_off, ly.ktot);
             if (j > 0) {
               float* other = cur == sm.A ? sm.B : sm.A;
               const float* ast = slot + dbase + (long long)dec.L[j - 1].stash_off * TM;
               const int J = ly.in_dim, pact = dec.L[j - 1].act;
-              gemm_nn<RM>(sm, cur, ldH, ly.out_dim, params + ly.w_off, ly.ktot, 0, J,
+              ENG::gemm_nn(sm, es, cur, ldH, ly.out_dim, params + ly.w_off, ly.ktot, 0, J,
                           [&](int r, int jc) { return jc < J ? __ldcg(ast + r * J + jc) : 0.f; },
                           [&](int r, int jc, float acc, float a) {
                             other[r * ldH + jc] = jc < J ? acc * act_bwd(pact, a) : 0.f;
                           });
               cur = other;
             } else {
-              gemm_nn<RM>(sm, cur, ldH, ly.out_dim, params + ly.w_off, ly.ktot, 0, S,
+              ENG::gemm_nn(sm, es, cur, ldH, ly.out_dim, params + ly.w_off, ly.ktot, 0, S,
                           [&](int, int) { return 0.f; },
                           [&](int r, int jc, float acc, float) {
                             if (jc < S) G[r * ldS + jc] += acc;
@@ -871,18 +910,18 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
           } else {
             seg.kind = SEG_STASH; seg.ptr = slot + ebase + (long long)enc.L[j - 1].stash_off * TM; seg.ld = ly.in_dim;
           }
-          gemm_tn<RM>(sm, cur, ldc, ly.out_dim, seg, use_drop ? drop : nodrop, rows_valid, grads + ly.w_off, ly.ktot);
+          ENG::gemm_tn(sm, es, cur, ldc, ly.out_dim, seg, use_drop ? drop : nodrop, rows_valid, grads + ly.w_off, ly.ktot);
           if (ly.has_state) {
             ASeg s2;
             s2.kind = SEG_STASH; s2.ptr = skm1; s2.ld = S; s2.width = S; s2.wcol = ly.in_dim;
-            gemm_tn<RM>(sm, cur, ldc, ly.out_dim, s2, use_drop ? drop : nodrop, TM, grads + ly.w_off, ly.ktot);
+            ENG::gemm_tn(sm, es, cur, ldc, ly.out_dim, s2, use_drop ? drop : nodrop, TM, grads + ly.w_off, ly.ktot);
           }
           float* other = nullptr;
           if (j > 0) {
             other = cur == sm.A ? sm.B : sm.A;
             const float* ast = slot + ebase + (long long)enc.L[j - 1].stash_off * TM;
             const int J = ly.in_dim, pact = enc.L[j - 1].act;
-            gemm_nn<RM>(sm, cur, ldc, ly.out_dim, params + ly.w_off, ly.ktot, 0, J,
+            ENG::gemm_nn(sm, es, cur, ldc, ly.out_dim, params + ly.w_off, ly.ktot, 0, J,
                         [&](int r, int jc) { return jc < J ? __ldcg(ast + r * J + jc) : 0.f; },
                         [&](int r, int jc, float acc, float a) {
                           other[r * ldH + jc] = jc < J ? acc * act_bwd(pact, a) : 0.f;
@@ -892,7 +931,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
             // carry into G: present rows take dz W_s (through the dropout mask), absent rows keep G;
             // then remove u_k, which belongs to s_{k-1} with the opposite sign (multimodn.py:165,174)
             const int in_dim = ly.in_dim;
-            gemm_nn<RM>(sm, cur, ldc, ly.out_dim, params + ly.w_off, ly.ktot, in_dim, S,
+            ENG::gemm_nn(sm, es, cur, ldc, ly.out_dim, params + ly.w_off, ly.ktot, in_dim, S,
                         [&](int r, int jc) {      // u_k, loaded before the multiply
                           return jc < S ? args.c_sc * (__ldcg(sk + r * S + jc) - __ldcg(skm1 + r * S + jc)) : 0.f;
                         },
@@ -917,6 +956,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
 
   // ---- flush this CTA's metric partials ----
   __syncthreads();
+  ENG::fini(sm, es);
   if (args.metrics) {
     const int nmat = 6 * (E + 1) * D;
     for (int i = tid; i < P.n_metrics; i += kThreads) {

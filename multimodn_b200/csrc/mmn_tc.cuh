@@ -191,6 +191,418 @@ __device__ __forceinline__ void tc_store_quad(float* hi_img, float* lo_img, int 
   *reinterpret_cast<float4*>(lo_img + o) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
 }
 
+// element-wise variant of tc_store_quad (ragged sources staged one float per thread)
+template <bool MN>
+__device__ __forceinline__ void tc_store_elem(float* hi_img, float* lo_img, int r, int c, float v) {
+  const int c4 = c >> 2;
+  const int o = (MN ? ((r >> 2) << 7) + ((r & 3) << 5) + ((((c4 >> 1) ^ (r & 3)) << 3) | ((c4 & 1) << 2))
+                    : ((r >> 3) << 8) + ((r & 7) << 5) + ((c4 ^ (r & 7)) << 2)) + (c & 3);
+  const float h = tf32_hi(v);
+  hi_img[o] = h;
+  lo_img[o] = v - h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-core engine: same three GEMM entry points as FmaEngine, 128-row tiles only.
+// Shared-memory staging (1024-byte aligned, first in the dynamic allocation):
+//   XB 64 KB = 2 buffers x {hi, lo} x [128 x 32] activation chunk images (16 KB each)
+//   WB 32 KB = 2 buffers x {hi, lo} x [64 x 32] weight block images (8 KB each)
+// The weight-gradient GEMM re-purposes them: XB = dz images {hi g0, hi g1, lo g0, lo g1}, WB = one
+// input-chunk image pair {hi, lo}.
+// ------------------------------------------------------------------------------------------------
+struct TcEngine {
+  static constexpr int RM = 4;
+  static constexpr int TM = 128;
+  static constexpr bool kTensor = true;
+  using State = TcState;
+  static size_t stage_bytes() { return 1024 + (size_t)(kTcStageXB + kTcStageWB + 256) * 4 + 32; }
+
+  __device__ static __forceinline__ char* carve(Smem& sm, char* p) {
+    p += (1024 - (smem_u32(p) & 1023)) & 1023;
+    float* f = reinterpret_cast<float*>(p);
+    sm.XB = f; f += kTcStageXB;
+    sm.WB = f; f += kTcStageWB;
+    sm.RED = f; f += 256;
+    sm.bar = reinterpret_cast<unsigned long long*>(f); f += 4;
+    sm.tslot = reinterpret_cast<unsigned*>(f); f += 4;
+    return reinterpret_cast<char*>(f);
+  }
+  __device__ static __forceinline__ void init(const Smem& sm, State& es) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kTcStageXB + kTcStageWB; i += kThreads) sm.XB[i] = 0.f;   // XB and WB are contiguous
+    if (tid == 0) { mbar_init(sm.bar, 1); mbar_init(sm.bar + 1, 1); mbar_fence_init(); }
+    if (tid < 32) tmem_alloc(sm.tslot, kTcTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    es.tmem = *sm.tslot;
+    es.pending[0] = es.pending[1] = 0;
+    es.parity[0] = es.parity[1] = 0;
+  }
+  __device__ static __forceinline__ void fini(const Smem& sm, State& es) {
+    drain(sm, es);
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(es.tmem, kTcTmemCols);
+  }
+  __device__ static __forceinline__ void wait(const Smem& sm, State& es, int b) {
+    if (es.pending[b]) {
+      mbar_wait(sm.bar + b, es.parity[b]);
+      es.parity[b] ^= 1;
+      es.pending[b] = 0;
+    }
+  }
+  __device__ static __forceinline__ void drain(const Smem& sm, State& es) { wait(sm, es, 0); wait(sm, es, 1); }
+
+  // ---- weight block: [nrows <= 64][ncols <= 32] of row-major W -> K-major image pair (rows = n) ----
+  __device__ static __forceinline__ void w_load_k(float (&w)[8], const float* __restrict__ W, int ldw, int row0, int nrows,
+                                                  int col0, int ncols, bool vec) {
+    const int t = threadIdx.x;
+    if (vec) {
+      const int c4 = (t & 7) * 4;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int r = (t >> 3) + 32 * i;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nrows && c4 < ncols) {
+          const float* p = W + (long long)(row0 + r) * ldw + col0 + c4;
+          if (c4 + 3 < ncols) q = __ldg(reinterpret_cast<const float4*>(p));
+          else { q.x = __ldg(p); if (c4 + 1 < ncols) q.y = __ldg(p + 1); if (c4 + 2 < ncols) q.z = __ldg(p + 2); }
+        }
+        w[4 * i] = q.x; w[4 * i + 1] = q.y; w[4 * i + 2] = q.z; w[4 * i + 3] = q.w;
+      }
+    } else {
+      const int c = t & 31;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = (t >> 5) + 8 * i;
+        w[i] = (r < nrows && c < ncols) ? __ldg(W + (long long)(row0 + r) * ldw + col0 + c) : 0.f;
+      }
+    }
+  }
+  __device__ static __forceinline__ void w_store_k(float* hi, float* lo, const float (&w)[8], bool vec) {
+    const int t = threadIdx.x;
+    if (vec) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        tc_store_quad<false>(hi, lo, (t >> 3) + 32 * i, t & 7, make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tc_store_elem<false>(hi, lo, (t >> 5) + 8 * i, t & 31, w[i]);
+    }
+  }
+  // ---- weight block for the data gradient: rows n (contraction) x up to 64 output columns j ->
+  //      MN-major image pairs, one 4 KB image per group of 32 columns ----
+  __device__ static __forceinline__ void w_load_mn(float (&w)[8], const float* __restrict__ W, int ldw, int row0, int nrows,
+                                                   int col0, int ncols, bool vec) {
+    const int t = threadIdx.x;
+    if (vec) {
+      const int c4 = (t & 15) * 4;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int r = (t >> 4) + 16 * i;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nrows && c4 < ncols) {
+          const float* p = W + (long long)(row0 + r) * ldw + col0 + c4;
+          if (c4 + 3 < ncols) q = __ldg(reinterpret_cast<const float4*>(p));
+          else { q.x = __ldg(p); if (c4 + 1 < ncols) q.y = __ldg(p + 1); if (c4 + 2 < ncols) q.z = __ldg(p + 2); }
+        }
+        w[4 * i] = q.x; w[4 * i + 1] = q.y; w[4 * i + 2] = q.z; w[4 * i + 3] = q.w;
+      }
+    } else {
+      const int c = t & 63;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = (t >> 6) + 4 * i;
+        w[i] = (r < nrows && c < ncols) ? __ldg(W + (long long)(row0 + r) * ldw + col0 + c) : 0.f;
+      }
+    }
+  }
+  __device__ static __forceinline__ void w_store_mn(float* hi, float* lo, const float (&w)[8], bool vec) {
+    const int t = threadIdx.x;
+    if (vec) {
+      const int c4 = t & 15, g = c4 >> 3;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        tc_store_quad<true>(hi + g * 1024, lo + g * 1024, (t >> 4) + 16 * i, c4 & 7,
+                            make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]));
+    } else {
+      const int c = t & 63, g = c >> 5;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tc_store_elem<true>(hi + g * 1024, lo + g * 1024, (t >> 6) + 4 * i, c & 31, w[i]);
+    }
+  }
+
+  // ---- activation chunk [128 x 32] -> image pair.  Global sources arrive in registers (a_chunk_load);
+  //      shared-memory tiles are read here.  NaN scan / sanitise for x, dropout when enabled. ----
+  template <bool MN>
+  __device__ static __forceinline__ void a_store(float* hi, float* lo, float (&v)[16], const Smem& sm, const ASeg& sg,
+                                                 int k0, int kw, const Drop& drop, bool scan_nan, bool vec) {
+    const int t = threadIdx.x;
+    const bool from_smem = sg.kind == SEG_SMEM || sg.kind == SEG_SMEM_STAGED;
+    if (vec || from_smem) {
+      const int c4 = t & 7, r0 = t >> 3;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + 32 * i;
+        float4 q;
+        if (from_smem) q = *reinterpret_cast<const float4*>(sg.ptr + (long long)r * sg.ld + k0 + 4 * c4);   // zero-padded tile
+        else q = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        if (sg.kind == SEG_X) {
+          bool bad = false;
+          if (q.x != q.x) { bad = true; q.x = 0.f; }
+          if (q.y != q.y) { bad = true; q.y = 0.f; }
+          if (q.z != q.z) { bad = true; q.z = 0.f; }
+          if (q.w != q.w) { bad = true; q.w = 0.f; }
+          if (bad && scan_nan) sm.rownan[r] = 1;
+        }
+        if (drop.enabled) {
+          const unsigned col = (unsigned)(sg.wcol + k0 + 4 * c4), row = drop.row_base + (unsigned)r;
+          if ((col & 1u) == 0) {
+            const unsigned h0 = mmn_dropout_hash(drop.seed_mix, row, col >> 1);
+            const unsigned h1 = mmn_dropout_hash(drop.seed_mix, row, (col >> 1) + 1);
+            q.x = (h0 & 0xffffu) >= drop.thr ? q.x * drop.scale : 0.f;
+            q.y = (h0 >> 16) >= drop.thr ? q.y * drop.scale : 0.f;
+            q.z = (h1 & 0xffffu) >= drop.thr ? q.z * drop.scale : 0.f;
+            q.w = (h1 >> 16) >= drop.thr ? q.w * drop.scale : 0.f;
+          } else {
+            q.x = mmn_dropout_keep(drop.seed_mix, row, col + 0, drop.thr) ? q.x * drop.scale : 0.f;
+            q.y = mmn_dropout_keep(drop.seed_mix, row, col + 1, drop.thr) ? q.y * drop.scale : 0.f;
+            q.z = mmn_dropout_keep(drop.seed_mix, row, col + 2, drop.thr) ? q.z * drop.scale : 0.f;
+            q.w = mmn_dropout_keep(drop.seed_mix, row, col + 3, drop.thr) ? q.w * drop.scale : 0.f;
+          }
+          if (4 * c4 + 0 >= kw) q.x = 0.f;
+          if (4 * c4 + 1 >= kw) q.y = 0.f;
+          if (4 * c4 + 2 >= kw) q.z = 0.f;
+          if (4 * c4 + 3 >= kw) q.w = 0.f;
+        }
+        tc_store_quad<MN>(hi, lo, r, c4, q);
+      }
+    } else {
+      const int c = t & 31, r0 = t >> 5;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int r = r0 + 8 * i;
+        float x = v[i];
+        if (sg.kind == SEG_X && x != x) {
+          if (scan_nan) sm.rownan[r] = 1;
+          x = 0.f;
+        }
+        if (drop.enabled && c < kw)
+          x = mmn_dropout_keep(drop.seed_mix, drop.row_base + (unsigned)r, (unsigned)(sg.wcol + k0 + c), drop.thr)
+                  ? x * drop.scale : 0.f;
+        tc_store_elem<MN>(hi, lo, r, c, x);
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // out[r][n] = bias[n] + sum_seg sum_k a[r][k] W[n][wcol + k]      (A, W K-major; N pass of 32 / 64)
+  // ------------------------------------------------------------------------------------------------
+  template <class Epi>
+  __device__ static __forceinline__ void gemm_nt(const Smem& sm, State& es, const float* __restrict__ W, int ldw, int N,
+                                                 const float* __restrict__ bias, const ASeg* segs, int nseg,
+                                                 const Drop& drop, int rows_valid, bool scan_nan, Epi epi) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, half = warp >> 2;
+    bool avec[2];
+    avec[0] = seg_vec_ok(segs[0]);
+    avec[1] = nseg > 1 ? seg_vec_ok(segs[1]) : false;
+    for (int n0 = 0; n0 < N; n0 += 64) {
+      const int nrows = min(64, N - n0);
+      const int Np = nrows <= 32 ? 32 : 64;
+      float wr[8], ar[16];
+      ChunkIt it{0, 0};
+      bool wv = w_vec_ok(W, ldw, segs[0].wcol);
+      w_load_k(wr, W, ldw, n0, nrows, segs[0].wcol, min(KC, segs[0].width), wv);
+      a_chunk_load<4>(ar, segs[0], 0, min(KC, segs[0].width), rows_valid, avec[0]);
+      int buf = 0;
+      unsigned first = 1;
+      while (it.valid(nseg)) {
+        const ASeg sg = segs[it.s];
+        const int kw = min(KC, sg.width - it.k0);
+        float* xh = sm.XB + buf * 8192;
+        float* wh = sm.WB + buf * 4096;
+        wait(sm, es, buf);                       // MMAs that read this buffer pair two chunks ago are done
+        w_store_k(wh, wh + 2048, wr, wv);
+        a_store<false>(xh, xh + 4096, ar, sm, sg, it.k0, kw, drop, scan_nan && n0 == 0, avec[it.s]);
+        ChunkIt nx = it;
+        nx.next(segs);
+        if (nx.valid(nseg)) {
+          const ASeg& ns = segs[nx.s];
+          const int nkw = min(KC, ns.width - nx.k0);
+          wv = w_vec_ok(W, ldw, ns.wcol + nx.k0);
+          w_load_k(wr, W, ldw, n0, nrows, ns.wcol + nx.k0, nkw, wv);
+          a_chunk_load<4>(ar, ns, nx.k0, nkw, rows_valid, avec[nx.s]);
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+          tc_fence_after();
+          const unsigned id = umma_idesc_tf32(128, Np, 0, 0);
+          const unsigned ah = smem_u32(xh), al = smem_u32(xh + 4096), bh = smem_u32(wh), bl = smem_u32(wh + 2048);
+          const int nj = (kw + 7) >> 3;
+          for (int j = 0; j < nj; ++j) {
+            umma_tf32(es.tmem, umma_desc_k(al, j), umma_desc_k(bh, j), id, (first && j == 0) ? 0u : 1u);
+            umma_tf32(es.tmem, umma_desc_k(ah, j), umma_desc_k(bl, j), id, 1u);
+            umma_tf32(es.tmem, umma_desc_k(ah, j), umma_desc_k(bh, j), id, 1u);
+          }
+          umma_commit(sm.bar + buf);
+        }
+        es.pending[buf] = 1;
+        first = 0;
+        it = nx;
+        buf ^= 1;
+      }
+      wait(sm, es, buf);          // older commit first (in-order completion), then the last one
+      wait(sm, es, buf ^ 1);
+      tc_fence_after();
+      const int r = 32 * q + lane;
+      for (int c0 = half * (Np >> 1); c0 < (half + 1) * (Np >> 1); c0 += 16) {
+        float v[16];
+        tmem_ld16(es.tmem + ((unsigned)(32 * q) << 16) + c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int n = n0 + c0 + i;
+          epi(r, n, v[i] + (n < N ? __ldg(bias + n) : 0.f));
+        }
+      }
+      tc_fence_before();
+      __syncthreads();            // accumulator columns and staging buffers are free again
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // out[r][j] = sum_n dz[r][n] W[n][col0 + j]      (dz K-major from its shared tile, W MN-major)
+  // ------------------------------------------------------------------------------------------------
+  template <class Pre, class Epi>
+  __device__ static __forceinline__ void gemm_nn(const Smem& sm, State& es, const float* dz, int ldd, int N,
+                                                 const float* __restrict__ W, int ldw, int col0, int J, Pre pre, Epi epi) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, half = warp >> 2;
+    const int r = 32 * q + lane;
+    Drop nodrop;
+    nodrop.enabled = 0; nodrop.seed_mix = 0; nodrop.thr = 0; nodrop.row_base = 0; nodrop.scale = 1.f;
+    for (int j0 = 0; j0 < J; j0 += 64) {
+      const int jw = min(64, J - j0);
+      const int Np = jw <= 32 ? 32 : 64;
+      float pv[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) pv[i] = i < (Np >> 1) ? pre(r, j0 + half * (Np >> 1) + i) : 0.f;
+      const bool wv = w_vec_ok(W, ldw, col0 + j0);
+      float wr[8], dummy[16];
+      w_load_mn(wr, W, ldw, 0, min(32, N), col0 + j0, jw, wv);
+      int buf = 0;
+      unsigned first = 1;
+      for (int n0 = 0; n0 < N; n0 += 32) {
+        const int nw = min(32, N - n0);
+        float* xh = sm.XB + buf * 8192;
+        float* wh = sm.WB + buf * 4096;
+        wait(sm, es, buf);
+        w_store_mn(wh, wh + 2048, wr, wv);
+        ASeg sg;
+        sg.ptr = dz; sg.ld = ldd; sg.width = N; sg.kind = SEG_SMEM; sg.wcol = 0;
+        a_store<false>(xh, xh + 4096, dummy, sm, sg, n0, nw, nodrop, false, false);
+        if (n0 + 32 < N) w_load_mn(wr, W, ldw, n0 + 32, min(32, N - n0 - 32), col0 + j0, jw, wv);
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+          tc_fence_after();
+          const unsigned id = umma_idesc_tf32(128, Np, 0, 1);
+          const unsigned ah = smem_u32(xh), al = smem_u32(xh + 4096), bh = smem_u32(wh), bl = smem_u32(wh + 2048);
+          const int nj = (nw + 7) >> 3;
+          for (int j = 0; j < nj; ++j) {
+            umma_tf32(es.tmem, umma_desc_k(al, j), umma_desc_mn(bh, j, 4096), id, (first && j == 0) ? 0u : 1u);
+            umma_tf32(es.tmem, umma_desc_k(ah, j), umma_desc_mn(bl, j, 4096), id, 1u);
+            umma_tf32(es.tmem, umma_desc_k(ah, j), umma_desc_mn(bh, j, 4096), id, 1u);
+          }
+          umma_commit(sm.bar + buf);
+        }
+        es.pending[buf] = 1;
+        first = 0;
+        buf ^= 1;
+      }
+      wait(sm, es, buf);
+      wait(sm, es, buf ^ 1);
+      tc_fence_after();
+      for (int c0 = 0; c0 < (Np >> 1); c0 += 16) {
+        float v[16];
+        tmem_ld16(es.tmem + ((unsigned)(32 * q) << 16) + half * (Np >> 1) + c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) epi(r, j0 + half * (Np >> 1) + c0 + i, v[i], pv[c0 + i]);
+      }
+      tc_fence_before();
+      __syncthreads();
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // gW[n][wcol + k] += sum_r dz[r][n] a[r][k]      (both operands MN-major, contraction = the 128 rows)
+  // D[n][k]: lanes = output rows n (two 32-column groups of dz per pass), columns = the 32 k of a chunk.
+  // ------------------------------------------------------------------------------------------------
+  __device__ static __forceinline__ void gemm_tn(const Smem& sm, State& es, const float* dz, int ldd, int N, const ASeg& sg,
+                                                 const Drop& drop, int rows_valid, float* __restrict__ gW, int ldw) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, half = warp >> 2;
+    const bool vec_ok = ((ldw & 3) == 0) && ((sg.wcol & 3) == 0) && ((reinterpret_cast<size_t>(gW) & 15) == 0);
+    const bool avec = seg_vec_ok(sg);
+    const int Npad = (N + 31) & ~31;
+    for (int nb0 = 0; nb0 < N; nb0 += 64) {
+      const int ngroups = min(2, (Npad - nb0) >> 5);
+      float ar[16];
+      a_chunk_load<4>(ar, sg, 0, min(KC, sg.width), rows_valid, avec);
+      drain(sm, es);
+      __syncthreads();
+      // dz column groups -> MN-major A images: XB = {hi g0, hi g1, lo g0, lo g1}
+      for (int idx = tid; idx < 128 * 8 * ngroups; idx += kThreads) {
+        const int g = idx >> 10, rr = (idx >> 3) & 127, c4 = idx & 7;
+        const float4 v = *reinterpret_cast<const float4*>(dz + rr * ldd + nb0 + 32 * g + 4 * c4);
+        tc_store_quad<true>(sm.XB + g * 4096, sm.XB + 8192 + g * 4096, rr, c4, v);
+      }
+      for (int k0 = 0; k0 < sg.width; k0 += KC) {
+        const int kw = min(KC, sg.width - k0);
+        wait(sm, es, 0);
+        a_store<true>(sm.WB, sm.WB + 4096, ar, sm, sg, k0, kw, drop, false, avec);
+        if (k0 + KC < sg.width) a_chunk_load<4>(ar, sg, k0 + KC, min(KC, sg.width - k0 - KC), rows_valid, avec);
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+          tc_fence_after();
+          const unsigned id = umma_idesc_tf32(128, 32, 1, 1);
+          const unsigned ah = smem_u32(sm.XB), al = smem_u32(sm.XB + 8192), bh = smem_u32(sm.WB), bl = smem_u32(sm.WB + 4096);
+          for (int j = 0; j < 16; ++j) {
+            umma_tf32(es.tmem, umma_desc_mn(al, j, 16384), umma_desc_mn(bh, j, 16384), id, j ? 1u : 0u);
+            umma_tf32(es.tmem, umma_desc_mn(ah, j, 16384), umma_desc_mn(bl, j, 16384), id, 1u);
+            umma_tf32(es.tmem, umma_desc_mn(ah, j, 16384), umma_desc_mn(bh, j, 16384), id, 1u);
+          }
+          umma_commit(sm.bar);
+        }
+        es.pending[0] = 1;
+        wait(sm, es, 0);
+        tc_fence_after();
+        {
+          float v[16];
+          tmem_ld16(es.tmem + ((unsigned)(32 * q) << 16) + half * 16, v);
+          const int n = nb0 + 32 * q + lane;
+          if (q < ngroups && n < N) {
+            const int kc = k0 + half * 16;
+            float* dst = gW + (long long)n * ldw + sg.wcol + kc;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              if (vec_ok && kc + i + 3 < sg.width) {
+                atomicAdd(reinterpret_cast<float4*>(dst + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+              } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (kc + i + u < sg.width) atomicAdd(dst + i + u, v[i + u]);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+      }
+      __syncthreads();
+    }
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
 // self-test of the three operand configurations the engine uses (validated on the GPU by
 // tests/test_gpu_tc_selftest.py): mode 0  D[r][n] = sum_k A[r][k] B[n][k]   (A, B K-major)

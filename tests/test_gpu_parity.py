@@ -218,3 +218,24 @@ def test_c5_predict_permutation_properties():
         first = int(perm[0])
         alone = model.predict([dev[first]], np.array([first]))
         assert (out[first + 1] == alone[first + 1]).all()
+
+
+# ---- both GEMM engines: the default is the tcgen05 3xTF32 engine where it fits; force the FP32-FMA one ----
+@pytest.mark.parametrize("name", ["multi_tile_ragged", "mnar_rows", "dropout_mnar"])
+def test_oracle_case_fma_engine(monkeypatch, name):
+    monkeypatch.setenv("MMN_ENGINE", "fma")
+    model = run_parity_case(name, DEV)
+    from multimodn_b200 import _lib
+    assert _lib.get_lib().dll.mmn_plan_engine(model.runtime().plan) == 0
+
+
+def test_golden_c2_full_dims_fma_engine(monkeypatch):
+    monkeypatch.setenv("MMN_ENGINE", "fma")
+    run_golden("c2_mimic_full", ["a", "b"], "row")
+
+
+def test_default_engine_is_tensor_core_for_c2():
+    from multimodn_b200 import _lib
+    fx = load_golden("c2_mimic_full")
+    model = model_from_spec(golden_spec(fx), 1.0, 0.3, DEV, "row")
+    assert _lib.get_lib().dll.mmn_plan_engine(model.runtime().plan) == 1
