@@ -246,7 +246,7 @@ int launch_engine(const mmn_plan* plan, const StepArgs& a, void* stream) {
   const int grid = grid_for(plan, a.n_rows);
   auto kfn = mmn_step_kernel<ENG, TRAIN>;
   MMN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  MMN_LAUNCH(kfn, dim3(grid), dim3(kThreads), smem, stream, a);
+  MMN_LAUNCH(kfn, dim3(grid), dim3(ENG::kBlockThreads), smem, stream, a);
   MMN_CUDA(cudaGetLastError());
   return 0;
 }

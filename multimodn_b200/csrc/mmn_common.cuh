@@ -11,6 +11,8 @@
 #define MMN_LAUNCH(kernel, grid, block, smem, stream, ...) \
   kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
 #define MMN_DYN_SMEM(name) extern __shared__ __align__(16) char name[]
+// barrier over the 256 worker threads only (the tensor-core engine adds a 9th, MMA-issuing warp)
+#define MMN_WSYNC() asm volatile("bar.sync 1, 256;" ::: "memory")
 #endif
 
 namespace mmn {

@@ -269,7 +269,7 @@ __device__ __forceinline__ void fma_gemm_nt(const Smem& sm, const float* __restr
     w_block_load(wr, W, ldw, n0, nrows, segs[0].wcol, min(KC, segs[0].width), wv);
     a_chunk_load<RM>(ar, segs[0], 0, min(KC, segs[0].width), rows_valid, avec[0]);
     int buf = 0;
-    __syncthreads();                    // previous users of the staging buffers are done
+    MMN_WSYNC();                    // previous users of the staging buffers are done
     while (it.valid(nseg)) {
       const ASeg sg = segs[it.s];
       const int kw = min(KC, sg.width - it.k0);
@@ -295,7 +295,7 @@ __device__ __forceinline__ void fma_gemm_nt(const Smem& sm, const float* __restr
         w_block_load(wr, W, ldw, n0, nrows, ns.wcol + nx.k0, nkw, wv);
         a_chunk_load<RM>(ar, ns, nx.k0, nkw, rows_valid, avec[nx.s]);
       }
-      __syncthreads();
+      MMN_WSYNC();
       const int nq = (kw + 3) >> 2;
 #pragma unroll 2
       for (int q = 0; q < nq; ++q) {
@@ -322,7 +322,7 @@ __device__ __forceinline__ void fma_gemm_nt(const Smem& sm, const float* __restr
 #pragma unroll
       for (int j = 0; j < 4; ++j) epi(ty + 32 * i, n0 + tx + 8 * j, acc[i][j] + bj[j]);
   }
-  __syncthreads();
+  MMN_WSYNC();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -349,13 +349,13 @@ __device__ __forceinline__ void fma_gemm_nn(const Smem& sm, const float* dz, int
     float wr[4];
     w_block_load(wr, W, ldw, 0, min(32, N), col0 + j0, jw, wv);
     int buf = 0;
-    __syncthreads();
+    MMN_WSYNC();
     for (int n0 = 0; n0 < N; n0 += 32) {
       const int nw = min(32, N - n0);
       float* WBb = sm.WB + buf * (32 * LDX);
       w_block_store(WBb, wr, wv);
       if (n0 + 32 < N) w_block_load(wr, W, ldw, n0 + 32, min(32, N - n0 - 32), col0 + j0, jw, wv);
-      __syncthreads();
+      MMN_WSYNC();
       const int nq = (nw + 3) >> 2;
 #pragma unroll 2
       for (int q = 0; q < nq; ++q) {
@@ -383,7 +383,7 @@ __device__ __forceinline__ void fma_gemm_nn(const Smem& sm, const float* dz, int
 #pragma unroll
       for (int c = 0; c < 4; ++c) epi(ty + 32 * i, j0 + 4 * tx + c, acc[i][c], pv[i][c]);
   }
-  __syncthreads();
+  MMN_WSYNC();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -404,7 +404,7 @@ __device__ __forceinline__ void fma_gemm_tn(const Smem& sm, const float* dz, int
   const int nnb = (N + 31) >> 5;
   float ar[4 * RM];
   a_chunk_load<RM>(ar, sg, 0, min(KC, sg.width), rows_valid, avec);
-  __syncthreads();                 // previous users of XB / RED are done
+  MMN_WSYNC();                 // previous users of XB / RED are done
   int xbuf = 0, rbuf = 0;
   // software pipeline over (chunk, n-block) items: the reduction of item i-1 runs after the sync of item i
   int pend_n0 = -1, pend_k0 = 0, pend_rbuf = 0;
@@ -447,7 +447,7 @@ __device__ __forceinline__ void fma_gemm_tn(const Smem& sm, const float* dz, int
     if (k0 + KC < sg.width) a_chunk_load<RM>(ar, sg, k0 + KC, min(KC, sg.width - k0 - KC), rows_valid, avec);
     for (int nb = 0; nb < nnb; ++nb) {
       const int n0 = nb * 32;
-      __syncthreads();             // chunk visible; RED of the pending item complete
+      MMN_WSYNC();             // chunk visible; RED of the pending item complete
       if (pend_n0 >= 0) flush(pend_n0, pend_k0, pend_rbuf);
       float acc[4][4];
 #pragma unroll
@@ -476,7 +476,7 @@ __device__ __forceinline__ void fma_gemm_tn(const Smem& sm, const float* dz, int
       rbuf ^= 1;
     }
   }
-  __syncthreads();
+  MMN_WSYNC();
   if (pend_n0 >= 0) flush(pend_n0, pend_k0, pend_rbuf);
 }
 
@@ -489,7 +489,9 @@ struct FmaEngine {
   static constexpr int RM = RM_;
   static constexpr int TM = 32 * RM_;
   static constexpr bool kTensor = false;
+  static constexpr int kBlockThreads = kThreads;
   using State = NoState;
+  __device__ static __forceinline__ void issuer_loop(const Smem&, State&) {}
   static size_t stage_bytes() { return (size_t)(2 * (TM * LDX + 32 * LDX) + 2 * kGroups * 1024) * 4; }
   __device__ static __forceinline__ char* carve(Smem& sm, char* p) {
     float* f = reinterpret_cast<float*>(p);
@@ -525,9 +527,9 @@ __device__ __forceinline__ void colsum_red(const Smem& sm, const float* dz, int 
   for (int n0 = 0; n0 < N; n0 += 32) {
     float s = 0.f;
     for (int r = part; r < TM; r += 8) s += dz[r * ldd + n0 + c];
-    __syncthreads();
+    MMN_WSYNC();
     sm.RED[part * 32 + c] = s;
-    __syncthreads();
+    MMN_WSYNC();
     if (tid < 32 && n0 + tid < N) {
       float tot = 0.f;
 #pragma unroll
@@ -535,7 +537,7 @@ __device__ __forceinline__ void colsum_red(const Smem& sm, const float* dz, int 
       atomicAdd(gb + n0 + tid, tot);
     }
   }
-  __syncthreads();
+  MMN_WSYNC();
 }
 
 // walks idx = tid, tid + kThreads, ... of a [rows x w] index space as (r, c) without a division per step
@@ -580,7 +582,7 @@ __device__ __forceinline__ unsigned warp_sum_u(unsigned v) {
 // the step kernel
 // ------------------------------------------------------------------------------------------------
 template <class ENG, bool TRAIN>
-__global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs args) {
+__global__ void __launch_bounds__(ENG::kBlockThreads, 1) mmn_step_kernel(const StepArgs args) {
   constexpr int RM = ENG::RM;
   constexpr int TM = ENG::TM;
   const DevPlan& P = *args.plan;
@@ -609,6 +611,10 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
   for (int i = tid; i < P.n_metrics; i += kThreads) sm.met[i] = 0.0;
   for (int i = tid; i < E + 1; i += kThreads) sm.cnt[i] = 0;
   ENG::init(sm, es);
+  if (ENG::kTensor && threadIdx.x >= kThreads) {      // 9th warp: issues the tensor-core MMAs
+    ENG::issuer_loop(sm, es);
+    return;
+  }
 
   const long long n_tiles = (args.n_rows + TM - 1) / TM;
   float* slot = TRAIN ? args.stash + (long long)blockIdx.x * args.slot_floats : nullptr;
@@ -618,7 +624,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long row0 = tile * TM;
     const int rows_valid = (int)min((long long)TM, args.n_rows - row0);
-    __syncthreads();
+    MMN_WSYNC();
 
     // ---- tile prologue: targets, initial state (state.py:29-32), masks ----
     if (args.targets) {
@@ -634,9 +640,9 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
       sm.S[idx] = c < S ? __ldg(params + P.init_off + c) : 0.f;
     }
     for (int r = tid; r < TM; r += kThreads) sm.present[r] = r < rows_valid;
-    if (tid == 0) sm.tile_any[0] = 1;
+    for (int i = tid; i < E + 1; i += kThreads) sm.tile_any[i] = i == 0;
     if (tid < TM && tid < rows_valid) atomicAdd(&sm.cnt[0], 1);
-    __syncthreads();
+    MMN_WSYNC();
     if (TRAIN) stash_store<RM>(slot + (long long)stash_state_off(P, 0) * TM, sm.S, ldS, S);
 
     // ---- decoders on the current state (multimodn.py:141-157, 176-191) ----
@@ -707,7 +713,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
             }
           }
         }
-        __syncthreads();
+        MMN_WSYNC();
       }
     };
     decoders_forward(0, 0, false);
@@ -718,7 +724,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
       const DevEncoder& enc = P.enc[e];
       const bool skip = args.skip_flags && args.skip_flags[k - 1] != 0;   // reference batch-level rule
       for (int r = tid; r < TM; r += kThreads) sm.rownan[r] = 0;
-      __syncthreads();
+      MMN_WSYNC();
       if (!skip) {
         Drop drop = nodrop;
         if (TRAIN && args.training && enc.p_drop > 0.f && enc.L[0].has_state) {
@@ -762,14 +768,13 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
         }
       }
       // per-row select (missing rows keep their state bit for bit) + state-change sum (multimodn.py:174)
-      int any = 0;
       if (tid < TM) {
         const bool pr = !skip && tid < rows_valid && sm.rownan[tid] == 0;
         sm.present[k * TM + tid] = pr;
-        if (pr) { atomicAdd(&sm.cnt[e + 1], 1); any = 1; }
+        if (pr) { atomicAdd(&sm.cnt[e + 1], 1); sm.tile_any[k] = 1; }
       }
-      any = __syncthreads_or(any);
-      if (tid == 0) sm.tile_any[k] = any;
+      MMN_WSYNC();
+      const int any = sm.tile_any[k];
       if (any) {
         float sc = 0.f;
         for (RowCol it(S); it.r < TM; it.next()) {
@@ -783,7 +788,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
         sc = warp_sum(sc);
         if ((tid & 31) == 0 && TRAIN) atomicAdd(&sm.met[met_sc(P, e)], (double)sc);
       }
-      __syncthreads();
+      MMN_WSYNC();
       if (TRAIN) stash_store<RM>(slot + (long long)stash_state_off(P, k) * TM, sm.S, ldS, S);
       decoders_forward(k, e + 1, e == E - 1);
     }
@@ -797,11 +802,11 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
     // holds dLoss/ds_k for the tile.
     // =============================================================================================
     if (TRAIN) {
-      __syncthreads();
+      MMN_WSYNC();
       float* G = sm.S;
       float* grads = args.grads;
       for (int idx = tid; idx < TM * ldS; idx += kThreads) G[idx] = 0.f;
-      __syncthreads();
+      MMN_WSYNC();
 
       auto decoders_backward = [&](int k) {
         const float* sk = slot + (long long)stash_state_off(P, k) * TM;
@@ -832,7 +837,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
                 sm.A[r * ldH + c] = v;
               }
             }
-            __syncthreads();
+            MMN_WSYNC();
           }
           float* cur = sm.A;
           for (int j = nl - 1; j >= 0; --j) {
@@ -886,7 +891,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
             }
             sm.T[r * ldS + c] = dzv;
           }
-          __syncthreads();
+          MMN_WSYNC();
         }
         Drop drop = nodrop;
         if (args.training && enc.p_drop > 0.f && enc.L[0].has_state) {
@@ -955,7 +960,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmn_step_kernel(const StepArgs ar
   }
 
   // ---- flush this CTA's metric partials ----
-  __syncthreads();
+  MMN_WSYNC();
   ENG::fini(sm, es);
   if (args.metrics) {
     const int nmat = 6 * (E + 1) * D;

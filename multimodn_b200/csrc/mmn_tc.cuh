@@ -59,10 +59,17 @@ __device__ __forceinline__ unsigned umma_idesc_tf32(int M, int N, int a_mn_major
          ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
 }
 
-struct TcState {        // identical in every thread of the CTA
+struct TcState {        // identical in every worker thread of the CTA
   unsigned tmem;        // TMEM base address of the accumulator columns
-  unsigned pending[2];  // an uncollected tcgen05.commit is outstanding on mbarrier b
+  unsigned seq;         // chunks posted so far; chunk i uses staging slot / mbarrier pair i & 1
+  unsigned pending[2];  // an uncollected tcgen05.commit is outstanding on done[slot]
   unsigned parity[2];
+};
+// One staged chunk handed to the MMA-issuing warp: nj k-slices, three MMAs each (lo*hi, hi*lo, hi*hi).
+struct TcCmd {
+  unsigned long long a_hi, a_lo, b_hi, b_lo;   // shared-memory descriptors of k-slice 0
+  unsigned a_step, b_step;                     // added to the descriptors' start-address field per k-slice
+  unsigned idesc, tmem, nj, first, quit, pad;
 };
 
 #ifndef MMN_EMU
@@ -85,6 +92,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     if (done) return;
     if (spins > (1u << 24)) __trap();
   }
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -147,7 +157,15 @@ inline float operand(unsigned long long desc, int mn_major, int mn, int k) {
 static inline unsigned smem_u32(const void* p) { return (unsigned)((const char*)p - emu::st().dyn_smem); }
 // mbarrier model: the word counts completed phases; a phase with parity P is complete once the count's
 // low bit differs from P (tcgen05.commit completes its phase immediately: the model's MMAs are synchronous)
-static inline void mbar_init(unsigned long long* bar, unsigned) { *bar = 0; }
+// word layout: [0,32) completed phases, [32,48) expected arrivals, [48,64) arrivals of the current phase
+static inline void mbar_init(unsigned long long* bar, unsigned count) { *bar = (unsigned long long)count << 32; }
+static inline void mbar_arrive(unsigned long long* bar) {
+  unsigned long long w = *bar;
+  const unsigned expected = (unsigned)((w >> 32) & 0xFFFF), arrived = (unsigned)(w >> 48) + 1;
+  if (arrived == expected) w = ((w & 0x0000FFFFFFFFFFFFull) + 1);       // phase complete, arrivals reset
+  else w = (w & 0x0000FFFFFFFFFFFFull) | ((unsigned long long)arrived << 48);
+  *bar = w;
+}
 static inline void mbar_fence_init() {}
 static inline void mbar_wait(unsigned long long* bar, unsigned parity) {
   while (((*bar) & 1ull) == (unsigned long long)parity) emu::yield();
@@ -169,7 +187,7 @@ static inline void umma_tf32(unsigned tmem_d, unsigned long long adesc, unsigned
       tcemu::tmem()[m][col0 + n] = s;
     }
 }
-static inline void umma_commit(unsigned long long* bar) { *bar += 1; }
+static inline void umma_commit(unsigned long long* bar) { mbar_arrive(bar); }
 static inline void tmem_ld16(unsigned taddr, float (&v)[16]) {
   const int lane = (taddr >> 16) + (threadIdx.x & 31), col = taddr & 0xFFFF;
   for (int i = 0; i < 16; ++i) v[i] = tcemu::tmem()[lane][col + i];
@@ -214,8 +232,16 @@ struct TcEngine {
   static constexpr int RM = 4;
   static constexpr int TM = 128;
   static constexpr bool kTensor = true;
+  static constexpr int kBlockThreads = kThreads + 32;     // 8 worker warps + the MMA-issuing warp
   using State = TcState;
-  static size_t stage_bytes() { return 1024 + (size_t)(kTcStageXB + kTcStageWB + 256) * 4 + 32; }
+  static size_t stage_bytes() { return 1024 + (size_t)(kTcStageXB + kTcStageWB + 256) * 4 + 64 + 2 * sizeof(TcCmd); }
+
+  // mbarriers: full[2] (256 worker arrivals: chunk staged) then done[2] (1 arrival: tcgen05.commit)
+  __device__ static __forceinline__ unsigned long long* full_bar(const Smem& sm, int slot) { return sm.bar + slot; }
+  __device__ static __forceinline__ unsigned long long* done_bar(const Smem& sm, int slot) { return sm.bar + 2 + slot; }
+  __device__ static __forceinline__ TcCmd* cmd_slot(const Smem& sm, int slot) {
+    return reinterpret_cast<TcCmd*>(sm.bar + 4) + slot;
+  }
 
   __device__ static __forceinline__ char* carve(Smem& sm, char* p) {
     p += (1024 - (smem_u32(p) & 1023)) & 1023;
@@ -223,36 +249,94 @@ struct TcEngine {
     sm.XB = f; f += kTcStageXB;
     sm.WB = f; f += kTcStageWB;
     sm.RED = f; f += 256;
-    sm.bar = reinterpret_cast<unsigned long long*>(f); f += 4;
-    sm.tslot = reinterpret_cast<unsigned*>(f); f += 4;
-    return reinterpret_cast<char*>(f);
+    sm.bar = reinterpret_cast<unsigned long long*>(f);
+    char* q = reinterpret_cast<char*>(sm.bar + 4) + 2 * sizeof(TcCmd);
+    sm.tslot = reinterpret_cast<unsigned*>(q);
+    return q + 16;
   }
-  __device__ static __forceinline__ void init(const Smem& sm, State& es) {
+  __device__ static __forceinline__ void init(const Smem& sm, State& es) {      // all 288 threads
     const int tid = threadIdx.x;
-    for (int i = tid; i < kTcStageXB + kTcStageWB; i += kThreads) sm.XB[i] = 0.f;   // XB and WB are contiguous
-    if (tid == 0) { mbar_init(sm.bar, 1); mbar_init(sm.bar + 1, 1); mbar_fence_init(); }
+    for (int i = tid; i < kTcStageXB + kTcStageWB; i += kBlockThreads) sm.XB[i] = 0.f;   // XB and WB are contiguous
+    if (tid == 0) {
+      mbar_init(full_bar(sm, 0), kThreads); mbar_init(full_bar(sm, 1), kThreads);
+      mbar_init(done_bar(sm, 0), 1); mbar_init(done_bar(sm, 1), 1);
+      mbar_fence_init();
+    }
     if (tid < 32) tmem_alloc(sm.tslot, kTcTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     es.tmem = *sm.tslot;
+    es.seq = 0;
     es.pending[0] = es.pending[1] = 0;
     es.parity[0] = es.parity[1] = 0;
   }
-  __device__ static __forceinline__ void fini(const Smem& sm, State& es) {
+  __device__ static __forceinline__ void fini(const Smem& sm, State& es) {      // workers only
     drain(sm, es);
+    const int slot = es.seq & 1;
+    if (threadIdx.x == 0) cmd_slot(sm, slot)->quit = 1;
+    mbar_arrive(full_bar(sm, slot));
     tc_fence_before();
-    __syncthreads();
+    MMN_WSYNC();
     if (threadIdx.x < 32) tmem_dealloc(es.tmem, kTcTmemCols);
   }
-  __device__ static __forceinline__ void wait(const Smem& sm, State& es, int b) {
-    if (es.pending[b]) {
-      mbar_wait(sm.bar + b, es.parity[b]);
-      es.parity[b] ^= 1;
-      es.pending[b] = 0;
+  // the 9th warp: wait for a staged chunk, issue its MMAs, commit them to the slot's done barrier
+  __device__ static __forceinline__ void issuer_loop(const Smem& sm, State&) {
+    if ((threadIdx.x & 31) != 0) return;
+    unsigned par[2] = {0u, 0u};
+    for (unsigned seq = 0;; ++seq) {
+      const int slot = seq & 1;
+      mbar_wait(full_bar(sm, slot), par[slot]);
+      par[slot] ^= 1u;
+      tc_fence_after();
+      const TcCmd c = *cmd_slot(sm, slot);   // mbar_wait above is an acquire + compiler barrier
+      if (c.quit) break;
+      unsigned long long ah = c.a_hi, al = c.a_lo, bh = c.b_hi, bl = c.b_lo;
+      for (unsigned j = 0; j < c.nj; ++j) {
+        umma_tf32(c.tmem, al, bh, c.idesc, (c.first && j == 0) ? 0u : 1u);
+        umma_tf32(c.tmem, ah, bl, c.idesc, 1u);
+        umma_tf32(c.tmem, ah, bh, c.idesc, 1u);
+        ah += c.a_step; al += c.a_step; bh += c.b_step; bl += c.b_step;   // start-address field is the low 14 bits
+      }
+      umma_commit(done_bar(sm, slot));
     }
   }
-  __device__ static __forceinline__ void drain(const Smem& sm, State& es) { wait(sm, es, 0); wait(sm, es, 1); }
+  __device__ static __forceinline__ void wait(const Smem& sm, State& es, int slot) {
+    if (es.pending[slot]) {
+      mbar_wait(done_bar(sm, slot), es.parity[slot]);
+      es.parity[slot] ^= 1;
+      es.pending[slot] = 0;
+    }
+  }
+  __device__ static __forceinline__ void drain(const Smem& sm, State& es) {
+    wait(sm, es, es.seq & 1);          // older commit first (in-order completion)
+    wait(sm, es, (es.seq & 1) ^ 1);
+  }
+  // hand the chunk staged in `slot` to the issuer.  a/b: image byte addresses; *_mn: MN-major operand
+  // (k-slice step 1024 B, SWIZZLE_128B_BASE32B, group stride *_grp) else K-major (step 32 B, SWIZZLE_128B)
+  __device__ static __forceinline__ void post(const Smem& sm, State& es, int slot, unsigned a_hi, unsigned a_lo,
+                                              bool a_mn, unsigned a_grp, unsigned b_hi, unsigned b_lo, bool b_mn,
+                                              unsigned b_grp, int N, int nj, unsigned first, unsigned tmem_col) {
+    if (threadIdx.x == 0) {
+      TcCmd* c = cmd_slot(sm, slot);
+      c->a_hi = a_mn ? umma_desc_mn(a_hi, 0, a_grp) : umma_desc_k(a_hi, 0);
+      c->a_lo = a_mn ? umma_desc_mn(a_lo, 0, a_grp) : umma_desc_k(a_lo, 0);
+      c->b_hi = b_mn ? umma_desc_mn(b_hi, 0, b_grp) : umma_desc_k(b_hi, 0);
+      c->b_lo = b_mn ? umma_desc_mn(b_lo, 0, b_grp) : umma_desc_k(b_lo, 0);
+      c->a_step = a_mn ? 64u : 2u;
+      c->b_step = b_mn ? 64u : 2u;
+      c->idesc = umma_idesc_tf32(128, N, a_mn ? 1 : 0, b_mn ? 1 : 0);
+      c->tmem = es.tmem + tmem_col;
+      c->nj = (unsigned)nj;
+      c->first = first;
+      c->quit = 0;
+    }
+    fence_proxy_async();               // this thread's image stores -> visible to the tensor-core (async) proxy
+    tc_fence_before();                 // this thread's earlier tcgen05.ld of the accumulator are ordered before
+    mbar_arrive(full_bar(sm, slot));
+    es.pending[slot] = 1;
+    es.seq += 1;
+  }
 
   // ---- weight block: [nrows <= 64][ncols <= 32] of row-major W -> K-major image pair (rows = n) ----
   __device__ static __forceinline__ void w_load_k(float (&w)[8], const float* __restrict__ W, int ldw, int row0, int nrows,
@@ -415,14 +499,15 @@ struct TcEngine {
       bool wv = w_vec_ok(W, ldw, segs[0].wcol);
       w_load_k(wr, W, ldw, n0, nrows, segs[0].wcol, min(KC, segs[0].width), wv);
       a_chunk_load<4>(ar, segs[0], 0, min(KC, segs[0].width), rows_valid, avec[0]);
-      int buf = 0;
       unsigned first = 1;
+      int slot = 0;
       while (it.valid(nseg)) {
         const ASeg sg = segs[it.s];
         const int kw = min(KC, sg.width - it.k0);
-        float* xh = sm.XB + buf * 8192;
-        float* wh = sm.WB + buf * 4096;
-        wait(sm, es, buf);                       // MMAs that read this buffer pair two chunks ago are done
+        slot = es.seq & 1;
+        float* xh = sm.XB + slot * 8192;
+        float* wh = sm.WB + slot * 4096;
+        wait(sm, es, slot);                       // MMAs that read this slot two chunks ago are done
         w_store_k(wh, wh + 2048, wr, wv);
         a_store<false>(xh, xh + 4096, ar, sm, sg, it.k0, kw, drop, scan_nan && n0 == 0, avec[it.s]);
         ChunkIt nx = it;
@@ -434,41 +519,27 @@ struct TcEngine {
           w_load_k(wr, W, ldw, n0, nrows, ns.wcol + nx.k0, nkw, wv);
           a_chunk_load<4>(ar, ns, nx.k0, nkw, rows_valid, avec[nx.s]);
         }
-        fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-          tc_fence_after();
-          const unsigned id = umma_idesc_tf32(128, Np, 0, 0);
-          const unsigned ah = smem_u32(xh), al = smem_u32(xh + 4096), bh = smem_u32(wh), bl = smem_u32(wh + 2048);
-          const int nj = (kw + 7) >> 3;
-          for (int j = 0; j < nj; ++j) {
-            umma_tf32(es.tmem, umma_desc_k(al, j), umma_desc_k(bh, j), id, (first && j == 0) ? 0u : 1u);
-            umma_tf32(es.tmem, umma_desc_k(ah, j), umma_desc_k(bl, j), id, 1u);
-            umma_tf32(es.tmem, umma_desc_k(ah, j), umma_desc_k(bh, j), id, 1u);
-          }
-          umma_commit(sm.bar + buf);
-        }
-        es.pending[buf] = 1;
+        post(sm, es, slot, smem_u32(xh), smem_u32(xh + 4096), false, 0, smem_u32(wh), smem_u32(wh + 2048), false, 0,
+             Np, (kw + 7) >> 3, first, 0);
         first = 0;
         it = nx;
-        buf ^= 1;
       }
-      wait(sm, es, buf);          // older commit first (in-order completion), then the last one
-      wait(sm, es, buf ^ 1);
+      float bj[32];
+      const int cbeg = half * (Np >> 1);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) bj[i] = (i < (Np >> 1) && n0 + cbeg + i < N) ? __ldg(bias + n0 + cbeg + i) : 0.f;
+      wait(sm, es, slot ^ 1);     // older commit first (in-order completion), then the last one
+      wait(sm, es, slot);
       tc_fence_after();
       const int r = 32 * q + lane;
-      for (int c0 = half * (Np >> 1); c0 < (half + 1) * (Np >> 1); c0 += 16) {
+      for (int c0 = 0; c0 < (Np >> 1); c0 += 16) {
         float v[16];
-        tmem_ld16(es.tmem + ((unsigned)(32 * q) << 16) + c0, v);
+        tmem_ld16(es.tmem + ((unsigned)(32 * q) << 16) + cbeg + c0, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int n = n0 + c0 + i;
-          epi(r, n, v[i] + (n < N ? __ldg(bias + n) : 0.f));
-        }
+        for (int i = 0; i < 16; ++i) epi(r, n0 + cbeg + c0 + i, v[i] + bj[c0 + i]);
       }
-      tc_fence_before();
-      __syncthreads();            // accumulator columns and staging buffers are free again
     }
+    MMN_WSYNC();                  // outputs (and the row NaN flags) visible to every worker
   }
 
   // ------------------------------------------------------------------------------------------------
@@ -484,122 +555,103 @@ struct TcEngine {
     for (int j0 = 0; j0 < J; j0 += 64) {
       const int jw = min(64, J - j0);
       const int Np = jw <= 32 ? 32 : 64;
+      const int cbeg = half * (Np >> 1);
       float pv[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) pv[i] = i < (Np >> 1) ? pre(r, j0 + half * (Np >> 1) + i) : 0.f;
+      for (int i = 0; i < 32; ++i) pv[i] = i < (Np >> 1) ? pre(r, j0 + cbeg + i) : 0.f;
       const bool wv = w_vec_ok(W, ldw, col0 + j0);
       float wr[8], dummy[16];
       w_load_mn(wr, W, ldw, 0, min(32, N), col0 + j0, jw, wv);
-      int buf = 0;
       unsigned first = 1;
+      int slot = 0;
       for (int n0 = 0; n0 < N; n0 += 32) {
         const int nw = min(32, N - n0);
-        float* xh = sm.XB + buf * 8192;
-        float* wh = sm.WB + buf * 4096;
-        wait(sm, es, buf);
+        slot = es.seq & 1;
+        float* xh = sm.XB + slot * 8192;
+        float* wh = sm.WB + slot * 4096;
+        wait(sm, es, slot);
         w_store_mn(wh, wh + 2048, wr, wv);
         ASeg sg;
         sg.ptr = dz; sg.ld = ldd; sg.width = N; sg.kind = SEG_SMEM; sg.wcol = 0;
         a_store<false>(xh, xh + 4096, dummy, sm, sg, n0, nw, nodrop, false, false);
         if (n0 + 32 < N) w_load_mn(wr, W, ldw, n0 + 32, min(32, N - n0 - 32), col0 + j0, jw, wv);
-        fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-          tc_fence_after();
-          const unsigned id = umma_idesc_tf32(128, Np, 0, 1);
-          const unsigned ah = smem_u32(xh), al = smem_u32(xh + 4096), bh = smem_u32(wh), bl = smem_u32(wh + 2048);
-          const int nj = (nw + 7) >> 3;
-          for (int j = 0; j < nj; ++j) {
-            umma_tf32(es.tmem, umma_desc_k(al, j), umma_desc_mn(bh, j, 4096), id, (first && j == 0) ? 0u : 1u);
-            umma_tf32(es.tmem, umma_desc_k(ah, j), umma_desc_mn(bl, j, 4096), id, 1u);
-            umma_tf32(es.tmem, umma_desc_k(ah, j), umma_desc_mn(bh, j, 4096), id, 1u);
-          }
-          umma_commit(sm.bar + buf);
-        }
-        es.pending[buf] = 1;
+        post(sm, es, slot, smem_u32(xh), smem_u32(xh + 4096), false, 0, smem_u32(wh), smem_u32(wh + 2048), true, 4096,
+             Np, (nw + 7) >> 3, first, 0);
         first = 0;
-        buf ^= 1;
       }
-      wait(sm, es, buf);
-      wait(sm, es, buf ^ 1);
+      wait(sm, es, slot ^ 1);
+      wait(sm, es, slot);
       tc_fence_after();
       for (int c0 = 0; c0 < (Np >> 1); c0 += 16) {
         float v[16];
-        tmem_ld16(es.tmem + ((unsigned)(32 * q) << 16) + half * (Np >> 1) + c0, v);
+        tmem_ld16(es.tmem + ((unsigned)(32 * q) << 16) + cbeg + c0, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) epi(r, j0 + half * (Np >> 1) + c0 + i, v[i], pv[c0 + i]);
+        for (int i = 0; i < 16; ++i) epi(r, j0 + cbeg + c0 + i, v[i], pv[c0 + i]);
       }
-      tc_fence_before();
-      __syncthreads();
     }
+    MMN_WSYNC();
   }
 
   // ------------------------------------------------------------------------------------------------
   // gW[n][wcol + k] += sum_r dz[r][n] a[r][k]      (both operands MN-major, contraction = the 128 rows)
-  // D[n][k]: lanes = output rows n (two 32-column groups of dz per pass), columns = the 32 k of a chunk.
+  // D[n][k]: lanes = output rows n of one 32-column group of dz (all four lane quarters see the same
+  // group: group stride 0), columns = the 32 k of a chunk.  Staging: XB[0,32K) = dz {hi, lo};
+  // input chunks alternate between WB and XB[32K,64K); accumulator columns alternate with them, so the
+  // epilogue (TMEM -> red.global) of chunk c overlaps the MMAs of chunk c + 1.
   // ------------------------------------------------------------------------------------------------
   __device__ static __forceinline__ void gemm_tn(const Smem& sm, State& es, const float* dz, int ldd, int N, const ASeg& sg,
                                                  const Drop& drop, int rows_valid, float* __restrict__ gW, int ldw) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, half = warp >> 2;
     const bool vec_ok = ((ldw & 3) == 0) && ((sg.wcol & 3) == 0) && ((reinterpret_cast<size_t>(gW) & 15) == 0);
     const bool avec = seg_vec_ok(sg);
-    const int Npad = (N + 31) & ~31;
-    for (int nb0 = 0; nb0 < N; nb0 += 64) {
-      const int ngroups = min(2, (Npad - nb0) >> 5);
+    auto epilogue = [&](int slot, int nb0, int k0) {
+      wait(sm, es, slot);
+      tc_fence_after();
+      float v[16];
+      tmem_ld16(es.tmem + ((unsigned)(32 * q) << 16) + 32 * slot + half * 16, v);
+      const int n = nb0 + lane;
+      if (q == 0 && n < N) {
+        const int kc = k0 + half * 16;
+        float* dst = gW + (long long)n * ldw + sg.wcol + kc;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          if (vec_ok && kc + i + 3 < sg.width) {
+            atomicAdd(reinterpret_cast<float4*>(dst + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (kc + i + u < sg.width) atomicAdd(dst + i + u, v[i + u]);
+          }
+        }
+      }
+    };
+    for (int nb0 = 0; nb0 < N; nb0 += 32) {
       float ar[16];
       a_chunk_load<4>(ar, sg, 0, min(KC, sg.width), rows_valid, avec);
       drain(sm, es);
-      __syncthreads();
-      // dz column groups -> MN-major A images: XB = {hi g0, hi g1, lo g0, lo g1}
-      for (int idx = tid; idx < 128 * 8 * ngroups; idx += kThreads) {
-        const int g = idx >> 10, rr = (idx >> 3) & 127, c4 = idx & 7;
-        const float4 v = *reinterpret_cast<const float4*>(dz + rr * ldd + nb0 + 32 * g + 4 * c4);
-        tc_store_quad<true>(sm.XB + g * 4096, sm.XB + 8192 + g * 4096, rr, c4, v);
+      MMN_WSYNC();                 // every worker is past its reads of the staging buffers / dz tile writes
+      for (int idx = tid; idx < 128 * 8; idx += kThreads) {      // dz column group -> MN-major A image pair
+        const int rr = idx >> 3, c4 = idx & 7;
+        const float4 v = *reinterpret_cast<const float4*>(dz + rr * ldd + nb0 + 4 * c4);
+        tc_store_quad<true>(sm.XB, sm.XB + 4096, rr, c4, v);
       }
+      int prev_slot = -1, prev_k0 = 0;
       for (int k0 = 0; k0 < sg.width; k0 += KC) {
         const int kw = min(KC, sg.width - k0);
-        wait(sm, es, 0);
-        a_store<true>(sm.WB, sm.WB + 4096, ar, sm, sg, k0, kw, drop, false, avec);
+        const int slot = es.seq & 1;
+        float* ih = slot ? sm.XB + 8192 : sm.WB;
+        wait(sm, es, slot);        // (already collected by the epilogue two chunks ago)
+        a_store<true>(ih, ih + 4096, ar, sm, sg, k0, kw, drop, false, avec);
         if (k0 + KC < sg.width) a_chunk_load<4>(ar, sg, k0 + KC, min(KC, sg.width - k0 - KC), rows_valid, avec);
-        fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-          tc_fence_after();
-          const unsigned id = umma_idesc_tf32(128, 32, 1, 1);
-          const unsigned ah = smem_u32(sm.XB), al = smem_u32(sm.XB + 8192), bh = smem_u32(sm.WB), bl = smem_u32(sm.WB + 4096);
-          for (int j = 0; j < 16; ++j) {
-            umma_tf32(es.tmem, umma_desc_mn(al, j, 16384), umma_desc_mn(bh, j, 16384), id, j ? 1u : 0u);
-            umma_tf32(es.tmem, umma_desc_mn(ah, j, 16384), umma_desc_mn(bl, j, 16384), id, 1u);
-            umma_tf32(es.tmem, umma_desc_mn(ah, j, 16384), umma_desc_mn(bh, j, 16384), id, 1u);
-          }
-          umma_commit(sm.bar);
-        }
-        es.pending[0] = 1;
-        wait(sm, es, 0);
-        tc_fence_after();
-        {
-          float v[16];
-          tmem_ld16(es.tmem + ((unsigned)(32 * q) << 16) + half * 16, v);
-          const int n = nb0 + 32 * q + lane;
-          if (q < ngroups && n < N) {
-            const int kc = k0 + half * 16;
-            float* dst = gW + (long long)n * ldw + sg.wcol + kc;
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              if (vec_ok && kc + i + 3 < sg.width) {
-                atomicAdd(reinterpret_cast<float4*>(dst + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
-              } else {
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                  if (kc + i + u < sg.width) atomicAdd(dst + i + u, v[i + u]);
-              }
-            }
-          }
-        }
-        tc_fence_before();
+        post(sm, es, slot, smem_u32(sm.XB), smem_u32(sm.XB + 4096), true, 0, smem_u32(ih), smem_u32(ih + 4096), true, 0,
+             32, 16, 1u, 32 * slot);
+        if (prev_slot >= 0) epilogue(prev_slot, nb0, prev_k0);
+        prev_slot = slot;
+        prev_k0 = k0;
       }
-      __syncthreads();
+      if (prev_slot >= 0) epilogue(prev_slot, nb0, prev_k0);
     }
+    MMN_WSYNC();
   }
 };
 

@@ -129,6 +129,14 @@ inline void block_barrier(int pred, int* or_out) {
   }
   if (or_out) *or_out = s.bar_or_result;
 }
+// barrier over threads [0, count) (bar.sync id, count); one id in use
+inline void named_barrier(unsigned count) {
+  State& s = st();
+  static unsigned n_arrived = 0, gen_ = 0;
+  unsigned gen = gen_;
+  if (++n_arrived == count) { n_arrived = 0; ++gen_; }
+  else while (gen_ == gen) yield();
+}
 inline void warp_barrier() {
   State& s = st();
   unsigned w = tIdx().x / 32;
@@ -158,6 +166,7 @@ inline T shfl(T v, unsigned src_lane) {
 #define gridDim (emu::gDim())
 
 static inline void __syncthreads() { emu::block_barrier(0, nullptr); }
+#define MMN_WSYNC() emu::named_barrier(256)
 static inline int __syncthreads_or(int p) { int r; emu::block_barrier(p != 0, &r); return r; }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_barrier(); }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu::shfl(v, (threadIdx.x % 32) ^ m); }
