@@ -135,9 +135,9 @@ int mmn_abi_version(void);
 int mmn_plan_create(const mmn_model_desc* desc, mmn_plan** out);
 void mmn_plan_destroy(mmn_plan* plan);
 
-/* Which GEMM engine the plan's step kernel uses: the tcgen05 3xTF32 tensor-core engine when the
- * model's tiles fit shared memory at 128 rows, else the FP32-FMA engine.  The environment variable
- * MMN_ENGINE=fma|tc (read by mmn_plan_create) forces one; results agree to fp32 round-off. */
+/* Which GEMM engine the plan's step kernel uses: the FP32-FMA engine (default) or the tcgen05 3xTF32
+ * tensor-core engine (environment variable MMN_ENGINE=tc, read by mmn_plan_create; needs the model's
+ * tiles to fit shared memory at 128 rows).  Results agree to fp32 round-off. */
 enum { MMN_ENGINE_FMA = 0, MMN_ENGINE_TC = 1 };
 int32_t mmn_plan_engine(const mmn_plan* plan);
 

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 using namespace mmn;
 
@@ -167,7 +168,9 @@ extern "C" int mmn_plan_create(const mmn_model_desc* desc, mmn_plan** out) {
     delete p;
     return fail("MMN_ENGINE=tc: the tensor-core engine needs %zu B of shared memory for this model (limit %d)", tc_smem(P), p->max_smem);
   }
-  p->engine = (tc_fits && !(want && !strcmp(want, "fma"))) ? MMN_ENGINE_TC : MMN_ENGINE_FMA;
+  // default: the FP32-FMA engine (faster at the current stage of tuning, profiles/r1_engine_timers.txt);
+  // MMN_ENGINE=tc opts into the tcgen05 3xTF32 engine
+  p->engine = (tc_fits && want && !strcmp(want, "tc")) ? MMN_ENGINE_TC : MMN_ENGINE_FMA;
   if (p->engine == MMN_ENGINE_FMA && p->rm == 0) {
     const size_t need = fma_smem(P, 1);
     delete p;
@@ -241,13 +244,29 @@ int fill_args(const mmn_plan* plan, const mmn_batch* b, const float* params, con
 }
 
 template <class ENG, bool TRAIN>
-int launch_engine(const mmn_plan* plan, const StepArgs& a, void* stream) {
+int launch_engine(const mmn_plan* plan, const StepArgs& a_in, void* stream) {
+  StepArgs a = a_in;
   const size_t smem = step_smem_bytes(plan->host, ENG::TM, ENG::stage_bytes());
   const int grid = grid_for(plan, a.n_rows);
   auto kfn = mmn_step_kernel<ENG, TRAIN>;
   MMN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool dbg = getenv("MMN_DEBUG_TIMERS") != nullptr;      // development aid: per-phase cycle counters
+  if (dbg) { MMN_CUDA(cudaMalloc((void**)&a.debug_timers, sizeof(long long) * 32 * grid)); MMN_CUDA(cudaMemsetAsync(a.debug_timers, 0, sizeof(long long) * 32 * grid, (cudaStream_t)stream)); }
   MMN_LAUNCH(kfn, dim3(grid), dim3(ENG::kBlockThreads), smem, stream, a);
   MMN_CUDA(cudaGetLastError());
+  if (dbg) {
+    std::vector<long long> h(32 * (size_t)grid);
+    MMN_CUDA(cudaMemcpy(h.data(), a.debug_timers, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+    cudaFree(a.debug_timers);
+    double s[16] = {0};
+    for (int b = 0; b < grid; ++b) for (int i = 0; i < 16; ++i) s[i] += (double)h[b * 16 + i] / grid;
+    fprintf(stderr, "[mmn timers, mean cycles/CTA] total %.0f | wait_done %.0f | nt %.0f (epi %.0f) | nn %.0f (epi %.0f) | tn %.0f (epi %.0f) | bwd %.0f | nt-store %.0f | post %.0f | bias %.0f | wsync %.0f | tn-dz %.0f\n",
+            s[15], s[0], s[1], s[4], s[2], s[5], s[3], s[6], s[9], s[10], s[11], s[12], s[13], s[14]);
+    double q[6] = {0};
+    for (int b = 0; b < grid; ++b) for (int i = 0; i < 6; ++i) q[i] += (double)h[(grid + b) * 16 + i] / grid;
+    fprintf(stderr, "[mmn issuer, mean/CTA] idle %.0f | issue %.0f | chain(nj<16) %.0f cycles x %.0f = %.0f each | chain(nj=16) %.0f x %.0f = %.0f each\n",
+            q[0], q[1], q[2], q[3], q[3] ? q[2] / q[3] : 0.0, q[4], q[5], q[5] ? q[4] / q[5] : 0.0);
+  }
   return 0;
 }
 template <bool TRAIN>

@@ -11,8 +11,9 @@
 #define MMN_LAUNCH(kernel, grid, block, smem, stream, ...) \
   kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
 #define MMN_DYN_SMEM(name) extern __shared__ __align__(16) char name[]
-// barrier over the 256 worker threads only (the tensor-core engine adds a 9th, MMA-issuing warp)
-#define MMN_WSYNC() asm volatile("bar.sync 1, 256;" ::: "memory")
+// barrier over the n worker threads only (the tensor-core engine adds one more, MMA-issuing warp)
+#define MMN_WSYNC_N(n) asm volatile("bar.sync 1, %0;" ::"n"(n) : "memory")
+#define MMN_CLOCK() clock64()
 #endif
 
 namespace mmn {
@@ -93,6 +94,7 @@ struct StepArgs {
   float c_err;   // err_penalty / (D (E+1) B_global)
   float c_sc;    // 2 * state_change_penalty_scaled / (E B_global S)
   unsigned dropout_seed;
+  long long* debug_timers;   // optional [grid][16] cycle counters (MMN_DEBUG_TIMERS=1), thread 0 of each CTA
 };
 
 // shared-memory footprint of the step kernel for a row tile of TM rows, given the engine's staging bytes

@@ -269,7 +269,7 @@ __device__ __forceinline__ void fma_gemm_nt(const Smem& sm, const float* __restr
     w_block_load(wr, W, ldw, n0, nrows, segs[0].wcol, min(KC, segs[0].width), wv);
     a_chunk_load<RM>(ar, segs[0], 0, min(KC, segs[0].width), rows_valid, avec[0]);
     int buf = 0;
-    MMN_WSYNC();                    // previous users of the staging buffers are done
+    MMN_WSYNC_N(kThreads);                    // previous users of the staging buffers are done
     while (it.valid(nseg)) {
       const ASeg sg = segs[it.s];
       const int kw = min(KC, sg.width - it.k0);
@@ -295,7 +295,7 @@ __device__ __forceinline__ void fma_gemm_nt(const Smem& sm, const float* __restr
         w_block_load(wr, W, ldw, n0, nrows, ns.wcol + nx.k0, nkw, wv);
         a_chunk_load<RM>(ar, ns, nx.k0, nkw, rows_valid, avec[nx.s]);
       }
-      MMN_WSYNC();
+      MMN_WSYNC_N(kThreads);
       const int nq = (kw + 3) >> 2;
 #pragma unroll 2
       for (int q = 0; q < nq; ++q) {
@@ -322,14 +322,14 @@ __device__ __forceinline__ void fma_gemm_nt(const Smem& sm, const float* __restr
 #pragma unroll
       for (int j = 0; j < 4; ++j) epi(ty + 32 * i, n0 + tx + 8 * j, acc[i][j] + bj[j]);
   }
-  MMN_WSYNC();
+  MMN_WSYNC_N(kThreads);
 }
 
 // ------------------------------------------------------------------------------------------------
 // gemm_nn: out[r][j] = sum_n dz[r][n] * W[n][col0 + j], j < J;  epi(r, j, acc, pre(r, j)) for every
 // (r, j) of each 32-column pass including pad columns j >= J.  dz: shared tile, zero-padded to 32
-// columns.  pre(r, j) is evaluated BEFORE the K loop so that its global loads (stashed activations)
-// are hidden behind the multiply.
+// columns.  pre(r, j4) -> float4 (columns j4 .. j4+3, j4 % 4 == 0) is evaluated BEFORE the K loop so that
+// its global loads (stashed activations) are hidden behind the multiply.
 // ------------------------------------------------------------------------------------------------
 template <int RM, class Pre, class Epi>
 __device__ __forceinline__ void fma_gemm_nn(const Smem& sm, const float* dz, int ldd, int N,
@@ -337,25 +337,25 @@ __device__ __forceinline__ void fma_gemm_nn(const Smem& sm, const float* dz, int
   const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
   for (int j0 = 0; j0 < J; j0 += 32) {
     const int jw = min(32, J - j0);
-    float acc[RM][4], pv[RM][4];
+    float acc[RM][4];
+    float4 pv[RM];
 #pragma unroll
-    for (int i = 0; i < RM; ++i)
+    for (int i = 0; i < RM; ++i) {
+      pv[i] = pre(ty + 32 * i, j0 + 4 * tx);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        acc[i][c] = 0.f;
-        pv[i][c] = pre(ty + 32 * i, j0 + 4 * tx + c);
-      }
+      for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+    }
     const bool wv = w_vec_ok(W, ldw, col0 + j0);
     float wr[4];
     w_block_load(wr, W, ldw, 0, min(32, N), col0 + j0, jw, wv);
     int buf = 0;
-    MMN_WSYNC();
+    MMN_WSYNC_N(kThreads);
     for (int n0 = 0; n0 < N; n0 += 32) {
       const int nw = min(32, N - n0);
       float* WBb = sm.WB + buf * (32 * LDX);
       w_block_store(WBb, wr, wv);
       if (n0 + 32 < N) w_block_load(wr, W, ldw, n0 + 32, min(32, N - n0 - 32), col0 + j0, jw, wv);
-      MMN_WSYNC();
+      MMN_WSYNC_N(kThreads);
       const int nq = (nw + 3) >> 2;
 #pragma unroll 2
       for (int q = 0; q < nq; ++q) {
@@ -381,9 +381,10 @@ __device__ __forceinline__ void fma_gemm_nn(const Smem& sm, const float* dz, int
 #pragma unroll
     for (int i = 0; i < RM; ++i)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) epi(ty + 32 * i, j0 + 4 * tx + c, acc[i][c], pv[i][c]);
+      for (int c = 0; c < 4; ++c)
+        epi(ty + 32 * i, j0 + 4 * tx + c, acc[i][c], c == 0 ? pv[i].x : c == 1 ? pv[i].y : c == 2 ? pv[i].z : pv[i].w);
   }
-  MMN_WSYNC();
+  MMN_WSYNC_N(kThreads);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -404,7 +405,7 @@ __device__ __forceinline__ void fma_gemm_tn(const Smem& sm, const float* dz, int
   const int nnb = (N + 31) >> 5;
   float ar[4 * RM];
   a_chunk_load<RM>(ar, sg, 0, min(KC, sg.width), rows_valid, avec);
-  MMN_WSYNC();                 // previous users of XB / RED are done
+  MMN_WSYNC_N(kThreads);                 // previous users of XB / RED are done
   int xbuf = 0, rbuf = 0;
   // software pipeline over (chunk, n-block) items: the reduction of item i-1 runs after the sync of item i
   int pend_n0 = -1, pend_k0 = 0, pend_rbuf = 0;
@@ -447,7 +448,7 @@ __device__ __forceinline__ void fma_gemm_tn(const Smem& sm, const float* dz, int
     if (k0 + KC < sg.width) a_chunk_load<RM>(ar, sg, k0 + KC, min(KC, sg.width - k0 - KC), rows_valid, avec);
     for (int nb = 0; nb < nnb; ++nb) {
       const int n0 = nb * 32;
-      MMN_WSYNC();             // chunk visible; RED of the pending item complete
+      MMN_WSYNC_N(kThreads);             // chunk visible; RED of the pending item complete
       if (pend_n0 >= 0) flush(pend_n0, pend_k0, pend_rbuf);
       float acc[4][4];
 #pragma unroll
@@ -476,22 +477,23 @@ __device__ __forceinline__ void fma_gemm_tn(const Smem& sm, const float* dz, int
       rbuf ^= 1;
     }
   }
-  MMN_WSYNC();
+  MMN_WSYNC_N(kThreads);
   if (pend_n0 >= 0) flush(pend_n0, pend_k0, pend_rbuf);
 }
 
 // ------------------------------------------------------------------------------------------------
 // FMA engine: the three GEMM shapes on the FP32 pipe (any tile height RM in {1, 2, 4})
 // ------------------------------------------------------------------------------------------------
-struct NoState {};
+struct NoState { long long t[16]; };
 template <int RM_>
 struct FmaEngine {
   static constexpr int RM = RM_;
   static constexpr int TM = 32 * RM_;
   static constexpr bool kTensor = false;
+  static constexpr int kWorkers = kThreads;
   static constexpr int kBlockThreads = kThreads;
   using State = NoState;
-  __device__ static __forceinline__ void issuer_loop(const Smem&, State&) {}
+  __device__ static __forceinline__ void issuer_loop(const Smem&, State&, long long* = nullptr) {}
   static size_t stage_bytes() { return (size_t)(2 * (TM * LDX + 32 * LDX) + 2 * kGroups * 1024) * 4; }
   __device__ static __forceinline__ char* carve(Smem& sm, char* p) {
     float* f = reinterpret_cast<float*>(p);
@@ -520,32 +522,33 @@ struct FmaEngine {
 };
 
 // bias gradient: gb[n] += sum_r dz[r][n]
-template <int RM>
+template <int TM, int NT>
 __device__ __forceinline__ void colsum_red(const Smem& sm, const float* dz, int ldd, int N, float* __restrict__ gb) {
-  constexpr int TM = Cfg<RM>::TM;
+  constexpr int PARTS = NT / 32;
   const int tid = threadIdx.x, c = tid & 31, part = tid >> 5;
   for (int n0 = 0; n0 < N; n0 += 32) {
     float s = 0.f;
-    for (int r = part; r < TM; r += 8) s += dz[r * ldd + n0 + c];
-    MMN_WSYNC();
+    for (int r = part; r < TM; r += PARTS) s += dz[r * ldd + n0 + c];
+    MMN_WSYNC_N(NT);
     sm.RED[part * 32 + c] = s;
-    MMN_WSYNC();
+    MMN_WSYNC_N(NT);
     if (tid < 32 && n0 + tid < N) {
       float tot = 0.f;
 #pragma unroll
-      for (int p = 0; p < 8; ++p) tot += sm.RED[p * 32 + tid];
+      for (int p = 0; p < PARTS; ++p) tot += sm.RED[p * 32 + tid];
       atomicAdd(gb + n0 + tid, tot);
     }
   }
-  MMN_WSYNC();
+  MMN_WSYNC_N(NT);
 }
 
 // walks idx = tid, tid + kThreads, ... of a [rows x w] index space as (r, c) without a division per step
+template <int NT>
 struct RowCol {
   int r, c, q, rem, w;
   __device__ __forceinline__ RowCol(int w_) : w(w_) {
     r = (int)threadIdx.x / w_; c = (int)threadIdx.x - r * w_;
-    q = kThreads / w_; rem = kThreads - q * w_;
+    q = NT / w_; rem = NT - q * w_;
   }
   __device__ __forceinline__ void next() {
     r += q; c += rem;
@@ -554,17 +557,30 @@ struct RowCol {
 };
 
 // shared tile [TM x width] -> global row-major [TM x width] (float4 when the width allows)
-template <int RM>
+template <int TM, int NT>
 __device__ __forceinline__ void stash_store(float* dst, const float* buf, int ld, int width) {
-  constexpr int TM = Cfg<RM>::TM;
   if ((width & 3) == 0) {
     const int w4 = width >> 2;
-    for (RowCol it(w4); it.r < TM; it.next())
+    for (RowCol<NT> it(w4); it.r < TM; it.next())
       __stcg(reinterpret_cast<float4*>(dst) + it.r * w4 + it.c,
              *reinterpret_cast<const float4*>(buf + it.r * ld + 4 * it.c));
   } else {
-    for (RowCol it(width); it.r < TM; it.next()) __stcg(dst + it.r * width + it.c, buf[it.r * ld + it.c]);
+    for (RowCol<NT> it(width); it.r < TM; it.next()) __stcg(dst + it.r * width + it.c, buf[it.r * ld + it.c]);
   }
+}
+
+// 4 consecutive columns (c4 % 4 == 0) of row r of a row-major [rows x width] global block, L2-coherent;
+// zero beyond width
+__device__ __forceinline__ float4 ldcg4(const float* base, int r, int width, int c4) {
+  const float* p = base + (long long)r * width + c4;
+  if (((width & 3) == 0) && ((reinterpret_cast<size_t>(base) & 15) == 0) && c4 + 3 < width)
+    return __ldcg(reinterpret_cast<const float4*>(p));
+  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c4 + 0 < width) q.x = __ldcg(p + 0);
+  if (c4 + 1 < width) q.y = __ldcg(p + 1);
+  if (c4 + 2 < width) q.z = __ldcg(p + 2);
+  if (c4 + 3 < width) q.w = __ldcg(p + 3);
+  return q;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -585,6 +601,7 @@ template <class ENG, bool TRAIN>
 __global__ void __launch_bounds__(ENG::kBlockThreads, 1) mmn_step_kernel(const StepArgs args) {
   constexpr int RM = ENG::RM;
   constexpr int TM = ENG::TM;
+  constexpr int NT = ENG::kWorkers;
   const DevPlan& P = *args.plan;
   const int tid = threadIdx.x;
   const int S = P.S, E = P.E, D = P.D, ldS = P.ldS, ldH = P.ldH;
@@ -608,11 +625,12 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, 1) mmn_step_kernel(const S
     sm.met = reinterpret_cast<double*>(smem_raw + off);
     sm.present = reinterpret_cast<unsigned char*>(sm.met + P.n_metrics);
   }
-  for (int i = tid; i < P.n_metrics; i += kThreads) sm.met[i] = 0.0;
-  for (int i = tid; i < E + 1; i += kThreads) sm.cnt[i] = 0;
+  for (int i = tid; i < P.n_metrics; i += NT) sm.met[i] = 0.0;
+  for (int i = tid; i < E + 1; i += NT) sm.cnt[i] = 0;
   ENG::init(sm, es);
-  if (ENG::kTensor && threadIdx.x >= kThreads) {      // 9th warp: issues the tensor-core MMAs
-    ENG::issuer_loop(sm, es);
+  const long long t_kernel = MMN_CLOCK();
+  if (ENG::kTensor && threadIdx.x >= NT) {      // 9th warp: issues the tensor-core MMAs
+    ENG::issuer_loop(sm, es, args.debug_timers ? args.debug_timers + 16 * (gridDim.x + blockIdx.x) : nullptr);
     return;
   }
 
@@ -624,26 +642,26 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, 1) mmn_step_kernel(const S
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long row0 = tile * TM;
     const int rows_valid = (int)min((long long)TM, args.n_rows - row0);
-    MMN_WSYNC();
+    MMN_WSYNC_N(NT);
 
     // ---- tile prologue: targets, initial state (state.py:29-32), masks ----
     if (args.targets) {
-      for (int idx = tid; idx < TM * D; idx += kThreads) {
+      for (int idx = tid; idx < TM * D; idx += NT) {
         const int r = idx / D;
         long long y = 0;
         if (r < rows_valid) y = args.targets[(row0 + r) * D + (idx - r * D)];
         sm.ys[idx] = (int)y;
       }
     }
-    for (int idx = tid; idx < TM * ldS; idx += kThreads) {
+    for (int idx = tid; idx < TM * ldS; idx += NT) {
       const int c = idx % ldS;
       sm.S[idx] = c < S ? __ldg(params + P.init_off + c) : 0.f;
     }
-    for (int r = tid; r < TM; r += kThreads) sm.present[r] = r < rows_valid;
-    for (int i = tid; i < E + 1; i += kThreads) sm.tile_any[i] = i == 0;
+    for (int r = tid; r < TM; r += NT) sm.present[r] = r < rows_valid;
+    for (int i = tid; i < E + 1; i += NT) sm.tile_any[i] = i == 0;
     if (tid < TM && tid < rows_valid) atomicAdd(&sm.cnt[0], 1);
-    MMN_WSYNC();
-    if (TRAIN) stash_store<RM>(slot + (long long)stash_state_off(P, 0) * TM, sm.S, ldS, S);
+    MMN_WSYNC_N(NT);
+    if (TRAIN) stash_store<TM, NT>(slot + (long long)stash_state_off(P, 0) * TM, sm.S, ldS, S);
 
     // ---- decoders on the current state (multimodn.py:141-157, 176-191) ----
     auto decoders_forward = [&](int k, int hist_row, bool is_last_enc) {
@@ -660,7 +678,7 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, 1) mmn_step_kernel(const S
           ENG::gemm_nt(sm, es, params + ly.w_off, ly.ktot, N, params + ly.b_off, &seg, 1, nodrop, rows_valid, false,
                       [&](int r, int n, float z) { out[r * ldH + n] = n < N ? act_fwd(act, z) : 0.f; });
           if (TRAIN)
-            stash_store<RM>(slot + (long long)(stash_dec_off(P, k) + dec.stash_off + ly.stash_off) * TM, out, ldH, N);
+            stash_store<TM, NT>(slot + (long long)(stash_dec_off(P, k) + dec.stash_off + ly.stash_off) * TM, out, ldH, N);
           in = out;
           ldin = ldH;
         }
@@ -713,7 +731,7 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, 1) mmn_step_kernel(const S
             }
           }
         }
-        MMN_WSYNC();
+        MMN_WSYNC_N(NT);
       }
     };
     decoders_forward(0, 0, false);
@@ -723,8 +741,8 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, 1) mmn_step_kernel(const S
       const int e = args.seq_enc[k - 1], pos = args.seq_pos[k - 1];
       const DevEncoder& enc = P.enc[e];
       const bool skip = args.skip_flags && args.skip_flags[k - 1] != 0;   // reference batch-level rule
-      for (int r = tid; r < TM; r += kThreads) sm.rownan[r] = 0;
-      MMN_WSYNC();
+      for (int r = tid; r < TM; r += NT) sm.rownan[r] = 0;
+      MMN_WSYNC_N(NT);
       if (!skip) {
         Drop drop = nodrop;
         if (TRAIN && args.training && enc.p_drop > 0.f && enc.L[0].has_state) {
@@ -762,7 +780,7 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, 1) mmn_step_kernel(const S
                       rows_valid, j == 0,
                       [&](int r, int n, float z) { out[r * ldo + n] = n < N ? act_fwd(act, z) : 0.f; });
           if (TRAIN && !last)
-            stash_store<RM>(slot + (long long)(stash_enc_off(P, k) + ly.stash_off) * TM, out, ldH, N);
+            stash_store<TM, NT>(slot + (long long)(stash_enc_off(P, k) + ly.stash_off) * TM, out, ldH, N);
           in = out;
           ldin = ldo;
         }
@@ -773,11 +791,11 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, 1) mmn_step_kernel(const S
         sm.present[k * TM + tid] = pr;
         if (pr) { atomicAdd(&sm.cnt[e + 1], 1); sm.tile_any[k] = 1; }
       }
-      MMN_WSYNC();
+      MMN_WSYNC_N(NT);
       const int any = sm.tile_any[k];
       if (any) {
         float sc = 0.f;
-        for (RowCol it(S); it.r < TM; it.next()) {
+        for (RowCol<NT> it(S); it.r < TM; it.next()) {
           const int r = it.r, c = it.c;
           if (sm.present[k * TM + r]) {
             const float o = sm.S[r * ldS + c], nw = sm.T[r * ldS + c], df = nw - o;
@@ -788,12 +806,12 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, 1) mmn_step_kernel(const S
         sc = warp_sum(sc);
         if ((tid & 31) == 0 && TRAIN) atomicAdd(&sm.met[met_sc(P, e)], (double)sc);
       }
-      MMN_WSYNC();
-      if (TRAIN) stash_store<RM>(slot + (long long)stash_state_off(P, k) * TM, sm.S, ldS, S);
+      MMN_WSYNC_N(NT);
+      if (TRAIN) stash_store<TM, NT>(slot + (long long)stash_state_off(P, k) * TM, sm.S, ldS, S);
       decoders_forward(k, e + 1, e == E - 1);
     }
     if (args.final_state) {
-      for (RowCol it(S); it.r < rows_valid; it.next())
+      for (RowCol<NT> it(S); it.r < rows_valid; it.next())
         args.final_state[(row0 + it.r) * S + it.c] = sm.S[it.r * ldS + it.c];
     }
 
@@ -802,11 +820,12 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, 1) mmn_step_kernel(const S
     // holds dLoss/ds_k for the tile.
     // =============================================================================================
     if (TRAIN) {
-      MMN_WSYNC();
+      MMN_WSYNC_N(NT);
+      const long long t_bwd = MMN_CLOCK();
       float* G = sm.S;
       float* grads = args.grads;
-      for (int idx = tid; idx < TM * ldS; idx += kThreads) G[idx] = 0.f;
-      MMN_WSYNC();
+      for (int idx = tid; idx < TM * ldS; idx += NT) G[idx] = 0.f;
+      MMN_WSYNC_N(NT);
 
       auto decoders_backward = [&](int k) {
         const float* sk = slot + (long long)stash_state_off(P, k) * TM;
@@ -837,12 +856,12 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, 1) mmn_step_kernel(const S
                 sm.A[r * ldH + c] = v;
               }
             }
-            MMN_WSYNC();
+            MMN_WSYNC_N(NT);
           }
           float* cur = sm.A;
           for (int j = nl - 1; j >= 0; --j) {
             const DevLayer& ly = dec.L[j];
-            colsum_red<RM>(sm, cur, ldH, ly.out_dim, grads + ly.b_off);
+            colsum_red<TM, NT>(sm, cur, ldH, ly.out_dim, grads + ly.b_off);
             ASeg seg;
             seg.kind = SEG_STASH; seg.wcol = 0; seg.width = ly.in_dim; seg.ld = ly.in_dim;
             seg.ptr = j == 0 ? sk : slot + dbase + (long long)dec.L[j - 1].stash_off * TM;
@@ -852,14 +871,14 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, 1) mmn_step_kernel(const S
               const float* ast = slot + dbase + (long long)dec.L[j - 1].stash_off * TM;
               const int J = ly.in_dim, pact = dec.L[j - 1].act;
               ENG::gemm_nn(sm, es, cur, ldH, ly.out_dim, params + ly.w_off, ly.ktot, 0, J,
-                          [&](int r, int jc) { return jc < J ? __ldcg(ast + r * J + jc) : 0.f; },
+                          [&](int r, int jc) { return ldcg4(ast, r, J, jc); },
                           [&](int r, int jc, float acc, float a) {
                             other[r * ldH + jc] = jc < J ? acc * act_bwd(pact, a) : 0.f;
                           });
               cur = other;
             } else {
               ENG::gemm_nn(sm, es, cur, ldH, ly.out_dim, params + ly.w_off, ly.ktot, 0, S,
-                          [&](int, int) { return 0.f; },
+                          [&](int, int) { return make_float4(0.f, 0.f, 0.f, 0.f); },
                           [&](int r, int jc, float acc, float) {
                             if (jc < S) G[r * ldS + jc] += acc;
                           });
@@ -880,7 +899,7 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, 1) mmn_step_kernel(const S
         {
           const int act = enc.L[nl - 1].act;
           const int Spad = (S + 31) & ~31;
-          for (RowCol it(Spad); it.r < TM; it.next()) {
+          for (RowCol<NT> it(Spad); it.r < TM; it.next()) {
             const int r = it.r, c = it.c;
             float dzv = 0.f;
             if (c < S) {
@@ -891,7 +910,7 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, 1) mmn_step_kernel(const S
             }
             sm.T[r * ldS + c] = dzv;
           }
-          MMN_WSYNC();
+          MMN_WSYNC_N(NT);
         }
         Drop drop = nodrop;
         if (args.training && enc.p_drop > 0.f && enc.L[0].has_state) {
@@ -907,7 +926,7 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, 1) mmn_step_kernel(const S
         for (int j = nl - 1; j >= 0; --j) {
           const DevLayer& ly = enc.L[j];
           const bool use_drop = drop.enabled && j == 0;
-          colsum_red<RM>(sm, cur, ldc, ly.out_dim, grads + ly.b_off);
+          colsum_red<TM, NT>(sm, cur, ldc, ly.out_dim, grads + ly.b_off);
           ASeg seg;
           seg.wcol = 0; seg.width = ly.in_dim;
           if (j == 0) {
@@ -927,7 +946,7 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, 1) mmn_step_kernel(const S
             const float* ast = slot + ebase + (long long)enc.L[j - 1].stash_off * TM;
             const int J = ly.in_dim, pact = enc.L[j - 1].act;
             ENG::gemm_nn(sm, es, cur, ldc, ly.out_dim, params + ly.w_off, ly.ktot, 0, J,
-                        [&](int r, int jc) { return jc < J ? __ldcg(ast + r * J + jc) : 0.f; },
+                        [&](int r, int jc) { return ldcg4(ast, r, J, jc); },
                         [&](int r, int jc, float acc, float a) {
                           other[r * ldH + jc] = jc < J ? acc * act_bwd(pact, a) : 0.f;
                         });
@@ -938,7 +957,9 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, 1) mmn_step_kernel(const S
             const int in_dim = ly.in_dim;
             ENG::gemm_nn(sm, es, cur, ldc, ly.out_dim, params + ly.w_off, ly.ktot, in_dim, S,
                         [&](int r, int jc) {      // u_k, loaded before the multiply
-                          return jc < S ? args.c_sc * (__ldcg(sk + r * S + jc) - __ldcg(skm1 + r * S + jc)) : 0.f;
+                          const float4 a = ldcg4(sk, r, S, jc), b = ldcg4(skm1, r, S, jc);
+                          return make_float4(args.c_sc * (a.x - b.x), args.c_sc * (a.y - b.y), args.c_sc * (a.z - b.z),
+                                             args.c_sc * (a.w - b.w));
                         },
                         [&](int r, int jc, float acc, float u) {
                           if (jc < S) {
@@ -955,16 +976,21 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, 1) mmn_step_kernel(const S
         }
       }
       decoders_backward(0);
-      colsum_red<RM>(sm, G, ldS, S, grads + P.init_off);      // tile backward of state.py:30
+      colsum_red<TM, NT>(sm, G, ldS, S, grads + P.init_off);      // tile backward of state.py:30
+      es.t[9] += MMN_CLOCK() - t_bwd;
     }
   }
 
   // ---- flush this CTA's metric partials ----
-  MMN_WSYNC();
+  MMN_WSYNC_N(NT);
   ENG::fini(sm, es);
+  if (args.debug_timers && tid == 0) {
+    es.t[15] = MMN_CLOCK() - t_kernel;
+    for (int i = 0; i < 16; ++i) args.debug_timers[blockIdx.x * 16 + i] = es.t[i];
+  }
   if (args.metrics) {
     const int nmat = 6 * (E + 1) * D;
-    for (int i = tid; i < P.n_metrics; i += kThreads) {
+    for (int i = tid; i < P.n_metrics; i += NT) {
       double v;
       if (i < (E + 1) * D) v = sm.met[i] * args.inv_rows_global;
       else if (i < nmat) v = sm.met[i];
@@ -974,7 +1000,7 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, 1) mmn_step_kernel(const S
     }
   }
   if (TRAIN && args.grads) {
-    for (int e = tid; e < E; e += kThreads)
+    for (int e = tid; e < E; e += NT)
       if (sm.cnt[e + 1]) atomicAdd(args.grads + P.n_params + e, (float)sm.cnt[e + 1]);
   }
 }

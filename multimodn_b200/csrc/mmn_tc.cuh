@@ -64,12 +64,15 @@ struct TcState {        // identical in every worker thread of the CTA
   unsigned seq;         // chunks posted so far; chunk i uses staging slot / mbarrier pair i & 1
   unsigned pending[2];  // an uncollected tcgen05.commit is outstanding on done[slot]
   unsigned parity[2];
+  long long t[16];      // debug cycle counters (thread 0): 0 wait-done, 1 nt, 2 nn, 3 tn, 4 nt-epi, 5 nn-epi, 6 tn-epi, 7 stage
 };
 // One staged chunk handed to the MMA-issuing warp: nj k-slices, three MMAs each (lo*hi, hi*lo, hi*hi).
+// Only an opcode crosses shared memory; the issuer rebuilds every MMA operand from warp-uniform values
+// (staging-buffer base addresses, the slot, immediates) so that they live in uniform registers.
+enum { TC_OP_NT = 0, TC_OP_NN = 1, TC_OP_TN = 2, TC_OP_QUIT = 3 };
 struct TcCmd {
-  unsigned long long a_hi, a_lo, b_hi, b_lo;   // shared-memory descriptors of k-slice 0
-  unsigned a_step, b_step;                     // added to the descriptors' start-address field per k-slice
-  unsigned idesc, tmem, nj, first, quit, pad;
+  unsigned op;      // [0,2) kind | [2] N == 64 | [3] first (overwrite the accumulator) | [4,9) nj
+  unsigned pad[3];
 };
 
 #ifndef MMN_EMU
@@ -117,6 +120,11 @@ __device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long ad
 __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ unsigned elect_one() {     // one lane of the (converged) warp
+  unsigned pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred;
+}
 // this thread's TMEM lane (row), 16 consecutive fp32 columns starting at taddr's column
 __device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
   unsigned r[16];
@@ -128,6 +136,16 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
       : "r"(taddr) : "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8(unsigned taddr, float (&v)[8]) {
+  unsigned r[8];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 #else
 // ------------------------------------------------------------------------------------------------
@@ -188,9 +206,14 @@ static inline void umma_tf32(unsigned tmem_d, unsigned long long adesc, unsigned
     }
 }
 static inline void umma_commit(unsigned long long* bar) { mbar_arrive(bar); }
+static inline unsigned elect_one() { return (threadIdx.x & 31) == 0; }
 static inline void tmem_ld16(unsigned taddr, float (&v)[16]) {
   const int lane = (taddr >> 16) + (threadIdx.x & 31), col = taddr & 0xFFFF;
   for (int i = 0; i < 16; ++i) v[i] = tcemu::tmem()[lane][col + i];
+}
+static inline void tmem_ld8(unsigned taddr, float (&v)[8]) {
+  const int lane = (taddr >> 16) + (threadIdx.x & 31), col = taddr & 0xFFFF;
+  for (int i = 0; i < 8; ++i) v[i] = tcemu::tmem()[lane][col + i];
 }
 #endif
 
@@ -232,11 +255,16 @@ struct TcEngine {
   static constexpr int RM = 4;
   static constexpr int TM = 128;
   static constexpr bool kTensor = true;
-  static constexpr int kBlockThreads = kThreads + 32;     // 8 worker warps + the MMA-issuing warp
+  static constexpr int kWorkers = 256;                    // worker warps: kWorkers / 128 per TMEM lane quarter
+  static constexpr int NW = kWorkers;
+  static constexpr int QA = 1024 / NW;                    // float4 per thread of a [128 x 32] chunk
+  static constexpr int QW = 512 / NW;                     // float4 per thread of a weight block
+  static constexpr int CS = NW / 128;                     // column slices of the accumulator (one per warp of a quarter)
+  static constexpr int kBlockThreads = kWorkers + 32;     // + the MMA-issuing warp
   using State = TcState;
-  static size_t stage_bytes() { return 1024 + (size_t)(kTcStageXB + kTcStageWB + 256) * 4 + 64 + 2 * sizeof(TcCmd); }
+  static size_t stage_bytes() { return 1024 + (size_t)(kTcStageXB + kTcStageWB + 512) * 4 + 64 + 2 * sizeof(TcCmd); }
 
-  // mbarriers: full[2] (256 worker arrivals: chunk staged) then done[2] (1 arrival: tcgen05.commit)
+  // mbarriers: full[2] (one arrival per worker: chunk staged) then done[2] (1 arrival: tcgen05.commit)
   __device__ static __forceinline__ unsigned long long* full_bar(const Smem& sm, int slot) { return sm.bar + slot; }
   __device__ static __forceinline__ unsigned long long* done_bar(const Smem& sm, int slot) { return sm.bar + 2 + slot; }
   __device__ static __forceinline__ TcCmd* cmd_slot(const Smem& sm, int slot) {
@@ -248,17 +276,17 @@ struct TcEngine {
     float* f = reinterpret_cast<float*>(p);
     sm.XB = f; f += kTcStageXB;
     sm.WB = f; f += kTcStageWB;
-    sm.RED = f; f += 256;
+    sm.RED = f; f += 512;
     sm.bar = reinterpret_cast<unsigned long long*>(f);
     char* q = reinterpret_cast<char*>(sm.bar + 4) + 2 * sizeof(TcCmd);
     sm.tslot = reinterpret_cast<unsigned*>(q);
     return q + 16;
   }
-  __device__ static __forceinline__ void init(const Smem& sm, State& es) {      // all 288 threads
+  __device__ static __forceinline__ void init(const Smem& sm, State& es) {      // every thread of the CTA
     const int tid = threadIdx.x;
     for (int i = tid; i < kTcStageXB + kTcStageWB; i += kBlockThreads) sm.XB[i] = 0.f;   // XB and WB are contiguous
     if (tid == 0) {
-      mbar_init(full_bar(sm, 0), kThreads); mbar_init(full_bar(sm, 1), kThreads);
+      mbar_init(full_bar(sm, 0), kWorkers); mbar_init(full_bar(sm, 1), kWorkers);
       mbar_init(done_bar(sm, 0), 1); mbar_init(done_bar(sm, 1), 1);
       mbar_fence_init();
     }
@@ -270,40 +298,78 @@ struct TcEngine {
     es.seq = 0;
     es.pending[0] = es.pending[1] = 0;
     es.parity[0] = es.parity[1] = 0;
+    for (int i = 0; i < 16; ++i) es.t[i] = 0;
   }
   __device__ static __forceinline__ void fini(const Smem& sm, State& es) {      // workers only
     drain(sm, es);
     const int slot = es.seq & 1;
-    if (threadIdx.x == 0) cmd_slot(sm, slot)->quit = 1;
+    if (threadIdx.x == 0) cmd_slot(sm, slot)->op = TC_OP_QUIT;
     mbar_arrive(full_bar(sm, slot));
     tc_fence_before();
-    MMN_WSYNC();
+    MMN_WSYNC_N(kWorkers);
     if (threadIdx.x < 32) tmem_dealloc(es.tmem, kTcTmemCols);
   }
-  // the 9th warp: wait for a staged chunk, issue its MMAs, commit them to the slot's done barrier
-  __device__ static __forceinline__ void issuer_loop(const Smem& sm, State&) {
-    if ((threadIdx.x & 31) != 0) return;
+  // one chunk: NJ k-slices x (lo*hi, hi*lo, hi*hi); every operand is a function of uniform values
+  template <bool AMN, bool BMN, int NJ>
+  __device__ static __forceinline__ void issue(unsigned a_hi, unsigned a_lo, unsigned a_grp, unsigned b_hi, unsigned b_lo,
+                                               unsigned b_grp, unsigned idesc, unsigned tmem, unsigned nj, bool first,
+                                               bool leader) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      if (j < (int)nj && leader) {
+        const unsigned long long ah = AMN ? umma_desc_mn(a_hi, j, a_grp) : umma_desc_k(a_hi, j);
+        const unsigned long long al = AMN ? umma_desc_mn(a_lo, j, a_grp) : umma_desc_k(a_lo, j);
+        const unsigned long long bh = BMN ? umma_desc_mn(b_hi, j, b_grp) : umma_desc_k(b_hi, j);
+        const unsigned long long bl = BMN ? umma_desc_mn(b_lo, j, b_grp) : umma_desc_k(b_lo, j);
+        umma_tf32(tmem, al, bh, idesc, (first && j == 0) ? 0u : 1u);
+        umma_tf32(tmem, ah, bl, idesc, 1u);
+        umma_tf32(tmem, ah, bh, idesc, 1u);
+      }
+    }
+  }
+  // the extra warp: wait for a staged chunk, issue its MMAs, commit them to the slot's done barrier
+  __device__ static __forceinline__ void issuer_loop(const Smem& sm, State& es, long long* dbg = nullptr) {
+    const unsigned xb = smem_u32(sm.XB), wb = smem_u32(sm.WB);     // warp-uniform
+    const unsigned tmem0 = 0;                                      // the CTA's only TMEM allocation starts at column 0
+    if (es.tmem != 0) __trap();
+    const bool leader = elect_one() != 0;
     unsigned par[2] = {0u, 0u};
+    long long t_idle = 0, t_issue = 0;
     for (unsigned seq = 0;; ++seq) {
-      const int slot = seq & 1;
+      const unsigned slot = seq & 1u;
+      const long long t0 = MMN_CLOCK();
       mbar_wait(full_bar(sm, slot), par[slot]);
       par[slot] ^= 1u;
       tc_fence_after();
-      const TcCmd c = *cmd_slot(sm, slot);   // mbar_wait above is an acquire + compiler barrier
-      if (c.quit) break;
-      unsigned long long ah = c.a_hi, al = c.a_lo, bh = c.b_hi, bl = c.b_lo;
-      for (unsigned j = 0; j < c.nj; ++j) {
-        umma_tf32(c.tmem, al, bh, c.idesc, (c.first && j == 0) ? 0u : 1u);
-        umma_tf32(c.tmem, ah, bl, c.idesc, 1u);
-        umma_tf32(c.tmem, ah, bh, c.idesc, 1u);
-        ah += c.a_step; al += c.a_step; bh += c.b_step; bl += c.b_step;   // start-address field is the low 14 bits
+      const unsigned op = cmd_slot(sm, slot)->op;    // mbar_wait above is an acquire + compiler barrier
+      const unsigned kind = op & 3u, nj = (op >> 4) & 31u;
+      const bool n64 = (op >> 2) & 1u, first = (op >> 3) & 1u;
+      if (kind == TC_OP_QUIT) break;
+      const long long t1 = MMN_CLOCK();
+      const unsigned a_hi = xb + slot * 32768u, b_hi = wb + slot * 16384u;
+      if (kind == TC_OP_NT) {
+        if (n64) issue<false, false, 4>(a_hi, a_hi + 16384u, 0, b_hi, b_hi + 8192u, 0, umma_idesc_tf32(128, 64, 0, 0), tmem0, nj, first, leader);
+        else issue<false, false, 4>(a_hi, a_hi + 16384u, 0, b_hi, b_hi + 8192u, 0, umma_idesc_tf32(128, 32, 0, 0), tmem0, nj, first, leader);
+      } else if (kind == TC_OP_NN) {
+        if (n64) issue<false, true, 4>(a_hi, a_hi + 16384u, 0, b_hi, b_hi + 8192u, 4096, umma_idesc_tf32(128, 64, 0, 1), tmem0, nj, first, leader);
+        else issue<false, true, 4>(a_hi, a_hi + 16384u, 0, b_hi, b_hi + 8192u, 4096, umma_idesc_tf32(128, 32, 0, 1), tmem0, nj, first, leader);
+      } else {           // TN: A = dz images at XB, B = input chunk at WB (slot 0) or the upper half of XB (slot 1)
+        const unsigned in_hi = slot ? xb + 32768u : wb;
+        issue<true, true, 16>(xb, xb + 16384u, 0, in_hi, in_hi + 16384u, 0, umma_idesc_tf32(128, 32, 1, 1), tmem0 + 32u * slot, 16, true, leader);
       }
-      umma_commit(done_bar(sm, slot));
+      if (leader) umma_commit(done_bar(sm, slot));
+      __syncwarp();
+      const long long t2 = MMN_CLOCK();
+      t_idle += t1 - t0;
+      t_issue += t2 - t1;
     }
+    if (dbg && leader) { dbg[0] = t_idle; dbg[1] = t_issue; }
   }
   __device__ static __forceinline__ void wait(const Smem& sm, State& es, int slot) {
     if (es.pending[slot]) {
+      const long long t0 = MMN_CLOCK();
       mbar_wait(done_bar(sm, slot), es.parity[slot]);
+      es.t[0] += MMN_CLOCK() - t0;
       es.parity[slot] ^= 1;
       es.pending[slot] = 0;
     }
@@ -312,25 +378,10 @@ struct TcEngine {
     wait(sm, es, es.seq & 1);          // older commit first (in-order completion)
     wait(sm, es, (es.seq & 1) ^ 1);
   }
-  // hand the chunk staged in `slot` to the issuer.  a/b: image byte addresses; *_mn: MN-major operand
-  // (k-slice step 1024 B, SWIZZLE_128B_BASE32B, group stride *_grp) else K-major (step 32 B, SWIZZLE_128B)
-  __device__ static __forceinline__ void post(const Smem& sm, State& es, int slot, unsigned a_hi, unsigned a_lo,
-                                              bool a_mn, unsigned a_grp, unsigned b_hi, unsigned b_lo, bool b_mn,
-                                              unsigned b_grp, int N, int nj, unsigned first, unsigned tmem_col) {
-    if (threadIdx.x == 0) {
-      TcCmd* c = cmd_slot(sm, slot);
-      c->a_hi = a_mn ? umma_desc_mn(a_hi, 0, a_grp) : umma_desc_k(a_hi, 0);
-      c->a_lo = a_mn ? umma_desc_mn(a_lo, 0, a_grp) : umma_desc_k(a_lo, 0);
-      c->b_hi = b_mn ? umma_desc_mn(b_hi, 0, b_grp) : umma_desc_k(b_hi, 0);
-      c->b_lo = b_mn ? umma_desc_mn(b_lo, 0, b_grp) : umma_desc_k(b_lo, 0);
-      c->a_step = a_mn ? 64u : 2u;
-      c->b_step = b_mn ? 64u : 2u;
-      c->idesc = umma_idesc_tf32(128, N, a_mn ? 1 : 0, b_mn ? 1 : 0);
-      c->tmem = es.tmem + tmem_col;
-      c->nj = (unsigned)nj;
-      c->first = first;
-      c->quit = 0;
-    }
+  // hand the chunk staged in `slot` to the issuer (the operand images sit at fixed places of the slot)
+  __device__ static __forceinline__ void post(const Smem& sm, State& es, int slot, unsigned kind, int N, int nj,
+                                              unsigned first) {
+    if (threadIdx.x == 0) cmd_slot(sm, slot)->op = kind | (N == 64 ? 4u : 0u) | (first ? 8u : 0u) | ((unsigned)nj << 4);
     fence_proxy_async();               // this thread's image stores -> visible to the tensor-core (async) proxy
     tc_fence_before();                 // this thread's earlier tcgen05.ld of the accumulator are ordered before
     mbar_arrive(full_bar(sm, slot));
@@ -339,14 +390,14 @@ struct TcEngine {
   }
 
   // ---- weight block: [nrows <= 64][ncols <= 32] of row-major W -> K-major image pair (rows = n) ----
-  __device__ static __forceinline__ void w_load_k(float (&w)[8], const float* __restrict__ W, int ldw, int row0, int nrows,
+  __device__ static __forceinline__ void w_load_k(float (&w)[4 * QW], const float* __restrict__ W, int ldw, int row0, int nrows,
                                                   int col0, int ncols, bool vec) {
     const int t = threadIdx.x;
     if (vec) {
       const int c4 = (t & 7) * 4;
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int r = (t >> 3) + 32 * i;
+      for (int i = 0; i < QW; ++i) {
+        const int r = (t >> 3) + (NW / 8) * i;
         float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < nrows && c4 < ncols) {
           const float* p = W + (long long)(row0 + r) * ldw + col0 + c4;
@@ -358,33 +409,33 @@ struct TcEngine {
     } else {
       const int c = t & 31;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = (t >> 5) + 8 * i;
+      for (int i = 0; i < 4 * QW; ++i) {
+        const int r = (t >> 5) + (NW / 32) * i;
         w[i] = (r < nrows && c < ncols) ? __ldg(W + (long long)(row0 + r) * ldw + col0 + c) : 0.f;
       }
     }
   }
-  __device__ static __forceinline__ void w_store_k(float* hi, float* lo, const float (&w)[8], bool vec) {
+  __device__ static __forceinline__ void w_store_k(float* hi, float* lo, const float (&w)[4 * QW], bool vec) {
     const int t = threadIdx.x;
     if (vec) {
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
-        tc_store_quad<false>(hi, lo, (t >> 3) + 32 * i, t & 7, make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]));
+      for (int i = 0; i < QW; ++i)
+        tc_store_quad<false>(hi, lo, (t >> 3) + (NW / 8) * i, t & 7, make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]));
     } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) tc_store_elem<false>(hi, lo, (t >> 5) + 8 * i, t & 31, w[i]);
+      for (int i = 0; i < 4 * QW; ++i) tc_store_elem<false>(hi, lo, (t >> 5) + (NW / 32) * i, t & 31, w[i]);
     }
   }
   // ---- weight block for the data gradient: rows n (contraction) x up to 64 output columns j ->
   //      MN-major image pairs, one 4 KB image per group of 32 columns ----
-  __device__ static __forceinline__ void w_load_mn(float (&w)[8], const float* __restrict__ W, int ldw, int row0, int nrows,
+  __device__ static __forceinline__ void w_load_mn(float (&w)[4 * QW], const float* __restrict__ W, int ldw, int row0, int nrows,
                                                    int col0, int ncols, bool vec) {
     const int t = threadIdx.x;
     if (vec) {
       const int c4 = (t & 15) * 4;
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int r = (t >> 4) + 16 * i;
+      for (int i = 0; i < QW; ++i) {
+        const int r = (t >> 4) + (NW / 16) * i;
         float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < nrows && c4 < ncols) {
           const float* p = W + (long long)(row0 + r) * ldw + col0 + c4;
@@ -396,39 +447,69 @@ struct TcEngine {
     } else {
       const int c = t & 63;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = (t >> 6) + 4 * i;
+      for (int i = 0; i < 4 * QW; ++i) {
+        const int r = (t >> 6) + (NW / 64) * i;
         w[i] = (r < nrows && c < ncols) ? __ldg(W + (long long)(row0 + r) * ldw + col0 + c) : 0.f;
       }
     }
   }
-  __device__ static __forceinline__ void w_store_mn(float* hi, float* lo, const float (&w)[8], bool vec) {
+  __device__ static __forceinline__ void w_store_mn(float* hi, float* lo, const float (&w)[4 * QW], bool vec) {
     const int t = threadIdx.x;
     if (vec) {
       const int c4 = t & 15, g = c4 >> 3;
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
-        tc_store_quad<true>(hi + g * 1024, lo + g * 1024, (t >> 4) + 16 * i, c4 & 7,
+      for (int i = 0; i < QW; ++i)
+        tc_store_quad<true>(hi + g * 1024, lo + g * 1024, (t >> 4) + (NW / 16) * i, c4 & 7,
                             make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]));
     } else {
       const int c = t & 63, g = c >> 5;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) tc_store_elem<true>(hi + g * 1024, lo + g * 1024, (t >> 6) + 4 * i, c & 31, w[i]);
+      for (int i = 0; i < 4 * QW; ++i) tc_store_elem<true>(hi + g * 1024, lo + g * 1024, (t >> 6) + (NW / 64) * i, c & 31, w[i]);
     }
   }
 
-  // ---- activation chunk [128 x 32] -> image pair.  Global sources arrive in registers (a_chunk_load);
-  //      shared-memory tiles are read here.  NaN scan / sanitise for x, dropout when enabled. ----
+  // ---- activation chunk [128 x 32]: global sources are fetched into 8 registers per thread early ...
+  __device__ static __forceinline__ void a_load(float (&v)[4 * QA], const ASeg& sg, int k0, int kw, int rows_valid, bool vec) {
+    if (sg.kind != SEG_X && sg.kind != SEG_STASH) return;
+    const int t = threadIdx.x;
+    if (vec) {
+      const int c4 = (t & 7) * 4;
+#pragma unroll
+      for (int i = 0; i < QA; ++i) {
+        const int r = (t >> 3) + (NW / 8) * i;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows_valid && c4 < kw) {
+          const float4* p = reinterpret_cast<const float4*>(sg.ptr + (long long)r * sg.ld + k0 + c4);
+          q = sg.kind == SEG_X ? __ldg(p) : __ldcg(p);
+        }
+        v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+      }
+    } else {
+      const int c = t & 31;
+#pragma unroll
+      for (int i = 0; i < 4 * QA; ++i) {
+        const int r = (t >> 5) + (NW / 32) * i;
+        float x = 0.f;
+        if (r < rows_valid && c < kw) {
+          const float* p = sg.ptr + (long long)r * sg.ld + k0 + c;
+          x = sg.kind == SEG_X ? __ldg(p) : __ldcg(p);   // stash: written earlier by this CTA, L2-coherent load
+        }
+        v[i] = x;
+      }
+    }
+  }
+  // ---- ... and written as an image pair here; shared-memory tiles are read here.  NaN scan / sanitise
+  //      for x, dropout when enabled. ----
   template <bool MN>
-  __device__ static __forceinline__ void a_store(float* hi, float* lo, float (&v)[16], const Smem& sm, const ASeg& sg,
+  __device__ static __forceinline__ void a_store(float* hi, float* lo, float (&v)[4 * QA], const Smem& sm, const ASeg& sg,
                                                  int k0, int kw, const Drop& drop, bool scan_nan, bool vec) {
     const int t = threadIdx.x;
     const bool from_smem = sg.kind == SEG_SMEM || sg.kind == SEG_SMEM_STAGED;
     if (vec || from_smem) {
-      const int c4 = t & 7, r0 = t >> 3;
+      const int c4 = t & 7;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = r0 + 32 * i;
+      for (int i = 0; i < QA; ++i) {
+        const int r = (t >> 3) + (NW / 8) * i;
         float4 q;
         if (from_smem) q = *reinterpret_cast<const float4*>(sg.ptr + (long long)r * sg.ld + k0 + 4 * c4);   // zero-padded tile
         else q = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -463,10 +544,10 @@ struct TcEngine {
         tc_store_quad<MN>(hi, lo, r, c4, q);
       }
     } else {
-      const int c = t & 31, r0 = t >> 5;
+      const int c = t & 31;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int r = r0 + 8 * i;
+      for (int i = 0; i < 4 * QA; ++i) {
+        const int r = (t >> 5) + (NW / 32) * i;
         float x = v[i];
         if (sg.kind == SEG_X && x != x) {
           if (scan_nan) sm.rownan[r] = 1;
@@ -479,6 +560,12 @@ struct TcEngine {
       }
     }
   }
+  // this thread's accumulator slice: lane quarter q = warp & 3 (row 32 q + lane), column slice warp >> 2
+  static_assert(CS == 2, "the epilogues below give each thread 16-column slices (2 warps per lane quarter)");
+  // this thread's 16-column slice h of an N = 32 (h = 0) or N = 64 (h = 0, 1) accumulator: columns 32 h + 16 cs ..
+  __device__ static __forceinline__ void acc_load(const State& es, int q, int col, float (&v)[16]) {
+    tmem_ld16(es.tmem + ((unsigned)(32 * q) << 16) + col, v);
+  }
 
   // ------------------------------------------------------------------------------------------------
   // out[r][n] = bias[n] + sum_seg sum_k a[r][k] W[n][wcol + k]      (A, W K-major; N pass of 32 / 64)
@@ -487,18 +574,19 @@ struct TcEngine {
   __device__ static __forceinline__ void gemm_nt(const Smem& sm, State& es, const float* __restrict__ W, int ldw, int N,
                                                  const float* __restrict__ bias, const ASeg* segs, int nseg,
                                                  const Drop& drop, int rows_valid, bool scan_nan, Epi epi) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, half = warp >> 2;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, cs = warp >> 2;
+    const long long t_begin = MMN_CLOCK();
     bool avec[2];
     avec[0] = seg_vec_ok(segs[0]);
     avec[1] = nseg > 1 ? seg_vec_ok(segs[1]) : false;
     for (int n0 = 0; n0 < N; n0 += 64) {
       const int nrows = min(64, N - n0);
       const int Np = nrows <= 32 ? 32 : 64;
-      float wr[8], ar[16];
+      float wr[4 * QW], ar[4 * QA];
       ChunkIt it{0, 0};
       bool wv = w_vec_ok(W, ldw, segs[0].wcol);
       w_load_k(wr, W, ldw, n0, nrows, segs[0].wcol, min(KC, segs[0].width), wv);
-      a_chunk_load<4>(ar, segs[0], 0, min(KC, segs[0].width), rows_valid, avec[0]);
+      a_load(ar, segs[0], 0, min(KC, segs[0].width), rows_valid, avec[0]);
       unsigned first = 1;
       int slot = 0;
       while (it.valid(nseg)) {
@@ -517,29 +605,44 @@ struct TcEngine {
           const int nkw = min(KC, ns.width - nx.k0);
           wv = w_vec_ok(W, ldw, ns.wcol + nx.k0);
           w_load_k(wr, W, ldw, n0, nrows, ns.wcol + nx.k0, nkw, wv);
-          a_chunk_load<4>(ar, ns, nx.k0, nkw, rows_valid, avec[nx.s]);
+          a_load(ar, ns, nx.k0, nkw, rows_valid, avec[nx.s]);
         }
-        post(sm, es, slot, smem_u32(xh), smem_u32(xh + 4096), false, 0, smem_u32(wh), smem_u32(wh + 2048), false, 0,
-             Np, (kw + 7) >> 3, first, 0);
+        post(sm, es, slot, TC_OP_NT, Np, (kw + 7) >> 3, first);
         first = 0;
         it = nx;
       }
-      float bj[32];
-      const int cbeg = half * (Np >> 1);
+      auto load_bias = [&](int n, float (&bj)[16]) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) bj[i] = (i < (Np >> 1) && n0 + cbeg + i < N) ? __ldg(bias + n0 + cbeg + i) : 0.f;
+        for (int i = 0; i < 16; i += 4) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (n + i + 3 < N) b4 = __ldg(reinterpret_cast<const float4*>(bias + n + i));     // bias offsets are 16-byte aligned
+          else {
+            if (n + i < N) b4.x = __ldg(bias + n + i);
+            if (n + i + 1 < N) b4.y = __ldg(bias + n + i + 1);
+            if (n + i + 2 < N) b4.z = __ldg(bias + n + i + 2);
+          }
+          bj[i] = b4.x; bj[i + 1] = b4.y; bj[i + 2] = b4.z; bj[i + 3] = b4.w;
+        }
+      };
+      float bj[16];
+      load_bias(n0 + 16 * cs, bj);
       wait(sm, es, slot ^ 1);     // older commit first (in-order completion), then the last one
       wait(sm, es, slot);
       tc_fence_after();
+      const long long t_epi = MMN_CLOCK();
       const int r = 32 * q + lane;
-      for (int c0 = 0; c0 < (Np >> 1); c0 += 16) {
+      for (int h = 0; h < (Np >> 5); ++h) {
+        const int cb = 32 * h + 16 * cs;
+        if (h) load_bias(n0 + cb, bj);
         float v[16];
-        tmem_ld16(es.tmem + ((unsigned)(32 * q) << 16) + cbeg + c0, v);
+        acc_load(es, q, cb, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) epi(r, n0 + cbeg + c0 + i, v[i] + bj[c0 + i]);
+        for (int i = 0; i < 16; ++i) epi(r, n0 + cb + i, v[i] + bj[i]);
       }
+      es.t[4] += MMN_CLOCK() - t_epi;
     }
-    MMN_WSYNC();                  // outputs (and the row NaN flags) visible to every worker
+    MMN_WSYNC_N(kWorkers);        // outputs (and the row NaN flags) visible to every worker
+    es.t[1] += MMN_CLOCK() - t_begin;
   }
 
   // ------------------------------------------------------------------------------------------------
@@ -548,19 +651,22 @@ struct TcEngine {
   template <class Pre, class Epi>
   __device__ static __forceinline__ void gemm_nn(const Smem& sm, State& es, const float* dz, int ldd, int N,
                                                  const float* __restrict__ W, int ldw, int col0, int J, Pre pre, Epi epi) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, half = warp >> 2;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, cs = warp >> 2;
     const int r = 32 * q + lane;
+    const long long t_begin = MMN_CLOCK();
     Drop nodrop;
     nodrop.enabled = 0; nodrop.seed_mix = 0; nodrop.thr = 0; nodrop.row_base = 0; nodrop.scale = 1.f;
     for (int j0 = 0; j0 < J; j0 += 64) {
       const int jw = min(64, J - j0);
       const int Np = jw <= 32 ? 32 : 64;
-      const int cbeg = half * (Np >> 1);
-      float pv[32];
+      float pv[16];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) pv[i] = i < (Np >> 1) ? pre(r, j0 + cbeg + i) : 0.f;
+      for (int i = 0; i < 16; i += 4) {
+        const float4 p4 = pre(r, j0 + 16 * cs + i);
+        pv[i] = p4.x; pv[i + 1] = p4.y; pv[i + 2] = p4.z; pv[i + 3] = p4.w;
+      }
       const bool wv = w_vec_ok(W, ldw, col0 + j0);
-      float wr[8], dummy[16];
+      float wr[4 * QW], dummy[4 * QA];
       w_load_mn(wr, W, ldw, 0, min(32, N), col0 + j0, jw, wv);
       unsigned first = 1;
       int slot = 0;
@@ -575,21 +681,31 @@ struct TcEngine {
         sg.ptr = dz; sg.ld = ldd; sg.width = N; sg.kind = SEG_SMEM; sg.wcol = 0;
         a_store<false>(xh, xh + 4096, dummy, sm, sg, n0, nw, nodrop, false, false);
         if (n0 + 32 < N) w_load_mn(wr, W, ldw, n0 + 32, min(32, N - n0 - 32), col0 + j0, jw, wv);
-        post(sm, es, slot, smem_u32(xh), smem_u32(xh + 4096), false, 0, smem_u32(wh), smem_u32(wh + 2048), true, 4096,
-             Np, (nw + 7) >> 3, first, 0);
+        post(sm, es, slot, TC_OP_NN, Np, (nw + 7) >> 3, first);
         first = 0;
       }
       wait(sm, es, slot ^ 1);
       wait(sm, es, slot);
       tc_fence_after();
-      for (int c0 = 0; c0 < (Np >> 1); c0 += 16) {
-        float v[16];
-        tmem_ld16(es.tmem + ((unsigned)(32 * q) << 16) + cbeg + c0, v);
+      const long long t_epi = MMN_CLOCK();
+      for (int h = 0; h < (Np >> 5); ++h) {
+        const int cb = 32 * h + 16 * cs;
+        if (h) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) epi(r, j0 + cbeg + c0 + i, v[i], pv[c0 + i]);
+          for (int i = 0; i < 16; i += 4) {
+            const float4 p4 = pre(r, j0 + cb + i);
+            pv[i] = p4.x; pv[i + 1] = p4.y; pv[i + 2] = p4.z; pv[i + 3] = p4.w;
+          }
+        }
+        float v[16];
+        acc_load(es, q, cb, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) epi(r, j0 + cb + i, v[i], pv[i]);
       }
+      es.t[5] += MMN_CLOCK() - t_epi;
     }
-    MMN_WSYNC();
+    MMN_WSYNC_N(kWorkers);
+    es.t[2] += MMN_CLOCK() - t_begin;
   }
 
   // ------------------------------------------------------------------------------------------------
@@ -601,20 +717,23 @@ struct TcEngine {
   // ------------------------------------------------------------------------------------------------
   __device__ static __forceinline__ void gemm_tn(const Smem& sm, State& es, const float* dz, int ldd, int N, const ASeg& sg,
                                                  const Drop& drop, int rows_valid, float* __restrict__ gW, int ldw) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, half = warp >> 2;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, cs = warp >> 2;
     const bool vec_ok = ((ldw & 3) == 0) && ((sg.wcol & 3) == 0) && ((reinterpret_cast<size_t>(gW) & 15) == 0);
     const bool avec = seg_vec_ok(sg);
+    const long long t_begin = MMN_CLOCK();
     auto epilogue = [&](int slot, int nb0, int k0) {
       wait(sm, es, slot);
       tc_fence_after();
+      const long long t_epi = MMN_CLOCK();
+      constexpr int TC = 16;               // chunk columns per thread
       float v[16];
-      tmem_ld16(es.tmem + ((unsigned)(32 * q) << 16) + 32 * slot + half * 16, v);
+      acc_load(es, q, 32 * slot + TC * cs, v);
       const int n = nb0 + lane;
       if (q == 0 && n < N) {
-        const int kc = k0 + half * 16;
+        const int kc = k0 + TC * cs;
         float* dst = gW + (long long)n * ldw + sg.wcol + kc;
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
+        for (int i = 0; i < TC; i += 4) {
           if (vec_ok && kc + i + 3 < sg.width) {
             atomicAdd(reinterpret_cast<float4*>(dst + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
           } else {
@@ -624,13 +743,14 @@ struct TcEngine {
           }
         }
       }
+      es.t[6] += MMN_CLOCK() - t_epi;
     };
     for (int nb0 = 0; nb0 < N; nb0 += 32) {
-      float ar[16];
-      a_chunk_load<4>(ar, sg, 0, min(KC, sg.width), rows_valid, avec);
+      float ar[4 * QA];
+      a_load(ar, sg, 0, min(KC, sg.width), rows_valid, avec);
       drain(sm, es);
-      MMN_WSYNC();                 // every worker is past its reads of the staging buffers / dz tile writes
-      for (int idx = tid; idx < 128 * 8; idx += kThreads) {      // dz column group -> MN-major A image pair
+      MMN_WSYNC_N(kWorkers);       // every worker is past its reads of the staging buffers / dz tile writes
+      for (int idx = tid; idx < 128 * 8; idx += kWorkers) {      // dz column group -> MN-major A image pair
         const int rr = idx >> 3, c4 = idx & 7;
         const float4 v = *reinterpret_cast<const float4*>(dz + rr * ldd + nb0 + 4 * c4);
         tc_store_quad<true>(sm.XB, sm.XB + 4096, rr, c4, v);
@@ -642,16 +762,16 @@ struct TcEngine {
         float* ih = slot ? sm.XB + 8192 : sm.WB;
         wait(sm, es, slot);        // (already collected by the epilogue two chunks ago)
         a_store<true>(ih, ih + 4096, ar, sm, sg, k0, kw, drop, false, avec);
-        if (k0 + KC < sg.width) a_chunk_load<4>(ar, sg, k0 + KC, min(KC, sg.width - k0 - KC), rows_valid, avec);
-        post(sm, es, slot, smem_u32(sm.XB), smem_u32(sm.XB + 4096), true, 0, smem_u32(ih), smem_u32(ih + 4096), true, 0,
-             32, 16, 1u, 32 * slot);
+        if (k0 + KC < sg.width) a_load(ar, sg, k0 + KC, min(KC, sg.width - k0 - KC), rows_valid, avec);
+        post(sm, es, slot, TC_OP_TN, 32, 16, 1u);
         if (prev_slot >= 0) epilogue(prev_slot, nb0, prev_k0);
         prev_slot = slot;
         prev_k0 = k0;
       }
       if (prev_slot >= 0) epilogue(prev_slot, nb0, prev_k0);
     }
-    MMN_WSYNC();
+    MMN_WSYNC_N(kWorkers);
+    es.t[3] += MMN_CLOCK() - t_begin;
   }
 };
 

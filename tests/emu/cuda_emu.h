@@ -166,7 +166,8 @@ inline T shfl(T v, unsigned src_lane) {
 #define gridDim (emu::gDim())
 
 static inline void __syncthreads() { emu::block_barrier(0, nullptr); }
-#define MMN_WSYNC() emu::named_barrier(256)
+#define MMN_WSYNC_N(n) emu::named_barrier(n)
+#define MMN_CLOCK() 0ll
 static inline int __syncthreads_or(int p) { int r; emu::block_barrier(p != 0, &r); return r; }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_barrier(); }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu::shfl(v, (threadIdx.x % 32) ^ m); }
@@ -175,6 +176,7 @@ template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) {
 }
 template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return emu::shfl(v, src); }
 static inline void __threadfence() {}
+static inline void __trap() { abort(); }
 
 template <class T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 static inline void atomicAdd(float4* p, float4 v) { p->x += v.x; p->y += v.y; p->z += v.z; p->w += v.w; }

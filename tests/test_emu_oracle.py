@@ -8,3 +8,11 @@ from parity_cases import CASES, run_parity_case
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_parity_case(emu, name):
     run_parity_case(name, "cpu")
+
+
+@pytest.mark.parametrize("name", ["multi_tile_ragged", "mnar_rows", "dropout_mnar", "mlp_kind_wide_hidden"])
+def test_parity_case_tc_engine(emu, monkeypatch, name):
+    """the tcgen05 engine's staging / command protocol against the emulator's functional UMMA model"""
+    monkeypatch.setenv("MMN_ENGINE", "tc")
+    model = run_parity_case(name, "cpu")
+    assert emu.dll.mmn_plan_engine(model.runtime().plan) == 1
