@@ -79,6 +79,7 @@ class _Runtime:
         self.gflat = torch.zeros(self.n_grads, dtype=torch.float32, device=self.device)
         self.sumC = sum(m.n_classes for m in self.packed.decoders)
         self._ws = None
+        self._copy_stream = None
         self._flags = torch.zeros(max(self.E, 1), dtype=torch.int32, device=self.device)
         self.step_counter = 0
         self.dropout_base_seed = int(torch.initial_seed() & 0x7FFFFFFF)
@@ -113,6 +114,44 @@ class _Runtime:
         if self.device.type == "cuda":
             return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         return C.c_void_p(0)
+
+    def staged(self, loader):
+        """Iterate a loader one batch ahead: the host->device copies of batch i+1 (multimodn.py:132-135)
+        run on a side stream while batch i computes.  Yields (data, target, encoder_sequence) with data
+        and target already on the device."""
+        if self.device.type != "cuda":
+            for batch in loader:
+                yield (list(batch) + [None])[:3]
+            return
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        main = torch.cuda.current_stream(self.device)
+
+        def fetch(batch):
+            data, target, seq = (list(batch) + [None])[:3]
+            with torch.cuda.stream(self._copy_stream):
+                dev = [torch.as_tensor(t).to(device=self.device, dtype=torch.float32, non_blocking=True) for t in data]
+                tgt = None if target is None else torch.as_tensor(target).to(device=self.device, dtype=torch.int64,
+                                                                             non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            return dev, tgt, seq, ev
+
+        it = iter(loader)
+        try:
+            nxt = fetch(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            dev, tgt, seq, ev = nxt
+            try:
+                nxt = fetch(next(it))
+            except StopIteration:
+                nxt = None
+            main.wait_event(ev)
+            for t in dev + ([tgt] if tgt is not None else []):
+                t.record_stream(main)
+            yield dev, tgt, seq
 
     def prepare_batch(self, data: List[Tensor], target: Optional[Tensor], seq: List[Tuple[int, int]],
                       missing_mode: str, dp):
@@ -337,8 +376,7 @@ class MultiModN(nn.Module):
         batch_metrics = rt.new_metrics() if log_interval else None
         E, D = rt.E, rt.D
 
-        for batch_idx, batch in enumerate(train_loader):
-            data, target, encoder_sequence = (list(batch) + [None])[:3]
+        for batch_idx, (data, target, encoder_sequence) in enumerate(rt.staged(train_loader)):
             seq = self.get_encoder_iterable(encoder_sequence, shuffle_mode=self.shuffle_mode, train=True)
             optimizer.zero_grad()
             mb, keep, n_rows = rt.prepare_batch(list(data), target, seq, self.missing_mode, self._dp)
@@ -392,8 +430,7 @@ class MultiModN(nn.Module):
         n_batches = len(test_loader)
         metrics = rt.new_metrics()
         outs, tgts = [], []
-        for batch in test_loader:
-            data, target, encoder_sequence = (list(batch) + [None])[:3]
+        for data, target, encoder_sequence in rt.staged(test_loader):
             seq = self.get_encoder_iterable(encoder_sequence, shuffle_mode=self.shuffle_mode, train=False)
             mb, keep, n_rows = rt.prepare_batch(list(data), target, seq, self.missing_mode, self._dp)
             last = torch.zeros((n_rows, rt.sumC), dtype=torch.float32, device=rt.device)
@@ -441,8 +478,7 @@ class MultiModN(nn.Module):
         self.eval()
         rt = self.runtime()
         states = []
-        for batch in data_loader:
-            data, _, encoder_sequence = (list(batch) + [None])[:3]
+        for data, _, encoder_sequence in rt.staged(data_loader):
             seq = self.get_encoder_iterable(encoder_sequence, shuffle_mode=self.shuffle_mode, train=False)
             mb, keep, n_rows = rt.prepare_batch(list(data), None, seq, self.missing_mode, None)
             st = torch.empty((n_rows, rt.S), dtype=torch.float32, device=rt.device)

@@ -1,0 +1,86 @@
+"""CPU, world_size 2 over gloo: the data-parallel path of MultiModN (row-sharded batches, gradient
+all-reduce, epoch-metric all-reduce, batch-mode skip-flag all-reduce) reproduces the single-process
+result on the concatenated batch.  Kernels run on the CPU emulator build (tests/emu); on the B200 box the
+same host code drives NCCL (bench.py --gpus N)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+from torch.nn import CrossEntropyLoss
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(HERE, "emu"))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _make(missing_mode, optimizer):
+    from emu_backend import get_emu_lib
+    from multimodn_b200 import MultiModN, FusedAdam
+    from oracle.spec_io import random_spec, synthetic_batch
+    from model_utils import model_from_spec
+    lib = get_emu_lib()
+    MultiModN._lib_factory = staticmethod(lambda: lib)
+    rng = np.random.default_rng(21)
+    feats = [6, 11, 20]
+    spec = random_spec(rng, 16, feats, enc_hidden=(8, 8), n_decoders=2, dec_hidden=(8,))
+    data, y = synthetic_batch(rng, feats, 2, 96, mnar=True)
+    if missing_mode == "batch":
+        data = [np.nan_to_num(x) for x in data]
+        data[1][70, 2] = np.nan                    # lives in rank 1's shard only: rank 0 must skip too
+    model = model_from_spec(spec, 0.9, 0.5, "cpu", missing_mode)
+    opt = FusedAdam(model, lr=1e-2) if optimizer == "fused" else torch.optim.Adam(list(model.parameters()), 1e-2)
+    return model, opt, data, y
+
+
+def _run(model, opt, data, y, lo, hi):
+    from multimodn_b200 import MultiModNHistory
+    hist = MultiModNHistory(["a", "b"])
+    loader = [([torch.from_numpy(x[lo:hi]) for x in data], torch.from_numpy(y[lo:hi]))]
+    for _ in range(2):
+        model.train_epoch(loader, opt, CrossEntropyLoss(), hist)
+    model.test(loader, CrossEntropyLoss(), hist, tag="val")
+    params = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).numpy().copy()
+    return params, hist
+
+
+def _worker(rank, world, port, missing_mode, optimizer, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model, opt, data, y = _make(missing_mode, optimizer)
+        model.enable_data_parallel()
+        n = len(y) // world
+        params, hist = _run(model, opt, data, y, rank * n, (rank + 1) * n)
+        if rank == 0:
+            np.savez(out, params=params, loss=np.stack(hist.loss["train"]), acc=np.stack(hist.accuracy["train"]),
+                     sc=np.stack(hist.state_change_loss), val=hist.loss["val"][0])
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("missing_mode,optimizer", [("row", "torch"), ("row", "fused"), ("batch", "torch")])
+def test_two_ranks_equal_one_rank(tmp_path, missing_mode, optimizer):
+    from helpers import assert_close
+    out = str(tmp_path / "dp.npz")
+    mp.spawn(_worker, args=(2, _free_port(), missing_mode, optimizer, out), nprocs=2, join=True)
+    got = np.load(out)
+    model, opt, data, y = _make(missing_mode, optimizer)
+    params, hist = _run(model, opt, data, y, 0, len(y))
+    assert_close(got["params"], params, rtol=2e-5, what="parameters after 2 DP steps")
+    assert_close(got["loss"], np.stack(hist.loss["train"]), rtol=1e-5, what="train loss history")
+    assert_close(got["acc"], np.stack(hist.accuracy["train"]), rtol=1e-6, what="train accuracy history")
+    assert_close(got["sc"], np.stack(hist.state_change_loss), rtol=1e-5, what="state-change history")
+    assert_close(got["val"], hist.loss["val"][0], rtol=1e-5, what="val loss")
