@@ -31,6 +31,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+# DRAM bytes of ONE launch of the step kernel at B = 65536 (ncu --set full; profiles/)
+DRAM_TRAFFIC_PER_LAUNCH = {"fp32-fma": 699.7e6 + 236.5e6, "tcgen05-3xtf32": 701.6e6 + 238.2e6}
+
 WORKLOAD = dict(name="c2_mimic", S=64, features=[6, 99, 1024], enc_hidden=(32, 32), n_decoders=2,
                 dec_hidden=(32, 32), dropout=0.2, err_penalty=1.0, state_change_penalty=0.3, lr=1e-3)
 
@@ -134,6 +137,15 @@ def cpu_port_rate(steps, warmup, B):
     return B * steps / dt, dt / steps
 
 
+def workload_config(B, world, **extra):
+    w = WORKLOAD
+    cfg = dict(workload=w["name"], state_size=w["S"], features=w["features"], enc_hidden=list(w["enc_hidden"]),
+               decoders=w["n_decoders"], dec_hidden=list(w["dec_hidden"]), dropout=w["dropout"],
+               batch_per_gpu=B, global_batch=B * world, missing_mode="row", parallelism=f"dp{world}")
+    cfg.update(extra)
+    return cfg
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -144,8 +156,8 @@ def run_reference(args):
     line = dict(impl="reference", metric="train samples/sec", value=rate, unit="samples/s", n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="fp32", data="synthetic",
-                config=dict(workload=WORKLOAD["name"], state_size=64, features=WORKLOAD["features"], decoders=2,
-                            batch_per_step=B, device="host CPU"),
+                config=workload_config(args.batch, max(1, args.gpus), optimizer="torch.optim.Adam",
+                                       device="host CPU", rows_per_timed_step=B),
                 cpu_baseline=dict(value=rate, unit="samples/s", cores=cores, kind="port",
                                   sample=f"{args.steps} train steps of {B} rows (vectorised torch port of the "
                                          f"reference, oracle/torch_port.py, {cores} threads)"),
@@ -225,9 +237,9 @@ def main():
 
     for i in range(W):
         step_resident(i)
-    with ClockSampler(local) as clk:
-        ms = timed(step_resident, K)
-    clocks = clk.summary()
+    clk = ClockSampler(local)
+    clk.__enter__()                                   # sampled over the value and kernel-only timed regions
+    ms = timed(step_resident, K)
     ms_per_step = ms / K
     value = B * world * K / (ms * 1e-3)
 
@@ -243,14 +255,21 @@ def main():
     for i in range(3):
         kernel_only(i)
     kms = timed(kernel_only, K) / K
+    for _ in range(3):                                # keep the load on while nvidia-smi gets a few samples in
+        timed(kernel_only, K)
+    clk.__exit__()
+    clocks = clk.summary()
     peaks, peak_kind = measured_peaks()
+    engine = {0: "fp32-fma", 1: "tcgen05-3xtf32"}[int(rt.lib.dll.mmn_plan_engine(rt.plan))]
     macs = macs_per_row(w)
     alg_bytes = B * (2 * 4 * sum(w["features"]) + 8 * w["n_decoders"])   # x read in fwd and again for wgrad
     achieved = alg_bytes / (kms * 1e-3) / 1e9
     flops = 6.0 * macs * B                                               # fwd + dgrad + wgrad
     fma_peak = 148 * 128 * 2 * 1.965e9 / 1e12
     roofline = dict(bound="hbm", achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"],
-                    traffic=None, kernel="mmn_step_kernel<4,true>", kernel_ms=kms, peak_source=peak_kind,
+                    traffic=DRAM_TRAFFIC_PER_LAUNCH.get(engine) if B == 65536 else None,
+                    traffic_source="ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_*_step_kernel_ncu.txt",
+                    kernel=f"mmn_step_kernel<{engine}, train>", kernel_ms=kms, peak_source=peak_kind,
                     algorithmic_bytes_per_sample=alg_bytes / B,
                     fp32_fma=dict(achieved_tflops=flops / (kms * 1e-3) / 1e12, peak_tflops_nominal=fma_peak,
                                   frac=flops / (kms * 1e-3) / 1e12 / fma_peak,
@@ -298,11 +317,8 @@ def main():
         line = dict(metric="train samples/sec", value=value, unit="samples/s", n_gpus=world, steps=K, warmup=W,
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fp32",
                     data="synthetic",
-                    config=dict(workload=w["name"], state_size=w["S"], features=w["features"], enc_hidden=list(w["enc_hidden"]),
-                                decoders=w["n_decoders"], dec_hidden=list(w["dec_hidden"]), dropout=w["dropout"],
-                                batch_per_gpu=B, global_batch=B * world, optimizer="FusedAdam", missing_mode="row",
-                                l2_policy=f"{n_resident} resident batches of {bytes_in / 1e6:.0f} MB each (> 126 MB L2), cycled",
-                                parallelism=f"dp{world}"),
+                    config=workload_config(B, world, optimizer="FusedAdam", engine=engine,
+                                           l2_policy=f"{n_resident} resident batches of {bytes_in / 1e6:.0f} MB each (> 126 MB L2), cycled"),
                     clocks=clocks, e2e=e2e, gpu_launches=3 * K, roofline=roofline, cpu_baseline=cpu)
         print(json.dumps(line))
     if dist is not None:

@@ -64,8 +64,9 @@ class _Runtime:
         if self.device.type != "cuda" and not self.lib.host_memory:
             raise RuntimeError(f"multimodn_b200 runs on CUDA devices only (got device '{self.device}'); "
                                "there is no CPU path")
-        if not isinstance(model.init_state, TrainableInitState):
-            raise NotImplementedError("the fused step supports TrainableInitState only")
+        sv = getattr(model.init_state, "state_value", None)
+        if not isinstance(sv, nn.Parameter) or tuple(sv.shape) != (1, int(model.init_state.state_size)):
+            raise NotImplementedError("the fused step supports TrainableInitState only (a (1, S) `state_value` parameter)")
         self.S = int(model.init_state.state_size)
         self.packed = PackedModel(model.init_state.state_value, model.encoders, model.decoders, self.S)
         self.E, self.D = len(self.packed.encoders), len(self.packed.decoders)
