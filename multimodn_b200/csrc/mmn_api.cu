@@ -20,6 +20,7 @@ struct mmn_plan {
   int max_smem = 0;
   int engine = MMN_ENGINE_FMA;   // MMN_ENGINE_*
   int rm = 0;                    // FMA engine: rows per tile / 32
+  int occ = 1;                   // FMA engine: CTAs per SM the kernel variant is built for
 };
 
 namespace {
@@ -42,8 +43,9 @@ int fail(const char* fmt, ...) {
 
 int round32(int v) { return (v + 31) & ~31; }
 
-size_t fma_smem(const DevPlan& P, int rm) {
-  const size_t stage = rm == 4 ? FmaEngine<4>::stage_bytes() : rm == 2 ? FmaEngine<2>::stage_bytes() : FmaEngine<1>::stage_bytes();
+size_t fma_smem(const DevPlan& P, int rm, int occ = 1) {
+  const size_t stage = occ == 2 ? FmaEngine<2, 2>::stage_bytes()
+                                : rm == 4 ? FmaEngine<4>::stage_bytes() : rm == 2 ? FmaEngine<2>::stage_bytes() : FmaEngine<1>::stage_bytes();
   return step_smem_bytes(P, 32 * rm, stage);
 }
 size_t tc_smem(const DevPlan& P) { return step_smem_bytes(P, TcEngine::TM, TcEngine::stage_bytes()); }
@@ -57,7 +59,8 @@ int tile_rows(const mmn_plan* p) { return p->engine == MMN_ENGINE_TC ? TcEngine:
 int grid_for(const mmn_plan* p, int64_t n_rows) {
   const int tm = tile_rows(p);
   const int64_t tiles = (n_rows + tm - 1) / tm;
-  return (int)std::max<int64_t>(1, std::min<int64_t>(tiles, p->n_sms));
+  const int per_sm = p->engine == MMN_ENGINE_FMA ? p->occ : 1;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)p->n_sms * per_sm));
 }
 
 int check_layer(const mmn_layer_desc& l, int S, int64_t n_params, const char* what, int idx, int j) {
@@ -162,6 +165,10 @@ extern "C" int mmn_plan_create(const mmn_model_desc* desc, mmn_plan** out) {
     return fail("mmn_plan_create: no CUDA device");
   }
   p->rm = pick_rm(p);
+  // two 64-row CTAs per SM (16 resident warps) when both fit: 228 KB of shared memory per SM, 1 KB reserved per CTA
+  const char* occ_env = getenv("MMN_FMA_OCC");        // "1" | "2" | unset = auto
+  const bool occ2_fits = fma_smem(P, 2, 2) + 1024 <= (size_t)(233472 / 2);
+  if (occ2_fits && !(occ_env && !strcmp(occ_env, "1"))) { p->rm = 2; p->occ = 2; }
   const bool tc_fits = tc_smem(P) <= (size_t)p->max_smem;
   const char* want = getenv("MMN_ENGINE");            // "tc" | "fma" | unset = auto
   if (want && !strcmp(want, "tc") && !tc_fits) {
@@ -272,6 +279,7 @@ int launch_engine(const mmn_plan* plan, const StepArgs& a_in, void* stream) {
 template <bool TRAIN>
 int launch_step(const mmn_plan* plan, const StepArgs& a, void* stream) {
   if (plan->engine == MMN_ENGINE_TC) return launch_engine<TcEngine, TRAIN>(plan, a, stream);
+  if (plan->occ == 2) return launch_engine<FmaEngine<2, 2>, TRAIN>(plan, a, stream);
   switch (plan->rm) {
     case 4: return launch_engine<FmaEngine<4>, TRAIN>(plan, a, stream);
     case 2: return launch_engine<FmaEngine<2>, TRAIN>(plan, a, stream);

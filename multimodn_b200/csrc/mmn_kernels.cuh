@@ -394,7 +394,7 @@ __device__ __forceinline__ void fma_gemm_nn(const Smem& sm, const float* dz, int
 // shared memory and the tile's contribution is added to global memory with one red per element.
 // Input chunks and the reduction scratch are double-buffered: one __syncthreads per 32x32 block.
 // ------------------------------------------------------------------------------------------------
-template <int RM>
+template <int RM, int REDBUFS>
 __device__ __forceinline__ void fma_gemm_tn(const Smem& sm, const float* dz, int ldd, int N, const ASeg& sg,
                                         const Drop& drop, int rows_valid, float* __restrict__ gW, int ldw) {
   constexpr int TM = Cfg<RM>::TM;
@@ -469,12 +469,13 @@ __device__ __forceinline__ void fma_gemm_tn(const Smem& sm, const float* dz, int
         acc[3][0] = fmaf(dv.w, iv.x, acc[3][0]); acc[3][1] = fmaf(dv.w, iv.y, acc[3][1]);
         acc[3][2] = fmaf(dv.w, iv.z, acc[3][2]); acc[3][3] = fmaf(dv.w, iv.w, acc[3][3]);
       }
+      if (REDBUFS == 1) MMN_WSYNC_N(kThreads);      // single scratch: every reader of the pending block is done
       float* red = sm.RED + rbuf * (kGroups * 1024) + g * 1024;
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         *reinterpret_cast<float4*>(red + (4 * nt + i) * 32 + 4 * kt) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
       pend_n0 = n0; pend_k0 = k0; pend_rbuf = rbuf;
-      rbuf ^= 1;
+      if (REDBUFS == 2) rbuf ^= 1;
     }
   }
   MMN_WSYNC_N(kThreads);
@@ -485,21 +486,25 @@ __device__ __forceinline__ void fma_gemm_tn(const Smem& sm, const float* dz, int
 // FMA engine: the three GEMM shapes on the FP32 pipe (any tile height RM in {1, 2, 4})
 // ------------------------------------------------------------------------------------------------
 struct NoState { long long t[16]; };
-template <int RM_>
+// MINB = CTAs per SM the kernel is compiled for (2 halves the register budget and single-buffers the
+// weight-gradient scratch so that two 64-row tiles share an SM: 16 resident warps instead of 8)
+template <int RM_, int MINB_ = 1>
 struct FmaEngine {
   static constexpr int RM = RM_;
   static constexpr int TM = 32 * RM_;
   static constexpr bool kTensor = false;
   static constexpr int kWorkers = kThreads;
   static constexpr int kBlockThreads = kThreads;
+  static constexpr int kMinBlocks = MINB_;
+  static constexpr int kRedBufs = MINB_ >= 2 ? 1 : 2;
   using State = NoState;
   __device__ static __forceinline__ void issuer_loop(const Smem&, State&, long long* = nullptr) {}
-  static size_t stage_bytes() { return (size_t)(2 * (TM * LDX + 32 * LDX) + 2 * kGroups * 1024) * 4; }
+  static size_t stage_bytes() { return (size_t)(2 * (TM * LDX + 32 * LDX) + kRedBufs * kGroups * 1024) * 4; }
   __device__ static __forceinline__ char* carve(Smem& sm, char* p) {
     float* f = reinterpret_cast<float*>(p);
     sm.XB = f; f += 2 * TM * LDX;
     sm.WB = f; f += 2 * 32 * LDX;
-    sm.RED = f; f += 2 * kGroups * 1024;
+    sm.RED = f; f += kRedBufs * kGroups * 1024;
     return reinterpret_cast<char*>(f);
   }
   __device__ static __forceinline__ void init(const Smem&, State&) {}
@@ -517,7 +522,7 @@ struct FmaEngine {
   }
   __device__ static __forceinline__ void gemm_tn(const Smem& sm, State&, const float* dz, int ldd, int N, const ASeg& sg,
                                                  const Drop& drop, int rows_valid, float* __restrict__ gW, int ldw) {
-    fma_gemm_tn<RM>(sm, dz, ldd, N, sg, drop, rows_valid, gW, ldw);
+    fma_gemm_tn<RM, kRedBufs>(sm, dz, ldd, N, sg, drop, rows_valid, gW, ldw);
   }
 };
 
@@ -598,7 +603,7 @@ __device__ __forceinline__ unsigned warp_sum_u(unsigned v) {
 // the step kernel
 // ------------------------------------------------------------------------------------------------
 template <class ENG, bool TRAIN>
-__global__ void __launch_bounds__(ENG::kBlockThreads, 1) mmn_step_kernel(const StepArgs args) {
+__global__ void __launch_bounds__(ENG::kBlockThreads, ENG::kMinBlocks) mmn_step_kernel(const StepArgs args) {
   constexpr int RM = ENG::RM;
   constexpr int TM = ENG::TM;
   constexpr int NT = ENG::kWorkers;

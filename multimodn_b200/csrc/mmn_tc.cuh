@@ -261,6 +261,7 @@ struct TcEngine {
   static constexpr int QW = 512 / NW;                     // float4 per thread of a weight block
   static constexpr int CS = NW / 128;                     // column slices of the accumulator (one per warp of a quarter)
   static constexpr int kBlockThreads = kWorkers + 32;     // + the MMA-issuing warp
+  static constexpr int kMinBlocks = 1;
   using State = TcState;
   static size_t stage_bytes() { return 1024 + (size_t)(kTcStageXB + kTcStageWB + 512) * 4 + 64 + 2 * sizeof(TcCmd); }
 
