@@ -176,7 +176,8 @@ int mmn_adam_step(const mmn_plan* plan, float* params, const float* grads, float
 
 /* Diagnostic (tests only): one 128-row tcgen05 3xTF32 GEMM in each operand configuration of the
  * tensor-core engine.  mode 0: out[r][j] = sum_k a[r][k] b[j][k]; mode 1: out[r][j] = sum_k a[r][k] b[k][j];
- * mode 2: out[i][j] = sum_r a[r][i] b[r][j] (a: 128 x 64, rows i < 64 meaningful).  k = 32, n in {32, 64}. */
+ * mode 2: out[i][j] = sum_r a[r][i] b[r][j] (a: 128 x 64, rows i < 64 meaningful); modes 3 / 4 = modes 0 / 1 with
+ * the A operand in tensor memory (tcgen05.st + TS-form MMA).  k = 32, n in {32, 64}. */
 int mmn_selftest_umma(int mode, int n, const float* a, const float* b, float* out, void* stream);
 
 #ifdef __cplusplus

@@ -297,22 +297,39 @@ __device__ __forceinline__ void fma_gemm_nt(const Smem& sm, const float* __restr
       }
       MMN_WSYNC_N(kThreads);
       const int nq = (kw + 3) >> 2;
-#pragma unroll 2
-      for (int q = 0; q < nq; ++q) {
+      const float* ap[RM];
+#pragma unroll
+      for (int i = 0; i < RM; ++i) ap[i] = a + (ty + 32 * i) * lda;
+      const float* bp = WBb + tx * LDX;
+      auto kstep = [&](int q) {          // q-th float4 of the chunk: RM + 4 LDS.128 feed 16 RM FFMA
         float4 av[RM], bv[4];
 #pragma unroll
-        for (int i = 0; i < RM; ++i) av[i] = *reinterpret_cast<const float4*>(a + (ty + 32 * i) * lda + 4 * q);
+        for (int i = 0; i < RM; ++i) av[i] = *reinterpret_cast<const float4*>(ap[i] + 4 * q);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) bv[j] = *reinterpret_cast<const float4*>(WBb + (tx + 8 * j) * LDX + 4 * q);
+        for (int j = 0; j < 4; ++j) bv[j] = *reinterpret_cast<const float4*>(bp + 8 * j * LDX + 4 * q);
 #pragma unroll
         for (int i = 0; i < RM; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            acc[i][j] = fmaf(av[i].x, bv[j].x, acc[i][j]);
-            acc[i][j] = fmaf(av[i].y, bv[j].y, acc[i][j]);
-            acc[i][j] = fmaf(av[i].z, bv[j].z, acc[i][j]);
-            acc[i][j] = fmaf(av[i].w, bv[j].w, acc[i][j]);
-          }
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i].x, bv[j].x, acc[i][j]);
+#pragma unroll
+        for (int i = 0; i < RM; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i].y, bv[j].y, acc[i][j]);
+#pragma unroll
+        for (int i = 0; i < RM; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i].z, bv[j].z, acc[i][j]);
+#pragma unroll
+        for (int i = 0; i < RM; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i].w, bv[j].w, acc[i][j]);
+      };
+      if (RM <= 2 && nq == 8) {          // full chunk: every shared-memory offset is an immediate
+#pragma unroll
+        for (int q = 0; q < 8; ++q) kstep(q);
+      } else {
+#pragma unroll 2
+        for (int q = 0; q < nq; ++q) kstep(q);
       }
       it = nx;
       buf ^= 1;
@@ -357,24 +374,43 @@ __device__ __forceinline__ void fma_gemm_nn(const Smem& sm, const float* dz, int
       if (n0 + 32 < N) w_block_load(wr, W, ldw, n0 + 32, min(32, N - n0 - 32), col0 + j0, jw, wv);
       MMN_WSYNC_N(kThreads);
       const int nq = (nw + 3) >> 2;
-#pragma unroll 2
-      for (int q = 0; q < nq; ++q) {
+      const float* ap[RM];
+#pragma unroll
+      for (int i = 0; i < RM; ++i) ap[i] = dz + (ty + 32 * i) * ldd + n0;
+      const float* bp = WBb + 4 * tx;
+      auto kstep = [&](int q) {
         float4 av[RM], bv[4];
 #pragma unroll
-        for (int i = 0; i < RM; ++i) av[i] = *reinterpret_cast<const float4*>(dz + (ty + 32 * i) * ldd + n0 + 4 * q);
+        for (int i = 0; i < RM; ++i) av[i] = *reinterpret_cast<const float4*>(ap[i] + 4 * q);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) bv[u] = *reinterpret_cast<const float4*>(WBb + (4 * q + u) * LDX + 4 * tx);
+        for (int u = 0; u < 4; ++u) bv[u] = *reinterpret_cast<const float4*>(bp + (4 * q + u) * LDX);
 #pragma unroll
         for (int i = 0; i < RM; ++i) {
           acc[i][0] = fmaf(av[i].x, bv[0].x, acc[i][0]); acc[i][1] = fmaf(av[i].x, bv[0].y, acc[i][1]);
           acc[i][2] = fmaf(av[i].x, bv[0].z, acc[i][2]); acc[i][3] = fmaf(av[i].x, bv[0].w, acc[i][3]);
+        }
+#pragma unroll
+        for (int i = 0; i < RM; ++i) {
           acc[i][0] = fmaf(av[i].y, bv[1].x, acc[i][0]); acc[i][1] = fmaf(av[i].y, bv[1].y, acc[i][1]);
           acc[i][2] = fmaf(av[i].y, bv[1].z, acc[i][2]); acc[i][3] = fmaf(av[i].y, bv[1].w, acc[i][3]);
+        }
+#pragma unroll
+        for (int i = 0; i < RM; ++i) {
           acc[i][0] = fmaf(av[i].z, bv[2].x, acc[i][0]); acc[i][1] = fmaf(av[i].z, bv[2].y, acc[i][1]);
           acc[i][2] = fmaf(av[i].z, bv[2].z, acc[i][2]); acc[i][3] = fmaf(av[i].z, bv[2].w, acc[i][3]);
+        }
+#pragma unroll
+        for (int i = 0; i < RM; ++i) {
           acc[i][0] = fmaf(av[i].w, bv[3].x, acc[i][0]); acc[i][1] = fmaf(av[i].w, bv[3].y, acc[i][1]);
           acc[i][2] = fmaf(av[i].w, bv[3].z, acc[i][2]); acc[i][3] = fmaf(av[i].w, bv[3].w, acc[i][3]);
         }
+      };
+      if (RM <= 2 && nq == 8) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) kstep(q);
+      } else {
+#pragma unroll 2
+        for (int q = 0; q < nq; ++q) kstep(q);
       }
       buf ^= 1;
     }
@@ -455,11 +491,12 @@ __device__ __forceinline__ void fma_gemm_tn(const Smem& sm, const float* dz, int
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-#pragma unroll 4
+      const float* dp = dz + g * RPG * ldd + n0 + 4 * nt;
+      const float* ip = a + g * RPG * lda + 4 * kt;
+#pragma unroll (RM <= 2 ? RPG : 4)
       for (int rr = 0; rr < RPG; ++rr) {
-        const int r = g * RPG + rr;
-        const float4 dv = *reinterpret_cast<const float4*>(dz + r * ldd + n0 + 4 * nt);
-        const float4 iv = *reinterpret_cast<const float4*>(a + r * lda + 4 * kt);
+        const float4 dv = *reinterpret_cast<const float4*>(dp + rr * ldd);
+        const float4 iv = *reinterpret_cast<const float4*>(ip + rr * lda);
         acc[0][0] = fmaf(dv.x, iv.x, acc[0][0]); acc[0][1] = fmaf(dv.x, iv.y, acc[0][1]);
         acc[0][2] = fmaf(dv.x, iv.z, acc[0][2]); acc[0][3] = fmaf(dv.x, iv.w, acc[0][3]);
         acc[1][0] = fmaf(dv.y, iv.x, acc[1][0]); acc[1][1] = fmaf(dv.y, iv.y, acc[1][1]);

@@ -26,7 +26,7 @@ namespace mmn {
 
 constexpr int kTcStageXB = 2 * 2 * 128 * 32;   // floats: 2 buffers x (hi, lo) x [128 x 32]      = 64 KB
 constexpr int kTcStageWB = 2 * 2 * 64 * 32;    // floats: 2 buffers x (hi, lo) x [64 x 32]       = 32 KB
-constexpr int kTcTmemCols = 64;
+constexpr int kTcTmemCols = 128;
 
 // float offset of element (row, col<32) inside a SWIZZLE_128B image
 __device__ __forceinline__ int sw128(int row, int col) {
@@ -117,6 +117,26 @@ __device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long ad
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
       "r"(accumulate) : "memory");
 }
+// A operand from TMEM (K-major: lane = row, 8 consecutive columns = one k-slice), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(unsigned tmem_d, unsigned tmem_a, unsigned long long bdesc, unsigned idesc,
+                                             unsigned accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d), "r"(tmem_a),
+      "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// this thread's TMEM lane, 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_st16(unsigned taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -205,6 +225,24 @@ static inline void umma_tf32(unsigned tmem_d, unsigned long long adesc, unsigned
       tcemu::tmem()[m][col0 + n] = s;
     }
 }
+static inline void umma_tf32_ts(unsigned tmem_d, unsigned tmem_a, unsigned long long bdesc, unsigned idesc,
+                                unsigned accumulate) {
+  const int M = ((idesc >> 24) & 31) << 4, N = ((idesc >> 17) & 63) << 3;
+  const int bmn = (idesc >> 16) & 1;
+  if ((idesc >> 15) & 1) abort();                      // A from TMEM cannot be MN-major
+  const int col0 = tmem_d & 0xFFFF, acol = tmem_a & 0xFFFF;
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      float s = accumulate ? tcemu::tmem()[m][col0 + n] : 0.f;
+      for (int k = 0; k < 8; ++k) s += tcemu::trunc_tf32(tcemu::tmem()[m][acol + k]) * tcemu::operand(bdesc, bmn, n, k);
+      tcemu::tmem()[m][col0 + n] = s;
+    }
+}
+static inline void tmem_st16(unsigned taddr, const float (&v)[16]) {
+  const int lane = (taddr >> 16) + (threadIdx.x & 31), col = taddr & 0xFFFF;
+  for (int i = 0; i < 16; ++i) tcemu::tmem()[lane][col + i] = v[i];
+}
+static inline void tmem_wait_st() {}
 static inline void umma_commit(unsigned long long* bar) { mbar_arrive(bar); }
 static inline unsigned elect_one() { return (threadIdx.x & 31) == 0; }
 static inline void tmem_ld16(unsigned taddr, float (&v)[16]) {
@@ -800,6 +838,20 @@ __global__ void __launch_bounds__(256, 1) mmn_tc_selftest_kernel(int mode, int N
   tc_fence_after();
   const unsigned tmem = *slot;
   float *a_hi, *a_lo, *b_hi, *b_lo;
+  const bool a_tmem = mode >= 3;                      // modes 3 / 4 = modes 0 / 1 with A staged in TMEM columns 64.. / 96..
+  if (a_tmem) {
+    const int q4 = warp & 3, cs = warp >> 2;
+    float v[16], h[16], l[16];
+    for (int i = 0; i < 16; i += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(A + (q4 * 32 + lane) * 32 + 16 * cs + i);
+      v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
+    }
+    for (int i = 0; i < 16; ++i) { h[i] = tf32_hi(v[i]); l[i] = v[i] - h[i]; }
+    tmem_st16(tmem + ((unsigned)(q4 * 32) << 16) + 64 + 16 * cs, h);
+    tmem_st16(tmem + ((unsigned)(q4 * 32) << 16) + 96 + 16 * cs, l);
+    tmem_wait_st();
+    mode -= 3;
+  }
   if (mode == 2) { a_hi = XB; a_lo = XB + 8192; b_hi = WB; b_lo = WB + 4096; }
   else { a_hi = XB; a_lo = XB + 4096; b_hi = WB; b_lo = WB + 2048; }
   // stage operands
@@ -814,10 +866,11 @@ __global__ void __launch_bounds__(256, 1) mmn_tc_selftest_kernel(int mode, int N
       tc_store_quad<true>(b_hi, b_lo, r, c4, *reinterpret_cast<const float4*>(B + r * 32 + 4 * c4));
     }
   } else {
-    for (int idx = tid; idx < 128 * 8; idx += 256) {
-      const int r = idx >> 3, c4 = idx & 7;
-      tc_store_quad<false>(a_hi, a_lo, r, c4, *reinterpret_cast<const float4*>(A + r * 32 + 4 * c4));
-    }
+    if (!a_tmem)
+      for (int idx = tid; idx < 128 * 8; idx += 256) {
+        const int r = idx >> 3, c4 = idx & 7;
+        tc_store_quad<false>(a_hi, a_lo, r, c4, *reinterpret_cast<const float4*>(A + r * 32 + 4 * c4));
+      }
     if (mode == 0) {
       for (int idx = tid; idx < N * 8; idx += 256) {
         const int r = idx >> 3, c4 = idx & 7;
@@ -833,11 +886,21 @@ __global__ void __launch_bounds__(256, 1) mmn_tc_selftest_kernel(int mode, int N
     }
   }
   fence_proxy_async();
+  tc_fence_before();
   __syncthreads();
   if (tid == 0) {
     tc_fence_after();
     const unsigned ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
-    if (mode == 0) {
+    if (a_tmem) {
+      const unsigned id = umma_idesc_tf32(128, N, 0, mode == 1 ? 1 : 0);
+      for (int j = 0; j < 4; ++j) {
+        const unsigned long long dbh = mode == 1 ? umma_desc_mn(bh, j, 4096) : umma_desc_k(bh, j);
+        const unsigned long long dbl = mode == 1 ? umma_desc_mn(bl, j, 4096) : umma_desc_k(bl, j);
+        umma_tf32_ts(tmem, tmem + 96 + 8 * j, dbh, id, j > 0);
+        umma_tf32_ts(tmem, tmem + 64 + 8 * j, dbl, id, 1);
+        umma_tf32_ts(tmem, tmem + 64 + 8 * j, dbh, id, 1);
+      }
+    } else if (mode == 0) {
       const unsigned id = umma_idesc_tf32(128, N, 0, 0);
       for (int j = 0; j < 4; ++j) {
         umma_tf32(tmem, umma_desc_k(al, j), umma_desc_k(bh, j), id, j > 0);

@@ -7,10 +7,10 @@ import torch
 
 def run_selftest(lib, device, mode, n, seed=0):
     rng = np.random.default_rng(seed + 10 * mode + n)
-    if mode == 0:
+    if mode in (0, 3):
         a, b = rng.standard_normal((128, 32)), rng.standard_normal((n, 32))
         ref = a @ b.T
-    elif mode == 1:
+    elif mode in (1, 4):
         a, b = rng.standard_normal((128, 32)), rng.standard_normal((32, n))
         ref = a @ b
     else:
@@ -27,9 +27,9 @@ def run_selftest(lib, device, mode, n, seed=0):
     if mode == 2:
         got = got[:64]
     ref32 = (ta.cpu().numpy().astype(np.float64), tb.cpu().numpy().astype(np.float64))
-    if mode == 0:
+    if mode in (0, 3):
         ref = ref32[0] @ ref32[1].T
-    elif mode == 1:
+    elif mode in (1, 4):
         ref = ref32[0] @ ref32[1]
     else:
         ref = ref32[0].T @ ref32[1]

@@ -6,6 +6,6 @@ import pytest
 from tc_selftest_common import run_selftest
 
 
-@pytest.mark.parametrize("mode,n", [(0, 32), (0, 64), (1, 32), (1, 64), (2, 32)])
+@pytest.mark.parametrize("mode,n", [(0, 32), (0, 64), (1, 32), (1, 64), (2, 32), (3, 32), (3, 64), (4, 32), (4, 64)])
 def test_umma_model(emu, mode, n):
     assert run_selftest(emu, "cpu", mode, n) < 2e-6
