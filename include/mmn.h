@@ -138,7 +138,7 @@ void mmn_plan_destroy(mmn_plan* plan);
 /* Which GEMM engine the plan's step kernel uses: the FP32-FMA engine (default) or the tcgen05 3xTF32
  * tensor-core engine (environment variable MMN_ENGINE=tc, read by mmn_plan_create; needs the model's
  * tiles to fit shared memory at 128 rows).  Results agree to fp32 round-off. */
-enum { MMN_ENGINE_FMA = 0, MMN_ENGINE_TC = 1 };
+enum { MMN_ENGINE_FMA = 0, MMN_ENGINE_TC = 1, MMN_ENGINE_TC2 = 2 };
 int32_t mmn_plan_engine(const mmn_plan* plan);
 
 int64_t mmn_metrics_count(const mmn_plan* plan);            /* doubles in mmn_outputs.metrics */
@@ -179,6 +179,9 @@ int mmn_adam_step(const mmn_plan* plan, float* params, const float* grads, float
  * mode 2: out[i][j] = sum_r a[r][i] b[r][j] (a: 128 x 64, rows i < 64 meaningful); modes 3 / 4 = modes 0 / 1 with
  * the A operand in tensor memory (tcgen05.st + TS-form MMA).  k = 32, n in {32, 64}. */
 int mmn_selftest_umma(int mode, int n, const float* a, const float* b, float* out, void* stream);
+
+/* Diagnostic: cycles per round of the worker <-> MMA-issuer mbarrier handshake (out: device int64[2]). */
+int mmn_selftest_protocol(int iters, int n_mma, int flags, long long* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -2,6 +2,7 @@
 // argument marshalling around the kernels in mmn_kernels.cuh.  No torch types, no hidden syncs.
 #include "mmn_kernels.cuh"
 #include "mmn_tc.cuh"
+#include "mmn_tc2.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -55,7 +56,7 @@ int pick_rm(const mmn_plan* p) {
     if (fma_smem(p->host, rm) <= (size_t)p->max_smem) return rm;
   return 0;
 }
-int tile_rows(const mmn_plan* p) { return p->engine == MMN_ENGINE_TC ? TcEngine::TM : 32 * p->rm; }
+int tile_rows(const mmn_plan* p) { return p->engine != MMN_ENGINE_FMA ? 128 : 32 * p->rm; }
 int grid_for(const mmn_plan* p, int64_t n_rows) {
   const int tm = tile_rows(p);
   const int64_t tiles = (n_rows + tm - 1) / tm;
@@ -178,6 +179,13 @@ extern "C" int mmn_plan_create(const mmn_model_desc* desc, mmn_plan** out) {
   // default: the FP32-FMA engine (faster at the current stage of tuning, profiles/r1_engine_timers.txt);
   // MMN_ENGINE=tc opts into the tcgen05 3xTF32 engine
   p->engine = (tc_fits && want && !strcmp(want, "tc")) ? MMN_ENGINE_TC : MMN_ENGINE_FMA;
+  if (want && !strcmp(want, "tc2")) {
+    if (!V2Engine::supports(P) || V2Engine::smem_bytes(P) > (size_t)p->max_smem) {
+      delete p;
+      return fail("MMN_ENGINE=tc2: the TMEM-resident kernel needs state <= 64, layers <= 64 wide, <= 16 classes");
+    }
+    p->engine = MMN_ENGINE_TC2;
+  }
   if (p->engine == MMN_ENGINE_FMA && p->rm == 0) {
     const size_t need = fma_smem(P, 1);
     delete p;
@@ -277,7 +285,33 @@ int launch_engine(const mmn_plan* plan, const StepArgs& a_in, void* stream) {
   return 0;
 }
 template <bool TRAIN>
+int launch_v2(const mmn_plan* plan, const StepArgs& a_in, void* stream) {
+  StepArgs a = a_in;
+  const size_t smem = V2Engine::smem_bytes(plan->host);
+  const int grid = grid_for(plan, a.n_rows);
+  auto kfn = mmn_step_kernel_v2<TRAIN>;
+  MMN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool dbg = getenv("MMN_DEBUG_TIMERS") != nullptr;
+  if (dbg) { MMN_CUDA(cudaMalloc((void**)&a.debug_timers, sizeof(long long) * 16 * grid)); MMN_CUDA(cudaMemsetAsync(a.debug_timers, 0, sizeof(long long) * 16 * grid, (cudaStream_t)stream)); }
+  MMN_LAUNCH(kfn, dim3(grid), dim3(V2Engine::kBlockThreads), smem, stream, a);
+  MMN_CUDA(cudaGetLastError());
+  if (dbg) {
+    std::vector<long long> h(16 * (size_t)grid);
+    MMN_CUDA(cudaMemcpy(h.data(), a.debug_timers, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+    cudaFree(a.debug_timers);
+    double s[16] = {0};
+    for (int b = 0; b < grid; ++b) for (int i = 0; i < 16; ++i) s[i] += (double)h[b * 16 + i] / grid;
+    fprintf(stderr, "[mmn v2 timers, mean cycles/CTA] total %.0f | gemms %.0f (%.0f calls, %.0f chunks) | slot-wait %.0f | W stage %.0f | prefetch+post %.0f | bias+mid %.0f | acc-wait %.0f | epilogue %.0f (dec hidden %.0f, dec metrics %.0f)\n",
+            s[15], s[6], s[8], s[7], s[0], s[1], s[2], s[3], s[4], s[5], s[9], s[10]);
+  }
+  return 0;
+}
+template <bool TRAIN>
 int launch_step(const mmn_plan* plan, const StepArgs& a, void* stream) {
+  if (plan->engine == MMN_ENGINE_TC2) {
+    if (TRAIN) return fail("MMN_ENGINE=tc2: training is not implemented yet");
+    return launch_v2<false>(plan, a, stream);
+  }
   if (plan->engine == MMN_ENGINE_TC) return launch_engine<TcEngine, TRAIN>(plan, a, stream);
   if (plan->occ == 2) return launch_engine<FmaEngine<2, 2>, TRAIN>(plan, a, stream);
   switch (plan->rm) {
@@ -363,6 +397,16 @@ extern "C" int mmn_selftest_umma(int mode, int n, const float* a, const float* b
   auto kfn = mmn_tc_selftest_kernel;
   MMN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   MMN_LAUNCH(kfn, dim3(1), dim3(256), smem, stream, mode, n, a, b, out);
+  MMN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Development aid: cycles per round of the worker <-> MMA-issuer handshake (mmn_tc2.cuh).  out: device int64[2].
+extern "C" int mmn_selftest_protocol(int iters, int n_mma, int flags, long long* out, void* stream) {
+  auto kfn = mmn_protocol_probe_kernel;
+  const size_t smem = 1024 + 32768 + 64;
+  MMN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MMN_LAUNCH(kfn, dim3(1), dim3(288), smem, stream, iters, n_mma, flags, out);
   MMN_CUDA(cudaGetLastError());
   return 0;
 }

@@ -37,7 +37,7 @@ namespace mmn {
 __device__ __forceinline__ float act_fwd(int act, float z) {
   switch (act) {
     case MMN_ACT_RELU: return z > 0.f ? z : 0.f;
-    case MMN_ACT_SIGMOID: return 1.f / (1.f + expf(-z));
+    case MMN_ACT_SIGMOID: return __fdividef(1.f, 1.f + expf(-z));
     case MMN_ACT_TANH: return tanhf(z);
     default: return z;
   }
@@ -51,6 +51,37 @@ __device__ __forceinline__ float act_bwd(int act, float out) {
     default: return 1.f;
   }
 }
+
+// activation over a small register array with the kind test hoisted out of the element loop
+// (a per-element switch unrolls into a branch ladder plus the slow-path division call, 16x per epilogue)
+template <int N>
+__device__ __forceinline__ void act_fwd_n(int act, float (&v)[N]) {
+  if (act == MMN_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = fmaxf(v[i], 0.f);
+  } else if (act == MMN_ACT_SIGMOID) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = __fdividef(1.f, 1.f + expf(-v[i]));
+  } else if (act == MMN_ACT_TANH) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = tanhf(v[i]);
+  }
+}
+// derivative through the activation OUTPUT as branch-free arithmetic: d = relu ? (a > 0) : c0 + c1 a + c2 a^2
+struct ActBwd {
+  float c0, c1, c2;
+  bool relu;
+  __device__ __forceinline__ explicit ActBwd(int act) {
+    relu = act == MMN_ACT_RELU;
+    c0 = (act == MMN_ACT_SIGMOID) ? 0.f : 1.f;
+    c1 = (act == MMN_ACT_SIGMOID) ? 1.f : 0.f;
+    c2 = (act == MMN_ACT_SIGMOID || act == MMN_ACT_TANH) ? -1.f : 0.f;
+  }
+  __device__ __forceinline__ float operator()(float a) const {
+    const float poly = fmaf(a, fmaf(a, c2, c1), c0);
+    return relu ? (a > 0.f ? 1.f : 0.f) : poly;
+  }
+};
 
 // dropout keep decision: counter-based hash of (seed, encoder, global row, column pair); one 32-bit
 // hash serves two adjacent columns (16 bits each).  The oracle (oracle/multimodn_oracle.py:
@@ -247,7 +278,7 @@ struct ChunkIt {
 // ------------------------------------------------------------------------------------------------
 template <int RM, class Epi>
 __device__ __forceinline__ void fma_gemm_nt(const Smem& sm, const float* __restrict__ W, int ldw, int N,
-                                        const float* __restrict__ bias, const ASeg* segs, int nseg,
+                                        const float* __restrict__ bias, int act, const ASeg* segs, int nseg,
                                         const Drop& drop, int rows_valid, bool scan_nan, Epi epi) {
   constexpr int TM = Cfg<RM>::TM;
   const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
@@ -335,9 +366,13 @@ __device__ __forceinline__ void fma_gemm_nt(const Smem& sm, const float* __restr
       buf ^= 1;
     }
 #pragma unroll
-    for (int i = 0; i < RM; ++i)
+    for (int i = 0; i < RM; ++i) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) epi(ty + 32 * i, n0 + tx + 8 * j, acc[i][j] + bj[j]);
+      for (int j = 0; j < 4; ++j) acc[i][j] += bj[j];
+      act_fwd_n(act, acc[i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) epi(ty + 32 * i, n0 + tx + 8 * j, acc[i][j]);
+    }
   }
   MMN_WSYNC_N(kThreads);
 }
@@ -548,9 +583,9 @@ struct FmaEngine {
   __device__ static __forceinline__ void fini(const Smem&, State&) {}
   template <class Epi>
   __device__ static __forceinline__ void gemm_nt(const Smem& sm, State&, const float* __restrict__ W, int ldw, int N,
-                                                 const float* __restrict__ bias, const ASeg* segs, int nseg,
+                                                 const float* __restrict__ bias, int act, const ASeg* segs, int nseg,
                                                  const Drop& drop, int rows_valid, bool scan_nan, Epi epi) {
-    fma_gemm_nt<RM>(sm, W, ldw, N, bias, segs, nseg, drop, rows_valid, scan_nan, epi);
+    fma_gemm_nt<RM>(sm, W, ldw, N, bias, act, segs, nseg, drop, rows_valid, scan_nan, epi);
   }
   template <class Pre, class Epi>
   __device__ static __forceinline__ void gemm_nn(const Smem& sm, State&, const float* dz, int ldd, int N,
@@ -717,8 +752,8 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, ENG::kMinBlocks) mmn_step_
           ASeg seg;
           seg.ptr = in; seg.ld = ldin; seg.width = ly.in_dim; seg.kind = SEG_SMEM; seg.wcol = 0;
           const int N = ly.out_dim, act = ly.act;
-          ENG::gemm_nt(sm, es, params + ly.w_off, ly.ktot, N, params + ly.b_off, &seg, 1, nodrop, rows_valid, false,
-                      [&](int r, int n, float z) { out[r * ldH + n] = n < N ? act_fwd(act, z) : 0.f; });
+          ENG::gemm_nt(sm, es, params + ly.w_off, ly.ktot, N, params + ly.b_off, act, &seg, 1, nodrop, rows_valid, false,
+                      [&](int r, int n, float z) { out[r * ldH + n] = n < N ? z : 0.f; });
           if (TRAIN)
             stash_store<TM, NT>(slot + (long long)(stash_dec_off(P, k) + dec.stash_off + ly.stash_off) * TM, out, ldH, N);
           in = out;
@@ -818,9 +853,9 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, ENG::kMinBlocks) mmn_step_
             nseg = 2;
           }
           const int N = ly.out_dim, act = ly.act;
-          ENG::gemm_nt(sm, es, params + ly.w_off, ly.ktot, N, params + ly.b_off, segs, nseg, use_drop ? drop : nodrop,
+          ENG::gemm_nt(sm, es, params + ly.w_off, ly.ktot, N, params + ly.b_off, act, segs, nseg, use_drop ? drop : nodrop,
                       rows_valid, j == 0,
-                      [&](int r, int n, float z) { out[r * ldo + n] = n < N ? act_fwd(act, z) : 0.f; });
+                      [&](int r, int n, float z) { out[r * ldo + n] = n < N ? z : 0.f; });
           if (TRAIN && !last)
             stash_store<TM, NT>(slot + (long long)(stash_enc_off(P, k) + ly.stash_off) * TM, out, ldH, N);
           in = out;
@@ -878,7 +913,7 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, ENG::kMinBlocks) mmn_step_
           // dz of the last layer from the stashed outputs p: CE-on-outputs gradient through out_act
           {
             const float* pst = slot + dbase + (long long)dec.L[nl - 1].stash_off * TM;
-            const int act = dec.L[nl - 1].act;
+            const ActBwd dact(dec.L[nl - 1].act);
             const int Cpad = (C + 31) & ~31;
             if (tid < TM) {
               const int r = tid;
@@ -894,7 +929,7 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, ENG::kMinBlocks) mmn_step_
               const float inv = 1.f / se;
               for (int c = 0; c < Cpad; ++c) {
                 float v = 0.f;
-                if (c < C) v = coef * (expf(p[c] - mx) * inv - (c == y ? 1.f : 0.f)) * act_bwd(act, p[c]);
+                if (c < C) v = coef * (expf(p[c] - mx) * inv - (c == y ? 1.f : 0.f)) * dact(p[c]);
                 sm.A[r * ldH + c] = v;
               }
             }
@@ -911,11 +946,12 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, ENG::kMinBlocks) mmn_step_
             if (j > 0) {
               float* other = cur == sm.A ? sm.B : sm.A;
               const float* ast = slot + dbase + (long long)dec.L[j - 1].stash_off * TM;
-              const int J = ly.in_dim, pact = dec.L[j - 1].act;
+              const int J = ly.in_dim;
+              const ActBwd dact(dec.L[j - 1].act);
               ENG::gemm_nn(sm, es, cur, ldH, ly.out_dim, params + ly.w_off, ly.ktot, 0, J,
                           [&](int r, int jc) { return ldcg4(ast, r, J, jc); },
                           [&](int r, int jc, float acc, float a) {
-                            other[r * ldH + jc] = jc < J ? acc * act_bwd(pact, a) : 0.f;
+                            other[r * ldH + jc] = jc < J ? acc * dact(a) : 0.f;
                           });
               cur = other;
             } else {
@@ -939,7 +975,7 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, ENG::kMinBlocks) mmn_step_
         const int nl = enc.n_layers;
         // G += u_k ; dz_last = present ? G * act'(s_k) : 0
         {
-          const int act = enc.L[nl - 1].act;
+          const ActBwd dact(enc.L[nl - 1].act);
           const int Spad = (S + 31) & ~31;
           for (RowCol<NT> it(Spad); it.r < TM; it.next()) {
             const int r = it.r, c = it.c;
@@ -948,7 +984,7 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, ENG::kMinBlocks) mmn_step_
               const float a = __ldcg(sk + r * S + c), b = __ldcg(skm1 + r * S + c);
               const float g = G[r * ldS + c] + args.c_sc * (a - b);
               G[r * ldS + c] = g;
-              if (sm.present[k * TM + r]) dzv = g * act_bwd(act, a);
+              if (sm.present[k * TM + r]) dzv = g * dact(a);
             }
             sm.T[r * ldS + c] = dzv;
           }
@@ -986,11 +1022,12 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, ENG::kMinBlocks) mmn_step_
           if (j > 0) {
             other = cur == sm.A ? sm.B : sm.A;
             const float* ast = slot + ebase + (long long)enc.L[j - 1].stash_off * TM;
-            const int J = ly.in_dim, pact = enc.L[j - 1].act;
+            const int J = ly.in_dim;
+            const ActBwd dact(enc.L[j - 1].act);
             ENG::gemm_nn(sm, es, cur, ldc, ly.out_dim, params + ly.w_off, ly.ktot, 0, J,
                         [&](int r, int jc) { return ldcg4(ast, r, J, jc); },
                         [&](int r, int jc, float acc, float a) {
-                          other[r * ldH + jc] = jc < J ? acc * act_bwd(pact, a) : 0.f;
+                          other[r * ldH + jc] = jc < J ? acc * dact(a) : 0.f;
                         });
           }
           if (ly.has_state) {

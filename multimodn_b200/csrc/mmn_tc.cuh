@@ -611,7 +611,7 @@ struct TcEngine {
   // ------------------------------------------------------------------------------------------------
   template <class Epi>
   __device__ static __forceinline__ void gemm_nt(const Smem& sm, State& es, const float* __restrict__ W, int ldw, int N,
-                                                 const float* __restrict__ bias, const ASeg* segs, int nseg,
+                                                 const float* __restrict__ bias, int act, const ASeg* segs, int nseg,
                                                  const Drop& drop, int rows_valid, bool scan_nan, Epi epi) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, cs = warp >> 2;
     const long long t_begin = MMN_CLOCK();
@@ -676,7 +676,10 @@ struct TcEngine {
         float v[16];
         acc_load(es, q, cb, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) epi(r, n0 + cb + i, v[i] + bj[i]);
+        for (int i = 0; i < 16; ++i) v[i] += bj[i];
+        act_fwd_n(act, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) epi(r, n0 + cb + i, v[i]);
       }
       es.t[4] += MMN_CLOCK() - t_epi;
     }
