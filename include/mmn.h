@@ -135,11 +135,15 @@ int mmn_abi_version(void);
 int mmn_plan_create(const mmn_model_desc* desc, mmn_plan** out);
 void mmn_plan_destroy(mmn_plan* plan);
 
-/* Which GEMM engine the plan's step kernel uses: the FP32-FMA engine (default) or the tcgen05 3xTF32
- * tensor-core engine (environment variable MMN_ENGINE=tc, read by mmn_plan_create; needs the model's
- * tiles to fit shared memory at 128 rows).  Results agree to fp32 round-off. */
+/* Which kernel family a plan uses (results agree to fp32 round-off):
+ *   MMN_ENGINE_FMA  FP32-FMA register-tile GEMMs — default of mmn_train_step
+ *   MMN_ENGINE_TC   tcgen05 3xTF32, operands staged through shared memory (MMN_ENGINE=tc)
+ *   MMN_ENGINE_TC2  tcgen05 3xTF32 with the activations resident in tensor memory — forward only; default of
+ *                   mmn_forward when the model qualifies (state <= 64, layers <= 64 wide, <= 16 classes)
+ * The environment variable MMN_ENGINE=fma|tc|tc2, read by mmn_plan_create, forces one. */
 enum { MMN_ENGINE_FMA = 0, MMN_ENGINE_TC = 1, MMN_ENGINE_TC2 = 2 };
-int32_t mmn_plan_engine(const mmn_plan* plan);
+int32_t mmn_plan_engine(const mmn_plan* plan);           /* engine of mmn_train_step */
+int32_t mmn_plan_forward_engine(const mmn_plan* plan);   /* engine of mmn_forward */
 
 int64_t mmn_metrics_count(const mmn_plan* plan);            /* doubles in mmn_outputs.metrics */
 int64_t mmn_grad_count(const mmn_plan* plan);               /* floats in the gradient buffer:

@@ -59,7 +59,7 @@ class TrainArgs(C.Structure):
 
 EXPORTS = ("mmn_last_error", "mmn_abi_version", "mmn_plan_create", "mmn_plan_destroy", "mmn_metrics_count",
            "mmn_grad_count", "mmn_workspace_bytes", "mmn_scan_missing", "mmn_forward", "mmn_train_step",
-           "mmn_adam_step", "mmn_selftest_umma", "mmn_selftest_protocol", "mmn_plan_engine")
+           "mmn_adam_step", "mmn_selftest_umma", "mmn_selftest_protocol", "mmn_plan_engine", "mmn_plan_forward_engine")
 
 
 class MMNError(RuntimeError):
@@ -101,6 +101,8 @@ class Library:
                                      C.POINTER(Outputs), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         d.mmn_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+        d.mmn_plan_forward_engine.argtypes = [C.c_void_p]
+        d.mmn_plan_forward_engine.restype = C.c_int32
         d.mmn_plan_engine.argtypes = [C.c_void_p]
         d.mmn_plan_engine.restype = C.c_int32
         d.mmn_selftest_protocol.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]

@@ -22,6 +22,7 @@ struct mmn_plan {
   int engine = MMN_ENGINE_FMA;   // MMN_ENGINE_*
   int rm = 0;                    // FMA engine: rows per tile / 32
   int occ = 1;                   // FMA engine: CTAs per SM the kernel variant is built for
+  int fwd_engine = MMN_ENGINE_FMA;   // engine of the forward-only path (test / predict / get_states)
 };
 
 namespace {
@@ -56,11 +57,11 @@ int pick_rm(const mmn_plan* p) {
     if (fma_smem(p->host, rm) <= (size_t)p->max_smem) return rm;
   return 0;
 }
-int tile_rows(const mmn_plan* p) { return p->engine != MMN_ENGINE_FMA ? 128 : 32 * p->rm; }
-int grid_for(const mmn_plan* p, int64_t n_rows) {
-  const int tm = tile_rows(p);
+int tile_rows(const mmn_plan* p, int engine) { return engine != MMN_ENGINE_FMA ? 128 : 32 * p->rm; }
+int grid_for(const mmn_plan* p, int engine, int64_t n_rows) {
+  const int tm = tile_rows(p, engine);
   const int64_t tiles = (n_rows + tm - 1) / tm;
-  const int per_sm = p->engine == MMN_ENGINE_FMA ? p->occ : 1;
+  const int per_sm = engine == MMN_ENGINE_FMA ? p->occ : 1;
   return (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)p->n_sms * per_sm));
 }
 
@@ -179,13 +180,13 @@ extern "C" int mmn_plan_create(const mmn_model_desc* desc, mmn_plan** out) {
   // default: the FP32-FMA engine (faster at the current stage of tuning, profiles/r1_engine_timers.txt);
   // MMN_ENGINE=tc opts into the tcgen05 3xTF32 engine
   p->engine = (tc_fits && want && !strcmp(want, "tc")) ? MMN_ENGINE_TC : MMN_ENGINE_FMA;
-  if (want && !strcmp(want, "tc2")) {
-    if (!V2Engine::supports(P) || V2Engine::smem_bytes(P) > (size_t)p->max_smem) {
-      delete p;
-      return fail("MMN_ENGINE=tc2: the TMEM-resident kernel needs state <= 64, layers <= 64 wide, <= 16 classes");
-    }
-    p->engine = MMN_ENGINE_TC2;
+  // forward-only launches (test / predict / get_states): the TMEM-resident kernel where the model qualifies
+  const bool v2_ok = V2Engine::supports(P) && V2Engine::smem_bytes(P) <= (size_t)p->max_smem;
+  if (want && !strcmp(want, "tc2") && !v2_ok) {
+    delete p;
+    return fail("MMN_ENGINE=tc2: the TMEM-resident kernel needs state <= 64, layers <= 64 wide, <= 16 classes");
   }
+  p->fwd_engine = (v2_ok && !want) || (want && !strcmp(want, "tc2")) ? MMN_ENGINE_TC2 : p->engine;
   if (p->engine == MMN_ENGINE_FMA && p->rm == 0) {
     const size_t need = fma_smem(P, 1);
     delete p;
@@ -210,11 +211,12 @@ extern "C" int64_t mmn_metrics_count(const mmn_plan* plan) { return plan ? plan-
 extern "C" int64_t mmn_grad_count(const mmn_plan* plan) { return plan ? plan->host.n_params + plan->host.E : -1; }
 
 extern "C" int32_t mmn_plan_engine(const mmn_plan* plan) { return plan ? plan->engine : -1; }
+extern "C" int32_t mmn_plan_forward_engine(const mmn_plan* plan) { return plan ? plan->fwd_engine : -1; }
 
 extern "C" int64_t mmn_workspace_bytes(const mmn_plan* plan, int64_t n_rows, int32_t with_backward) {
   if (!plan || n_rows < 0) return -1;
   if (!with_backward) return 0;
-  return (int64_t)grid_for(plan, n_rows) * tile_rows(plan) * plan->host.stash_row * 4;
+  return (int64_t)grid_for(plan, plan->engine, n_rows) * tile_rows(plan, plan->engine) * plan->host.stash_row * 4;
 }
 
 namespace {
@@ -262,7 +264,7 @@ template <class ENG, bool TRAIN>
 int launch_engine(const mmn_plan* plan, const StepArgs& a_in, void* stream) {
   StepArgs a = a_in;
   const size_t smem = step_smem_bytes(plan->host, ENG::TM, ENG::stage_bytes());
-  const int grid = grid_for(plan, a.n_rows);
+  const int grid = grid_for(plan, ENG::kTensor ? MMN_ENGINE_TC : MMN_ENGINE_FMA, a.n_rows);
   auto kfn = mmn_step_kernel<ENG, TRAIN>;
   MMN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const bool dbg = getenv("MMN_DEBUG_TIMERS") != nullptr;      // development aid: per-phase cycle counters
@@ -288,7 +290,7 @@ template <bool TRAIN>
 int launch_v2(const mmn_plan* plan, const StepArgs& a_in, void* stream) {
   StepArgs a = a_in;
   const size_t smem = V2Engine::smem_bytes(plan->host);
-  const int grid = grid_for(plan, a.n_rows);
+  const int grid = grid_for(plan, MMN_ENGINE_TC2, a.n_rows);
   auto kfn = mmn_step_kernel_v2<TRAIN>;
   MMN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const bool dbg = getenv("MMN_DEBUG_TIMERS") != nullptr;
@@ -308,11 +310,9 @@ int launch_v2(const mmn_plan* plan, const StepArgs& a_in, void* stream) {
 }
 template <bool TRAIN>
 int launch_step(const mmn_plan* plan, const StepArgs& a, void* stream) {
-  if (plan->engine == MMN_ENGINE_TC2) {
-    if (TRAIN) return fail("MMN_ENGINE=tc2: training is not implemented yet");
-    return launch_v2<false>(plan, a, stream);
-  }
-  if (plan->engine == MMN_ENGINE_TC) return launch_engine<TcEngine, TRAIN>(plan, a, stream);
+  const int engine = TRAIN ? plan->engine : plan->fwd_engine;
+  if (engine == MMN_ENGINE_TC2) return launch_v2<false>(plan, a, stream);      // forward only
+  if (engine == MMN_ENGINE_TC) return launch_engine<TcEngine, TRAIN>(plan, a, stream);
   if (plan->occ == 2) return launch_engine<FmaEngine<2, 2>, TRAIN>(plan, a, stream);
   switch (plan->rm) {
     case 4: return launch_engine<FmaEngine<4>, TRAIN>(plan, a, stream);
@@ -368,7 +368,7 @@ extern "C" int mmn_train_step(const mmn_plan* plan, const mmn_batch* batch, cons
   const double bg = 1.0 / a.inv_rows_global;
   a.grads = grads;
   a.stash = (float*)workspace;
-  a.slot_floats = (long long)tile_rows(plan) * P.stash_row;
+  a.slot_floats = (long long)tile_rows(plan, plan->engine) * P.stash_row;
   a.c_err = (float)((double)targs->err_penalty / ((double)P.D * (P.E + 1) * bg));
   a.c_sc = (float)(2.0 * (double)targs->state_change_penalty_scaled / ((double)P.E * bg * P.S));
   a.dropout_seed = targs->dropout_seed;

@@ -239,6 +239,7 @@ static inline void umma_tf32_ts(unsigned tmem_d, unsigned tmem_a, unsigned long 
     }
 }
 static inline void tmem_st16(unsigned taddr, const float (&v)[16]) {
+  emu::warp_collective();
   const int lane = (taddr >> 16) + (threadIdx.x & 31), col = taddr & 0xFFFF;
   for (int i = 0; i < 16; ++i) tcemu::tmem()[lane][col + i] = v[i];
 }
@@ -246,10 +247,12 @@ static inline void tmem_wait_st() {}
 static inline void umma_commit(unsigned long long* bar) { mbar_arrive(bar); }
 static inline unsigned elect_one() { return (threadIdx.x & 31) == 0; }
 static inline void tmem_ld16(unsigned taddr, float (&v)[16]) {
+  emu::warp_collective();
   const int lane = (taddr >> 16) + (threadIdx.x & 31), col = taddr & 0xFFFF;
   for (int i = 0; i < 16; ++i) v[i] = tcemu::tmem()[lane][col + i];
 }
 static inline void tmem_ld8(unsigned taddr, float (&v)[8]) {
+  emu::warp_collective();
   const int lane = (taddr >> 16) + (threadIdx.x & 31), col = taddr & 0xFFFF;
   for (int i = 0; i < 8; ++i) v[i] = tcemu::tmem()[lane][col + i];
 }

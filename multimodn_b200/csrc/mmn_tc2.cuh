@@ -469,11 +469,30 @@ __global__ void __launch_bounds__(V2Engine::kBlockThreads, 1) mmn_step_kernel_v2
                        es.t[9] += MMN_CLOCK() - te0;
                      } else if (t.cs == 0 && h == 0) {
                        // per-row epilogue: first-max arg-max, CE on the outputs, confusion cells (whole warps 0..3)
-                       float best = v[0];
-                       int pred = 0;
+                       float best = v[0], mx = v[0], se, py;
+                       int pred = 0, y = 0;
+                       if (args.targets) {
+                         y = sm.ys[t.r * D + d];
+                         y = y < 0 ? 0 : (y >= C ? C - 1 : y);
+                       }
+                       if (C == 2) {                       // binary heads: every reference pipeline
+                         pred = (v[1] > v[0] || (v[1] != v[1] && v[0] == v[0])) ? 1 : 0;
+                         mx = fmaxf(v[0], v[1]);
+                         se = 1.f + expf(-fabsf(v[0] - v[1]));
+                         py = y ? v[1] : v[0];
+                       } else {
 #pragma unroll
-                       for (int c = 1; c < 16; ++c)
-                         if (c < C && (v[c] > best || (v[c] != v[c] && best == best))) { best = v[c]; pred = c; }
+                         for (int c = 1; c < 16; ++c)
+                           if (c < C) {
+                             if (v[c] > best || (v[c] != v[c] && best == best)) { best = v[c]; pred = c; }
+                             mx = fmaxf(mx, v[c]);
+                           }
+                         se = 0.f;
+                         py = v[0];
+#pragma unroll
+                         for (int c = 0; c < 16; ++c)
+                           if (c < C) { se += expf(v[c] - mx); if (c == y) py = v[c]; }
+                       }
                        if (valid) {
                          if (args.predictions) args.predictions[((long long)hist_row * D + d) * args.pred_ld + row0 + t.r] = (unsigned char)pred;
                          if (args.last_outputs && is_last_enc) {
@@ -484,16 +503,6 @@ __global__ void __launch_bounds__(V2Engine::kBlockThreads, 1) mmn_step_kernel_v2
                          }
                        }
                        if (args.targets) {
-                         int y = sm.ys[t.r * D + d];
-                         y = y < 0 ? 0 : (y >= C ? C - 1 : y);
-                         float mx = v[0], py = v[0];
-#pragma unroll
-                         for (int c = 1; c < 16; ++c)
-                           if (c < C) mx = fmaxf(mx, v[c]);
-                         float se = 0.f;
-#pragma unroll
-                         for (int c = 0; c < 16; ++c)
-                           if (c < C) { se += expf(v[c] - mx); if (c == y) py = v[c]; }
                          float ce = pr ? (mx + logf(se) - py) : 0.f;
                          unsigned pk1 = 0, pk2 = 0;
                          if (pr) {
@@ -597,7 +606,7 @@ __global__ void __launch_bounds__(V2Engine::kBlockThreads, 1) mmn_step_kernel_v2
                          sc = fmaf(df, df, sc);
                          v[i] = nw;
                        }
-                       if (pr) v2_st_pair(t, V2_S_HI + 32 * h, V2_S_LO + 32 * h, v);
+                       v2_st_pair(t, V2_S_HI + 32 * h, V2_S_LO + 32 * h, v);   // unconditional: tcgen05.st is warp-collective
                      }
                    });
           in_sel = out_sel;

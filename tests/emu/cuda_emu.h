@@ -143,8 +143,16 @@ inline void warp_barrier() {
   unsigned lanes = (w == s.wcount.size() - 1 && s.nthreads % 32) ? s.nthreads % 32 : 32;
   unsigned gen = s.wgen[w];
   if (++s.wcount[w] == lanes) { s.wcount[w] = 0; ++s.wgen[w]; }
-  else while (s.wgen[w] == gen) yield();
+  else {
+    unsigned long spins = 0;
+    while (s.wgen[w] == gen) {
+      yield();
+      if (++spins > 50000000ul) { fprintf(stderr, "cuda_emu: warp-collective op reached by only part of warp %u (divergence)\n", w); abort(); }
+    }
+  }
 }
+// a .sync.aligned instruction: every lane of the warp must execute it together
+inline void warp_collective() { warp_barrier(); }
 template <class T>
 inline T shfl(T v, unsigned src_lane) {
   static_assert(sizeof(T) <= 8, "shfl payload");

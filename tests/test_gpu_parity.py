@@ -251,3 +251,22 @@ def test_default_engine_is_fma():
     fx = load_golden("c2_mimic_full")
     model = model_from_spec(golden_spec(fx), 1.0, 0.3, DEV, "row")
     assert _lib.get_lib().dll.mmn_plan_engine(model.runtime().plan) == 0
+
+
+# ---- forward-only launches (test / predict / get_states) default to the TMEM-resident kernel where the model
+#      qualifies; MMN_ENGINE=fma keeps them on the FP32-FMA kernel ---------------------------------------------------
+def test_forward_engine_default_is_tmem_resident_for_c2():
+    from multimodn_b200 import _lib
+    fx = load_golden("c2_mimic_full")
+    model = model_from_spec(golden_spec(fx), 1.0, 0.3, DEV, "row")
+    assert _lib.get_lib().dll.mmn_plan_forward_engine(model.runtime().plan) == 2
+
+
+@pytest.mark.parametrize("name,names,mode", [("c2_mimic_full", ["a", "b"], "row"), ("sequence", ["a", "b", "c"], "row"),
+                                             ("zoo", ["a", "b", "c"], "row")])
+def test_golden_fma_forward(monkeypatch, name, names, mode):
+    monkeypatch.setenv("MMN_ENGINE", "fma")
+    fx = load_golden(name)
+    model, _, _ = run_golden(name, names, mode, seq=fx.get("seq"), check_val=name != "zoo")
+    from multimodn_b200 import _lib
+    assert _lib.get_lib().dll.mmn_plan_forward_engine(model.runtime().plan) == 0
