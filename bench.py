@@ -260,7 +260,7 @@ def main():
     clk.__exit__()
     clocks = clk.summary()
     peaks, peak_kind = measured_peaks()
-    engine = {0: "fp32-fma", 1: "tcgen05-3xtf32"}[int(rt.lib.dll.mmn_plan_engine(rt.plan))]
+    engine = {0: "fp32-fma", 1: "tcgen05-3xtf32", 2: "tcgen05-3xtf32-tmem"}[int(rt.lib.dll.mmn_plan_engine(rt.plan))]
     macs = macs_per_row(w)
     alg_bytes = B * (2 * 4 * sum(w["features"]) + 8 * w["n_decoders"])   # x read in fwd and again for wgrad
     achieved = alg_bytes / (kms * 1e-3) / 1e9

@@ -138,8 +138,9 @@ void mmn_plan_destroy(mmn_plan* plan);
 /* Which kernel family a plan uses (results agree to fp32 round-off):
  *   MMN_ENGINE_FMA  FP32-FMA register-tile GEMMs — default of mmn_train_step
  *   MMN_ENGINE_TC   tcgen05 3xTF32, operands staged through shared memory (MMN_ENGINE=tc)
- *   MMN_ENGINE_TC2  tcgen05 3xTF32 with the activations resident in tensor memory — forward only; default of
- *                   mmn_forward when the model qualifies (state <= 64, layers <= 64 wide, <= 16 classes)
+ *   MMN_ENGINE_TC2  tcgen05 3xTF32 with the activations (forward) and the state / layer gradients (backward)
+ *                   resident in tensor memory; needs state <= 64, layers <= 64 wide, <= 16 classes.  Default of
+ *                   mmn_forward when the model qualifies; mmn_train_step uses it under MMN_ENGINE=tc2
  * The environment variable MMN_ENGINE=fma|tc|tc2, read by mmn_plan_create, forces one. */
 enum { MMN_ENGINE_FMA = 0, MMN_ENGINE_TC = 1, MMN_ENGINE_TC2 = 2 };
 int32_t mmn_plan_engine(const mmn_plan* plan);           /* engine of mmn_train_step */

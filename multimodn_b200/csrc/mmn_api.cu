@@ -187,6 +187,7 @@ extern "C" int mmn_plan_create(const mmn_model_desc* desc, mmn_plan** out) {
     return fail("MMN_ENGINE=tc2: the TMEM-resident kernel needs state <= 64, layers <= 64 wide, <= 16 classes");
   }
   p->fwd_engine = (v2_ok && !want) || (want && !strcmp(want, "tc2")) ? MMN_ENGINE_TC2 : p->engine;
+  if (want && !strcmp(want, "tc2")) p->engine = MMN_ENGINE_TC2;
   if (p->engine == MMN_ENGINE_FMA && p->rm == 0) {
     const size_t need = fma_smem(P, 1);
     delete p;
@@ -303,15 +304,15 @@ int launch_v2(const mmn_plan* plan, const StepArgs& a_in, void* stream) {
     cudaFree(a.debug_timers);
     double s[16] = {0};
     for (int b = 0; b < grid; ++b) for (int i = 0; i < 16; ++i) s[i] += (double)h[b * 16 + i] / grid;
-    fprintf(stderr, "[mmn v2 timers, mean cycles/CTA] total %.0f | gemms %.0f (%.0f calls, %.0f chunks) | slot-wait %.0f | W stage %.0f | prefetch+post %.0f | bias+mid %.0f | acc-wait %.0f | epilogue %.0f (dec hidden %.0f, dec metrics %.0f)\n",
-            s[15], s[6], s[8], s[7], s[0], s[1], s[2], s[3], s[4], s[5], s[9], s[10]);
+    fprintf(stderr, "[mmn v2 timers, mean cycles/CTA] total %.0f | gemms %.0f (%.0f calls, %.0f chunks) | slot-wait %.0f | W stage %.0f | prefetch+post %.0f | bias+mid %.0f | acc-wait %.0f | epilogue %.0f (dec hidden %.0f, dec metrics %.0f) | backward %.0f: colsum %.0f, wgrad %.0f, dgrad %.0f\n",
+            s[15], s[6], s[8], s[7], s[0], s[1], s[2], s[3], s[4], s[5], s[9], s[10], s[14], s[11], s[12], s[13]);
   }
   return 0;
 }
 template <bool TRAIN>
 int launch_step(const mmn_plan* plan, const StepArgs& a, void* stream) {
   const int engine = TRAIN ? plan->engine : plan->fwd_engine;
-  if (engine == MMN_ENGINE_TC2) return launch_v2<false>(plan, a, stream);      // forward only
+  if (engine == MMN_ENGINE_TC2) return launch_v2<TRAIN>(plan, a, stream);
   if (engine == MMN_ENGINE_TC) return launch_engine<TcEngine, TRAIN>(plan, a, stream);
   if (plan->occ == 2) return launch_engine<FmaEngine<2, 2>, TRAIN>(plan, a, stream);
   switch (plan->rm) {
