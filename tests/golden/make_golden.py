@@ -324,6 +324,54 @@ def fixture_dropout():
          **{f"x{i}": x for i, x in enumerate(data)}, **arrays)
 
 
+def fixture_titanic_pipeline():
+    """pipelines/titanic/titanic_mlp_pipeline.py:24-85 end to end with the reference's own
+    TitanicDataset / PartitionDataset.random_split / DataLoader / MultiModN / MultiModNHistory.get_results,
+    on the synthetic Titanic-shaped table of multimodn_b200/datasets/titanic.py (the real CSV is fetched by
+    datasets/titanic/get_data.sh, impossible offline).  The reference hard-codes the CSV location inside its
+    read-only tree (titanic_dataset.py:22), so pandas.read_csv is redirected for that one call."""
+    import tempfile
+    import pandas as pd
+    from torch.utils.data import DataLoader
+    import datasets.titanic.titanic_dataset as ref_td
+    from multimodn_b200.datasets.titanic import write_synthetic_titanic_csv
+
+    n_rows, seed, epochs, batch_size = 400, 0, 3, 32
+    csv = os.path.join(tempfile.mkdtemp(), "titanic.csv")
+    write_synthetic_titanic_csv(csv, n_rows, seed)
+    real_read = pd.read_csv
+    ref_td.pd.read_csv = lambda path, *a, **k: real_read(csv, *a, **k)
+    try:
+        features = ['Fare', 'Pclass', 'Age', 'Sex_male', 'Relatives', 'Embarked']
+        targets = ['Survived']
+        torch.manual_seed(seed)
+        full = ref_td.TitanicDataset(features, targets, dropna=True, std=True)
+        dataset = full.partition_dataset()
+    finally:
+        ref_td.pd.read_csv = real_read
+    train_data, val_data, test_data = dataset.random_split((0.8, 0.2, 0), seed, 0)
+    train_loader = DataLoader(train_data, batch_size)
+    val_loader = DataLoader(val_data, batch_size)
+    encoders = [MLPEncoder(1, len(features), (5, 5), F.relu)]
+    decoders = [LogisticDecoder(1) for _ in targets]
+    model = MultiModN(1, encoders, decoders, 0.7, 0.3, device=CPU)
+    arrays = spec_to_arrays(spec_from_modules(model), "spec0")
+    optimizer = torch.optim.Adam(list(model.parameters()), 0.01)
+    history = MultiModNHistory(targets)
+    for _ in range(epochs):
+        model.train_epoch(train_loader, optimizer, CrossEntropyLoss(), history)
+        model.test(val_loader, CrossEntropyLoss(), history, tag='val')
+    arrays.update(spec_to_arrays(spec_from_modules(model), "spec_final"))
+    arrays.update(hist_arrays(history, "train", "train"))
+    arrays.update(hist_arrays(history, "val", "val"))
+    results = history.get_results()
+    save("titanic_pipeline", n_rows=n_rows, seed=seed, epochs=epochs, batch_size=batch_size,
+         X=np.asarray(full.X, dtype=np.float64), y=np.asarray(full.y),
+         train_idx=np.asarray(train_data.indices), val_idx=np.asarray(val_data.indices),
+         test_idx=np.asarray(test_data.indices), results=results.to_numpy(dtype=np.float64),
+         results_columns=np.array(list(results.columns)), results_index=np.array(list(results.index)), **arrays)
+
+
 if __name__ == "__main__":
     fixture_c1_titanic()
     fixture_c2("c2_mimic_small", 16, [6, 19, 40], (8, 8), 16, 1)
@@ -333,3 +381,4 @@ if __name__ == "__main__":
     fixture_sequence()
     fixture_zoo()
     fixture_dropout()
+    fixture_titanic_pipeline()
