@@ -188,6 +188,13 @@ int mmn_selftest_umma(int mode, int n, const float* a, const float* b, float* ou
 /* Diagnostic: cycles per round of the worker <-> MMA-issuer mbarrier handshake (out: device int64[2]). */
 int mmn_selftest_protocol(int iters, int n_mma, int flags, long long* out, void* stream);
 
+/* Diagnostic (tests, profiles): the wide regime's GEMM on its own — out[M x N] = a[M x K] . b[N x K]^T, a and b bf16
+ * with K contiguous (row pitches lda / ldb in elements, multiples of 8), fp32 accumulation in tensor memory.  Any of
+ * out_f32 (M x N fp32), out_bf16 (M x N) and out_bf16_t (N x M, the transposed copy every wide-regime epilogue also
+ * writes) may be NULL. */
+int mmn_selftest_gemm_bf16(int M, int N, int K, const void* a, long long lda, const void* b, long long ldb,
+                           float* out_f32, void* out_bf16, void* out_bf16_t, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

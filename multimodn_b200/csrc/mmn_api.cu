@@ -3,6 +3,9 @@
 #include "mmn_kernels.cuh"
 #include "mmn_tc.cuh"
 #include "mmn_tc2.cuh"
+#ifndef MMN_EMU
+#include "mmn_wide.cuh"
+#endif
 
 #include <algorithm>
 #include <cstdarg>
@@ -410,4 +413,79 @@ extern "C" int mmn_selftest_protocol(int iters, int n_mma, int flags, long long*
   MMN_LAUNCH(kfn, dim3(1), dim3(288), smem, stream, iters, n_mma, flags, out);
   MMN_CUDA(cudaGetLastError());
   return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// wide regime: layer-wise tcgen05 bf16 GEMMs (mmn_wide.cuh)
+// ------------------------------------------------------------------------------------------------
+#ifndef MMN_EMU
+namespace {
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TmapEncodeFn tmap_encoder() {
+  static TmapEncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (TmapEncodeFn)p;
+  }();
+  return fn;
+}
+// K-major bf16 operand [rows x k] with row pitch ld (elements): boxes of 64 k x box_rows rows, SWIZZLE_128B
+int make_operand_map(CUtensorMap* m, const void* base, long long rows, long long k, long long ld, int box_rows) {
+  TmapEncodeFn enc = tmap_encoder();
+  if (!enc) return fail("cuTensorMapEncodeTiled is not available in this driver");
+  if ((reinterpret_cast<size_t>(base) & 15) || (ld & 7)) return fail("wide GEMM operand: base must be 16-byte aligned and the row pitch a multiple of 8 elements");
+  const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)wide::BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for a %lld x %lld operand, pitch %lld", (int)r, rows, k, ld);
+  return 0;
+}
+// D[M x N] = A[M x K] . B[N x K]^T
+int wide_gemm(int n_sms, const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, const wide::Epi& epi,
+              void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  alignas(64) CUtensorMap ma, mb;
+  if (make_operand_map(&ma, A, M, K, lda, wide::BM) || make_operand_map(&mb, B, N, K, ldb, wide::BN)) return 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MMN_CUDA(cudaFuncSetAttribute(wide::mmn_wide_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wide::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = ((M + wide::BM - 1) / wide::BM) * ((N + wide::BN - 1) / wide::BN);
+  const int grid = std::min(tiles, n_sms);
+  wide::mmn_wide_gemm_kernel<<<grid, wide::kThreads, wide::kSmemBytes, (cudaStream_t)stream>>>(ma, mb, M, N, K, epi);
+  MMN_CUDA(cudaGetLastError());
+  return 0;
+}
+}  // namespace
+#endif
+
+extern "C" int mmn_selftest_gemm_bf16(int M, int N, int K, const void* a, long long lda, const void* b, long long ldb,
+                                      float* out_f32, void* out_bf16, void* out_bf16_t, void* stream) {
+#ifdef MMN_EMU
+  (void)M; (void)N; (void)K; (void)a; (void)lda; (void)b; (void)ldb; (void)out_f32; (void)out_bf16; (void)out_bf16_t; (void)stream;
+  return fail("mmn_selftest_gemm_bf16: the wide-regime GEMM is not part of the host emulator");
+#else
+  int dev = 0, n_sms = 0;
+  MMN_CUDA(cudaGetDevice(&dev));
+  MMN_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+  wide::Epi e;
+  memset(&e, 0, sizeof e);
+  e.mode = wide::EPI_ACCUM_F32;
+  e.scale = 1.f;
+  e.out_f32 = out_f32; e.ld_f32 = N;
+  e.out = (__nv_bfloat16*)out_bf16; e.ld_out = N;
+  e.out_t = (__nv_bfloat16*)out_bf16_t; e.ld_out_t = M;
+  return wide_gemm(n_sms, a, lda, b, ldb, M, N, K, e, stream);
+#endif
 }

@@ -1,0 +1,300 @@
+// mmn_wide.cuh — the wide regime (BASELINE config 4: state 1024, hidden 2048, bf16): layers that are real dense
+// contractions run layer by layer as persistent tcgen05 GEMMs instead of inside the per-tile step kernel.
+//
+//   D[M x N] = A[M x K] . B[N x K]^T        A, B bf16, K contiguous (K-major); fp32 accumulation in tensor memory
+//
+// One kernel shape serves forward (A = activations, B = W), data gradient (A = dZ, B = W^T copy) and weight gradient
+// (A = dZ^T, B = X^T: the contraction runs over the batch rows) because every epilogue that produces an activation or a
+// dZ writes it in both orientations (row-major and transposed).
+//
+//   warp 0   TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B boxes of 64 bf16 x 128 / 256 rows) into a 4-stage ring
+//   warp 1   MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M128 N256 K16, 4 per stage; tcgen05.commit frees the stage
+//   warp 2   TMEM allocator (512 columns = two 128 x 256 fp32 accumulators: the epilogue of tile i overlaps tile i+1)
+//   warps 4-7 epilogue: tcgen05.ld 16 columns at a time -> bias / activation / select / derivative -> global stores
+//
+// Out-of-range rows / columns / k are zero-filled by the TMA unit, so M, N, K need no padding (row pitches: 16 bytes).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "mmn_tc.cuh"
+
+namespace mmn {
+namespace wide {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int kThreads = 256;
+constexpr int kStageBytes = (BM + BN) * BK * 2;                  // 48 KB
+constexpr int kSmemBytes = STAGES * kStageBytes + 1024 + 256;      // + alignment slack + barriers
+
+enum {
+  EPI_STORE = 0,       // out = act(acc + bias)                                   (forward hidden / decoder layers)
+  EPI_SELECT = 1,      // out = present[r] ? act(acc + bias) : aux[r][n]; sc += (out - aux)^2   (encoder output = new state)
+  EPI_DACT = 2,        // out = acc * act'(aux[r][n])                             (data gradient into a hidden layer)
+  EPI_ACCUM_F32 = 3,   // out_f32 (+)= acc                                         (weight gradient; state gradient G += ...)
+  EPI_CARRY = 4,       // out_f32 = present[r] ? acc : out_f32                     (state carry through an encoder)
+};
+
+struct Epi {
+  int mode, act, accumulate;
+  const float* bias;                                  // [N] or null
+  float* out_f32; long long ld_f32;                   // row-major fp32
+  __nv_bfloat16* out; long long ld_out;               // row-major bf16
+  __nv_bfloat16* out_t; long long ld_out_t;           // transposed bf16 [N x M]
+  const __nv_bfloat16* aux; long long ld_aux;         // activation for act' / previous state for the select
+  const unsigned char* present;                       // [M]
+  float* sc_sum;                                      // state-change accumulator (one float)
+  float scale;                                        // multiplies acc before everything else (EPI_ACCUM_F32)
+};
+
+__device__ __forceinline__ unsigned umma_idesc_bf16(int M, int N) {
+  // kind::f16: c_format = F32 (1) @4, a_format = b_format = BF16 (1) @7 / @10, both K-major, N>>3 @17, M>>4 @24
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc, unsigned idesc,
+                                          unsigned accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
+      "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, unsigned long long* bar, void* dst, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(map)) : "memory");
+}
+
+struct Pipe {
+  int stage;
+  unsigned phase;
+  __device__ __forceinline__ void advance() {
+    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+  }
+};
+
+__device__ __forceinline__ float wide_act(int act, float z) {
+  switch (act) {
+    case MMN_ACT_RELU: return fmaxf(z, 0.f);
+    case MMN_ACT_SIGMOID: return 1.f / (1.f + __expf(-z));
+    case MMN_ACT_TANH: return tanhf(z);
+    default: return z;
+  }
+}
+__device__ __forceinline__ float wide_dact(int act, float a) {      // derivative from the OUTPUT of the activation
+  switch (act) {
+    case MMN_ACT_RELU: return a > 0.f ? 1.f : 0.f;
+    case MMN_ACT_SIGMOID: return a * (1.f - a);
+    case MMN_ACT_TANH: return 1.f - a * a;
+    default: return 1.f;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N, int K,
+                     const Epi epi) {
+  extern __shared__ __align__(1024) char smem_raw[];
+  char* base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(base + STAGES * kStageBytes);
+  unsigned long long* empty = full + STAGES;
+  unsigned long long* acc_full = empty + STAGES;      // [2]
+  unsigned long long* acc_empty = acc_full + 2;       // [2]
+  unsigned* tslot = reinterpret_cast<unsigned*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN, n_tiles = tiles_m * tiles_n;
+  const int kb_n = (K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 128); }
+    mbar_fence_init();
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 2) tmem_alloc(tslot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem = *tslot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      Pipe p{0, 0};
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+        for (int kb = 0; kb < kb_n; ++kb) {
+          mbar_wait(empty + p.stage, p.phase ^ 1u);
+          char* sa = base + p.stage * kStageBytes;
+          mbar_expect_tx(full + p.stage, kStageBytes);
+          tma_load_2d(&map_a, full + p.stage, sa, kb * BK, m0);
+          tma_load_2d(&map_b, full + p.stage, sa + BM * BK * 2, kb * BK, n0);
+          p.advance();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const bool leader = elect_one() != 0;
+    const unsigned idesc = umma_idesc_bf16(BM, BN);
+    const unsigned sbase = smem_u32(base);
+    Pipe p{0, 0};
+    unsigned acc_phase[2] = {0u, 0u};
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      mbar_wait(acc_empty + acc, acc_phase[acc] ^ 1u);
+      acc_phase[acc] ^= 1u;
+      tc_fence_after();
+      for (int kb = 0; kb < kb_n; ++kb) {
+        mbar_wait(full + p.stage, p.phase);
+        tc_fence_after();
+        if (leader) {
+          const unsigned sa = sbase + p.stage * kStageBytes, sb = sa + BM * BK * 2;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(tmem + acc * BN, umma_desc_k(sa, k), umma_desc_k(sb, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(empty + p.stage);
+          if (kb == kb_n - 1) umma_commit(acc_full + acc);
+        }
+        __syncwarp();
+        p.advance();
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue =====
+    const int q = warp & 3;
+    unsigned acc_phase[2] = {0u, 0u};
+    int it = 0;
+    float sc = 0.f;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+      const int r = m0 + 32 * q + lane;
+      const bool rv = r < M;
+      mbar_wait(acc_full + acc, acc_phase[acc]);
+      acc_phase[acc] ^= 1u;
+      tc_fence_after();
+      const bool pres = (epi.present && rv) ? epi.present[r] != 0 : true;
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem + ((unsigned)(32 * q) << 16) + acc * BN + c0, v);     // warp-collective: outside every branch
+        const int n = n0 + c0;
+        if (n >= N) continue;                                              // uniform
+        const bool full16 = n + 16 <= N;
+        float aux[16];
+        if (epi.aux && rv) {
+          const __nv_bfloat16* ap = epi.aux + (long long)r * epi.ld_aux + n;
+          if (full16 && ((epi.ld_aux & 7) == 0)) {
+            const uint4 a0 = *reinterpret_cast<const uint4*>(ap), a1 = *reinterpret_cast<const uint4*>(ap + 8);
+            const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&a0);
+            const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&a1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f0 = __bfloat1622float2(h0[i]), f1 = __bfloat1622float2(h1[i]);
+              aux[2 * i] = f0.x; aux[2 * i + 1] = f0.y; aux[8 + 2 * i] = f1.x; aux[8 + 2 * i + 1] = f1.y;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) aux[i] = n + i < N ? __bfloat162float(ap[i]) : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) aux[i] = 0.f;
+        }
+        if (epi.mode == EPI_STORE || epi.mode == EPI_SELECT) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float b = (epi.bias && n + i < N) ? __ldg(epi.bias + n + i) : 0.f;
+            v[i] = wide_act(epi.act, v[i] + b);
+          }
+          if (epi.mode == EPI_SELECT) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              // what the next layer reads is the bf16-rounded state: measure the change on that
+              const float nw = pres ? __bfloat162float(__float2bfloat16(v[i])) : aux[i];
+              const float df = (rv && n + i < N) ? nw - aux[i] : 0.f;
+              sc = fmaf(df, df, sc);
+              v[i] = nw;
+            }
+          }
+        } else if (epi.mode == EPI_DACT) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = v[i] * wide_dact(epi.act, aux[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= epi.scale;
+        }
+        if (rv) {
+        if (epi.out_f32) {
+          float* op = epi.out_f32 + (long long)r * epi.ld_f32 + n;
+          if (epi.mode == EPI_CARRY) {
+            if (pres) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (n + i < N) op[i] = v[i];
+            }
+          } else if (full16 && ((epi.ld_f32 & 3) == 0)) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              if (epi.accumulate) {
+                const float4 old = *reinterpret_cast<const float4*>(op + i);
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
+              *reinterpret_cast<float4*>(op + i) = o;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (n + i < N) op[i] = epi.accumulate ? op[i] + v[i] : v[i];
+          }
+        }
+        if (epi.out) {
+          __nv_bfloat16* op = epi.out + (long long)r * epi.ld_out + n;
+          if (full16 && ((epi.ld_out & 7) == 0)) {
+            uint4 o[2];
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            *reinterpret_cast<uint4*>(op) = o[0];
+            *reinterpret_cast<uint4*>(op + 8) = o[1];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (n + i < N) op[i] = __float2bfloat16(v[i]);
+          }
+        }
+        if (epi.out_t) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (n + i < N) epi.out_t[(long long)(n + i) * epi.ld_out_t + r] = __float2bfloat16(v[i]);
+        }
+        }
+        __syncwarp();                 // the next tcgen05.ld is warp-collective
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty + acc);
+    }
+    if (epi.sc_sum) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+      if (lane == 0 && sc != 0.f) atomicAdd(epi.sc_sum, sc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace wide
+}  // namespace mmn

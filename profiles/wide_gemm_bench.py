@@ -1,0 +1,32 @@
+"""Throughput of the wide regime's tcgen05 bf16 GEMM at config-4 layer shapes (B = 8192 rows per GPU).
+usage: python profiles/wide_gemm_bench.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from multimodn_b200 import _lib
+
+lib = _lib.get_lib()
+dev = torch.device("cuda")
+stream = torch.cuda.current_stream().cuda_stream
+for (M, N, K, what) in [(8192, 2048, 2048, "fwd hidden 2048->2048"), (8192, 1024, 2048, "fwd 2048->state 1024"),
+                        (2048, 2048, 8192, "wgrad 2048x2048 over 8192 rows"), (8192, 2048, 1024, "decoder 1024->2048")]:
+    a = torch.randn(M, K, device=dev).to(torch.bfloat16)
+    b = torch.randn(N, K, device=dev).to(torch.bfloat16)
+    ob = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    ot = torch.empty(N, M, dtype=torch.bfloat16, device=dev)
+    def run():
+        lib.check(lib.dll.mmn_selftest_gemm_bf16(M, N, K, a.data_ptr(), K, b.data_ptr(), K, None, ob.data_ptr(), ot.data_ptr(), stream))
+    for _ in range(3): run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20): run()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    for _ in range(3): torch.matmul(a, b.T)
+    e0.record()
+    for _ in range(20): torch.matmul(a, b.T)
+    e1.record(); torch.cuda.synchronize()
+    ms_ref = e0.elapsed_time(e1) / 20
+    fl = 2.0 * M * N * K
+    print(f"{what:34s} M={M} N={N} K={K}: {ms*1e3:7.1f} us  {fl/ms/1e9:7.1f} TFLOP/s   (cuBLAS {ms_ref*1e3:7.1f} us, {fl/ms_ref/1e9:7.1f} TFLOP/s)")
