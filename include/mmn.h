@@ -37,6 +37,11 @@ extern "C" {
 #define MMN_MAX_DECODERS 16
 #define MMN_MAX_CLASSES 32
 
+/* Arithmetic of a plan.  FP32: the fused per-tile step kernels, 1e-5 relative to the reference.  BF16: the wide regime
+ * (BASELINE config 4) — every layer is a tensor-core GEMM over the whole batch with bf16 weights / activations / layer
+ * gradients, fp32 accumulation, fp32 master weights and gradients; 1e-2 relative to the reference. */
+enum { MMN_PRECISION_FP32 = 0, MMN_PRECISION_BF16 = 1 };
+
 /* activation applied after a Linear layer (mlp_encoder.py:46,76; decoders.py:20,44-45) */
 enum { MMN_ACT_IDENTITY = 0, MMN_ACT_RELU = 1, MMN_ACT_SIGMOID = 2, MMN_ACT_TANH = 3 };
 
@@ -75,7 +80,7 @@ typedef struct mmn_model_desc {
   int32_t state_size;
   int32_t n_encoders;
   int32_t n_decoders;
-  int32_t reserved;
+  int32_t precision;  /* MMN_PRECISION_* */
   int64_t init_off;   /* TrainableInitState.state_value (1,S) (state.py:25-27) */
   int64_t n_params;   /* length of the packed parameter buffer in floats */
   const mmn_encoder_desc* encoders; /* host */
@@ -142,7 +147,7 @@ void mmn_plan_destroy(mmn_plan* plan);
  *                   resident in tensor memory; needs state <= 64, layers <= 64 wide, <= 16 classes.  Default of
  *                   mmn_forward when the model qualifies; mmn_train_step uses it under MMN_ENGINE=tc2
  * The environment variable MMN_ENGINE=fma|tc|tc2, read by mmn_plan_create, forces one. */
-enum { MMN_ENGINE_FMA = 0, MMN_ENGINE_TC = 1, MMN_ENGINE_TC2 = 2 };
+enum { MMN_ENGINE_FMA = 0, MMN_ENGINE_TC = 1, MMN_ENGINE_TC2 = 2, MMN_ENGINE_WIDE = 3 /* precision = bf16 */ };
 int32_t mmn_plan_engine(const mmn_plan* plan);           /* engine of mmn_train_step */
 int32_t mmn_plan_forward_engine(const mmn_plan* plan);   /* engine of mmn_forward */
 
@@ -150,7 +155,8 @@ int64_t mmn_metrics_count(const mmn_plan* plan);            /* doubles in mmn_ou
 int64_t mmn_grad_count(const mmn_plan* plan);               /* floats in the gradient buffer:
                                                                n_params + E (tail: per-encoder
                                                                present-row counts of the step) */
-/* Bytes of scratch (activation stash of the resident batch tiles) for a call on n_rows rows. */
+/* Bytes of scratch for a call on n_rows rows: the activation stash of the resident batch tiles (fp32 plans, backward
+ * only) or every layer's activations in both orientations (bf16 plans; mmn_forward needs a workspace too). */
 int64_t mmn_workspace_bytes(const mmn_plan* plan, int64_t n_rows, int32_t with_backward);
 
 /* Reference batch-level missingness test, `any(data_encoder.isnan().flatten())`
@@ -194,6 +200,9 @@ int mmn_selftest_protocol(int iters, int n_mma, int flags, long long* out, void*
  * writes) may be NULL. */
 int mmn_selftest_gemm_bf16(int M, int N, int K, const void* a, long long lda, const void* b, long long ldb,
                            float* out_f32, void* out_bf16, void* out_bf16_t, void* stream);
+
+/* Kernels launched so far by bf16 (wide-regime) plans in this process: launch accounting for benchmarks. */
+int64_t mmn_wide_launch_count(void);
 
 #ifdef __cplusplus
 }

@@ -35,7 +35,7 @@ class DecoderDesc(C.Structure):
 
 class ModelDesc(C.Structure):
     _fields_ = [("state_size", C.c_int32), ("n_encoders", C.c_int32), ("n_decoders", C.c_int32),
-                ("reserved", C.c_int32), ("init_off", C.c_int64), ("n_params", C.c_int64),
+                ("precision", C.c_int32), ("init_off", C.c_int64), ("n_params", C.c_int64),
                 ("encoders", C.POINTER(EncoderDesc)), ("decoders", C.POINTER(DecoderDesc))]
 
 
@@ -57,10 +57,12 @@ class TrainArgs(C.Structure):
                 ("dropout_seed", C.c_uint32), ("training", C.c_int32)]
 
 
+PRECISIONS = {"fp32": 0, "bf16": 1}      # MMN_PRECISION_*
+
 EXPORTS = ("mmn_last_error", "mmn_abi_version", "mmn_plan_create", "mmn_plan_destroy", "mmn_metrics_count",
            "mmn_grad_count", "mmn_workspace_bytes", "mmn_scan_missing", "mmn_forward", "mmn_train_step",
            "mmn_adam_step", "mmn_selftest_umma", "mmn_selftest_protocol", "mmn_plan_engine", "mmn_plan_forward_engine",
-           "mmn_selftest_gemm_bf16")
+           "mmn_selftest_gemm_bf16", "mmn_wide_launch_count")
 
 
 class MMNError(RuntimeError):
@@ -110,6 +112,7 @@ class Library:
         d.mmn_selftest_umma.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         d.mmn_selftest_gemm_bf16.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        d.mmn_wide_launch_count.restype = C.c_int64
         if d.mmn_abi_version() != ABI_VERSION:
             raise MMNError(f"{path}: ABI version {d.mmn_abi_version()} != {ABI_VERSION}; rebuild the library")
 

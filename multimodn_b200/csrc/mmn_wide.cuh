@@ -44,6 +44,8 @@ struct Epi {
   __nv_bfloat16* out_t; long long ld_out_t;           // transposed bf16 [N x M]
   const __nv_bfloat16* aux; long long ld_aux;         // activation for act' / previous state for the select
   const unsigned char* present;                       // [M]
+  const int* skip;                                    // device flag: non-zero = the step is skipped for every row
+  unsigned drop_thr, drop_seed, drop_row_base, drop_col_base;   // EPI_CARRY through a dropout mask (thr 0 = none)
   float* sc_sum;                                      // state-change accumulator (one float)
   float scale;                                        // multiplies acc before everything else (EPI_ACCUM_F32)
 };
@@ -184,7 +186,8 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       mbar_wait(acc_full + acc, acc_phase[acc]);
       acc_phase[acc] ^= 1u;
       tc_fence_after();
-      const bool pres = (epi.present && rv) ? epi.present[r] != 0 : true;
+      const bool skipped = epi.skip && *epi.skip != 0;
+      const bool pres = ((epi.present && rv) ? epi.present[r] != 0 : true) && !skipped;
       for (int c0 = 0; c0 < BN; c0 += 16) {
         float v[16];
         tmem_ld16(tmem + ((unsigned)(32 * q) << 16) + acc * BN + c0, v);     // warp-collective: outside every branch
@@ -230,6 +233,11 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         } else if (epi.mode == EPI_DACT) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = v[i] * wide_dact(epi.act, aux[i]);
+        } else if (epi.mode == EPI_CARRY && epi.drop_thr) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            v[i] = mmn_dropout_keep(epi.drop_seed, epi.drop_row_base + (unsigned)r, epi.drop_col_base + (unsigned)(n + i), epi.drop_thr)
+                       ? v[i] * epi.scale : 0.f;
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] *= epi.scale;

@@ -71,7 +71,7 @@ class _Runtime:
         self.packed = PackedModel(model.init_state.state_value, model.encoders, model.decoders, self.S)
         self.E, self.D = len(self.packed.encoders), len(self.packed.decoders)
         self.flat = self.packed.pack(self.device)
-        desc, self._keep = self.packed.model_desc()
+        desc, self._keep = self.packed.model_desc(_lib.PRECISIONS[model.precision])
         handle = C.c_void_p()
         self.lib.check(self.lib.dll.mmn_plan_create(C.byref(desc), C.byref(handle)))
         self.plan = handle
@@ -223,8 +223,9 @@ class _Runtime:
     def forward(self, batch, n_rows, **outs):
         self.ensure_packed()
         o = self.outputs(**outs)
-        self.lib.check(self.lib.dll.mmn_forward(self.plan, C.byref(batch), self.flat.data_ptr(), C.byref(o), None, 0,
-                                                self.stream()))
+        ws, ws_bytes = self.workspace(n_rows, False)        # bf16 plans keep their activations there; fp32 plans need none
+        self.lib.check(self.lib.dll.mmn_forward(self.plan, C.byref(batch), self.flat.data_ptr(), C.byref(o),
+                                                ws.data_ptr() if ws is not None else None, ws_bytes, self.stream()))
 
     def train_step(self, batch, n_rows, err_penalty, scp_scaled, training, metrics):
         self.ensure_packed()
@@ -272,6 +273,7 @@ class MultiModN(nn.Module):
             init_state: Optional[InitState] = None,
             device: Optional[torch.device] = None,
             missing_mode: str = "row",
+            precision: str = "fp32",
     ):
         super().__init__()
         self.shuffle_mode = shuffle_mode
@@ -285,6 +287,9 @@ class MultiModN(nn.Module):
         if missing_mode not in ("row", "batch"):
             raise ValueError(f"missing_mode must be 'row' or 'batch', got {missing_mode!r}")
         self.missing_mode = missing_mode
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {precision!r}")
+        self.precision = precision
         self.to(self.device)
         self._rt: Optional[_Runtime] = None
         self._dp = None                 # (world, rank, group) once data parallelism is enabled

@@ -160,8 +160,8 @@ class PackedModel:
                 raise NotImplementedError("parameters shared between layers are not supported")
             seen.add(id(p))
 
-    def model_desc(self):
-        """-> (ModelDesc, keep-alive tuple)"""
+    def model_desc(self, precision: int = 0):
+        """-> (ModelDesc, keep-alive tuple); precision: 0 = fp32 (fused step kernels), 1 = bf16 (wide regime)"""
         E, D = len(self.encoders), len(self.decoders)
         encs = (_lib.EncoderDesc * E)()
         decs = (_lib.DecoderDesc * D)()
@@ -182,7 +182,7 @@ class PackedModel:
                 raise NotImplementedError(f"at most {_lib.MAX_CLASSES} classes per decoder")
             decs[d].n_classes, decs[d].n_layers = m.n_classes, len(m.layers)
             fill(decs[d].layers, m.layers)
-        desc = _lib.ModelDesc(self.S, E, D, 0, self.init_off, self.n_params,
+        desc = _lib.ModelDesc(self.S, E, D, int(precision), self.init_off, self.n_params,
                               C.cast(encs, C.POINTER(_lib.EncoderDesc)), C.cast(decs, C.POINTER(_lib.DecoderDesc)))
         return desc, (encs, decs)
 

@@ -137,6 +137,8 @@ def expand_decoder(dec):
 
 def cast_spec(spec, dtype):
     out = dict(state_size=spec["state_size"], init_state=spec["init_state"].astype(dtype))
+    if "precision" in spec:
+        out["precision"] = spec["precision"]
     out["encoders"] = [dict(e, layers=[(W.astype(dtype), b.astype(dtype)) for W, b in e["layers"]])
                        for e in spec["encoders"]]
     out["decoders"] = [dict(d, layers=[(W.astype(dtype), b.astype(dtype)) for W, b in d["layers"]])
@@ -160,14 +162,34 @@ def resolve_sequence(encoder_sequence, n_encoders):
 # --------------------------------------------------------------------------------------
 # forward
 # --------------------------------------------------------------------------------------
-def _mlp_forward(layers, a, s_prev, keep_scale):
+def round_bf16(x):
+    """round-to-nearest-even to bfloat16, returned in the input's float32 container"""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    u = x.view(np.uint32)
+    r = ((u + np.uint32(0x7FFF) + ((u >> np.uint32(16)) & np.uint32(1))) & np.uint32(0xFFFF0000)).view(np.float32)
+    return np.where(np.isfinite(x), r, x)
+
+
+def _rounding(spec):
+    """spec['precision'] == 'bf16' restates the wide regime (multimodn_b200/csrc/mmn_wide_step.cuh): the same
+    algorithm with weights, layer inputs, activations, states and layer gradients rounded to bfloat16 where the
+    CUDA path stores them as bfloat16; sums, the state gradient and the parameter gradients stay float32."""
+    return round_bf16 if spec.get("precision") == "bf16" else None
+
+
+def _mlp_forward(layers, a, s_prev, keep_scale, rnd=None, round_last=True):
     cache = []
     for j, L in enumerate(layers):
         inp = np.concatenate([a, s_prev], axis=1) if L["has_state"] else a
         if j == 0 and keep_scale is not None:
             inp = inp * keep_scale
-        z = inp @ L["W"].T + L["b"]
+        W = L["W"]
+        if rnd is not None:
+            inp, W = rnd(inp), rnd(W)
+        z = inp @ W.T + L["b"]
         a = act_fwd(L["act"], z)
+        if rnd is not None and (round_last or j < len(layers) - 1):
+            a = rnd(a)
         cache.append((inp, a))
     return a, cache
 
@@ -201,6 +223,7 @@ def forward(spec, data, targets, encoder_sequence=None, missing_mode="row", trai
     enc_layers = [expand_encoder(e, S) for e in spec["encoders"]]
     dec_layers = [expand_decoder(d) for d in spec["decoders"]]
 
+    rnd = _rounding(spec)
     ce = np.zeros((E + 1, D))
     n_correct = np.zeros((E + 1, D))
     cm = np.zeros((4, E + 1, D))           # tp, tn, fp, fn
@@ -213,7 +236,7 @@ def forward(spec, data, targets, encoder_sequence=None, missing_mode="row", trai
 
     def eval_decoders(state, row, mask):
         for d in range(D):
-            p, dcache = _mlp_forward(dec_layers[d], state, None, None)
+            p, dcache = _mlp_forward(dec_layers[d], state, None, None, rnd, round_last=False)
             pred = _first_argmax(p)
             preds[row, d] = pred
             outputs[row][d] = p
@@ -233,6 +256,8 @@ def forward(spec, data, targets, encoder_sequence=None, missing_mode="row", trai
                 cm[:, row, d] = np.nan
 
     state = np.tile(spec["init_state"][None, :], (B, 1))     # state.py:30
+    if rnd is not None:
+        state = rnd(state)
     states = [state]
     ones = np.ones(B, dtype=bool)
     n_present[0] = B
@@ -257,7 +282,7 @@ def forward(spec, data, targets, encoder_sequence=None, missing_mode="row", trai
             if train and enc["kind"] == "mimic" and p_drop > 0:
                 keep = dropout_keep(dropout_seed, e, np.arange(B) + row_offset, x.shape[1] + S, p_drop)
                 keep_scale = (keep * dtype.type(1.0 / (1.0 - p_drop))).astype(dtype)
-            s_hat, ecache = _mlp_forward(enc_layers[e], xc, state, keep_scale)
+            s_hat, ecache = _mlp_forward(enc_layers[e], xc, state, keep_scale, rnd)
             new_state = np.where(present[:, None], s_hat, state)
             sc[e] = float((((new_state - state).astype(np.float64)) ** 2).sum() / (Bg * S))  # :174
             step.update(cache=ecache, keep_scale=keep_scale)
@@ -269,7 +294,7 @@ def forward(spec, data, targets, encoder_sequence=None, missing_mode="row", trai
             # whole step skipped: history row e+1 untouched; predictions = decoders on the
             # unchanged state (deliberate deviation B2: reference predict has no NaN check)
             for d in range(D):
-                p, _ = _mlp_forward(dec_layers[d], state, None, None)
+                p, _ = _mlp_forward(dec_layers[d], state, None, None, rnd, round_last=False)
                 preds[e + 1, d] = _first_argmax(p)
                 outputs[e + 1][d] = p
         step["s_new"] = state
@@ -293,7 +318,7 @@ def loss_from(fwd, spec, err_penalty, state_change_penalty_scaled):
 # --------------------------------------------------------------------------------------
 # backward (hand-derived)
 # --------------------------------------------------------------------------------------
-def _mlp_backward(layers, cache, dout, S, grads, keep_scale=None):
+def _mlp_backward(layers, cache, dout, S, grads, keep_scale=None, rnd=None):
     """returns (d_first_input_without_state_or_None, d_state_or_None); accumulates grads."""
     d_state = None
     da = dout
@@ -301,9 +326,12 @@ def _mlp_backward(layers, cache, dout, S, grads, keep_scale=None):
         L = layers[j]
         inp, out = cache[j]
         dz = act_bwd(L["act"], out, da)
+        W = L["W"]
+        if rnd is not None:
+            dz, W = rnd(dz), rnd(W)
         grads[j][0] += dz.T @ inp
         grads[j][1] += dz.sum(axis=0)
-        dinp = dz @ L["W"]
+        dinp = dz @ W
         if j == 0 and keep_scale is not None:
             dinp = dinp * keep_scale
         if L["has_state"]:
@@ -335,6 +363,7 @@ def train_step(spec, data, targets, err_penalty, state_change_penalty_scaled, en
     g_enc = [[[np.zeros_like(L["W"]), np.zeros_like(L["b"])] for L in ls] for ls in enc_layers]
     g_dec = [[[np.zeros_like(L["W"]), np.zeros_like(L["b"])] for L in ls] for ls in dec_layers]
     touched = np.zeros(E, dtype=bool)
+    rnd = _rounding(spec)
     c_err = dtype.type(err_penalty / (D * (E + 1) * Bg))
     c_sc = dtype.type(2.0 * state_change_penalty_scaled / (E * Bg * S))
 
@@ -352,7 +381,7 @@ def train_step(spec, data, targets, err_penalty, state_change_penalty_scaled, en
             sm = ex / ex.sum(axis=1, keepdims=True)
             sm[np.arange(B), y] -= 1
             dp = (sm * (c_err * mask.astype(dtype))[:, None]).astype(dtype)
-            da, _ = _mlp_backward(dec_layers[d], dcache, dp, S, g_dec[d])
+            da, _ = _mlp_backward(dec_layers[d], dcache, dp, S, g_dec[d], rnd=rnd)
             g = g + da
         return g
 
@@ -366,7 +395,7 @@ def train_step(spec, data, targets, err_penalty, state_change_penalty_scaled, en
         u = c_sc * (step["s_new"] - step["s_prev"])
         G = G + u
         dout = G * present[:, None]
-        _, d_state = _mlp_backward(enc_layers[e], step["cache"], dout, S, g_enc[e], step.get("keep_scale"))
+        _, d_state = _mlp_backward(enc_layers[e], step["cache"], dout, S, g_enc[e], step.get("keep_scale"), rnd=rnd)
         touched[e] = True
         G = np.where(present[:, None], d_state, G) - u
     G = G + decoders_backward(0)

@@ -10,7 +10,8 @@ from multimodn_b200.decoders import ClassDecoder, MLPDecoder
 ACT = {"relu": F.relu, "sigmoid": torch.sigmoid, "tanh": torch.tanh, "identity": lambda x: x}
 
 
-def model_from_spec(spec, err_penalty, state_change_penalty, device, missing_mode="row", shuffle_mode=False):
+def model_from_spec(spec, err_penalty, state_change_penalty, device, missing_mode="row", shuffle_mode=False,
+                    precision="fp32"):
     S = spec["state_size"]
     encs, decs = [], []
     for e in spec["encoders"]:
@@ -39,7 +40,7 @@ def model_from_spec(spec, err_penalty, state_change_penalty, device, missing_mod
             lin.bias.data = torch.from_numpy(np.array(b, dtype=np.float32))
         decs.append(dec)
     model = MultiModN(S, encs, decs, err_penalty, state_change_penalty, shuffle_mode=shuffle_mode,
-                      device=device, missing_mode=missing_mode)
+                      device=device, missing_mode=missing_mode, precision=precision)
     model.init_state.state_value.data = torch.from_numpy(
         np.array(spec["init_state"], dtype=np.float32).reshape(1, -1)).to(device)
     return model
