@@ -10,7 +10,8 @@
 //   warp 0   TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B boxes of 64 bf16 x 128 / 256 rows) into a 4-stage ring
 //   warp 1   MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M128 N256 K16, 4 per stage; tcgen05.commit frees the stage
 //   warp 2   TMEM allocator (512 columns = two 128 x 256 fp32 accumulators: the epilogue of tile i overlaps tile i+1)
-//   warps 4-7 epilogue: tcgen05.ld 16 columns at a time -> bias / activation / select / derivative -> global stores
+//   warps 4-11 epilogue (two per TMEM lane quarter, 128 columns each): tcgen05.ld 16 columns at a time -> bias /
+//            activation / select / derivative -> row-major stores + lane-pair-packed transposed stores
 //
 // Out-of-range rows / columns / k are zero-filled by the TMA unit, so M, N, K need no padding (row pitches: 16 bytes).
 #pragma once
@@ -24,7 +25,7 @@ namespace mmn {
 namespace wide {
 
 constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;          // warps 0-2: TMA / MMA / TMEM allocator; warps 4-11: epilogue
 constexpr int kStageBytes = (BM + BN) * BK * 2;                  // 48 KB
 constexpr int kSmemBytes = STAGES * kStageBytes + 1024 + 256;      // + alignment slack + barriers
 
@@ -117,7 +118,7 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 256); }
     mbar_fence_init();
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
@@ -174,7 +175,8 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     }
   } else if (warp >= 4) {
     // ===== epilogue =====
-    const int q = warp & 3;
+    // warp w may touch TMEM lanes 32 (w % 4) ..: two warps per lane quarter, each takes half of the 256 columns
+    const int q = warp & 3, half = (warp - 4) >> 2;
     unsigned acc_phase[2] = {0u, 0u};
     int it = 0;
     float sc = 0.f;
@@ -188,7 +190,8 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       tc_fence_after();
       const bool skipped = epi.skip && *epi.skip != 0;
       const bool pres = ((epi.present && rv) ? epi.present[r] != 0 : true) && !skipped;
-      for (int c0 = 0; c0 < BN; c0 += 16) {
+      const bool pair_ok = (r | 1) < M;                // rows r and r ^ 1 both exist: packed transposed stores
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 16) {
         float v[16];
         tmem_ld16(tmem + ((unsigned)(32 * q) << 16) + acc * BN + c0, v);     // warp-collective: outside every branch
         const int n = n0 + c0;
@@ -215,10 +218,27 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           for (int i = 0; i < 16; ++i) aux[i] = 0.f;
         }
         if (epi.mode == EPI_STORE || epi.mode == EPI_SELECT) {
+          if (epi.bias) {
+            if (full16 && ((reinterpret_cast<size_t>(epi.bias) & 15) == 0)) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float b = (epi.bias && n + i < N) ? __ldg(epi.bias + n + i) : 0.f;
-            v[i] = wide_act(epi.act, v[i] + b);
+              for (int i = 0; i < 16; i += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(epi.bias + n + i));
+                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += n + i < N ? __ldg(epi.bias + n + i) : 0.f;
+            }
+          }
+          if (epi.act == MMN_ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+          } else if (epi.act == MMN_ACT_SIGMOID) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __fdividef(1.f, 1.f + __expf(-v[i]));
+          } else if (epi.act == MMN_ACT_TANH) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
           }
           if (epi.mode == EPI_SELECT) {
 #pragma unroll
@@ -231,8 +251,16 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             }
           }
         } else if (epi.mode == EPI_DACT) {
+          if (epi.act == MMN_ACT_RELU) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = v[i] * wide_dact(epi.act, aux[i]);
+            for (int i = 0; i < 16; ++i) v[i] = aux[i] > 0.f ? v[i] : 0.f;
+          } else if (epi.act == MMN_ACT_SIGMOID) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= aux[i] * (1.f - aux[i]);
+          } else if (epi.act == MMN_ACT_TANH) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= 1.f - aux[i] * aux[i];
+          }
         } else if (epi.mode == EPI_CARRY && epi.drop_thr) {
 #pragma unroll
           for (int i = 0; i < 16; ++i)
@@ -282,11 +310,22 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
               if (n + i < N) op[i] = __float2bfloat16(v[i]);
           }
         }
-        if (epi.out_t) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (n + i < N) epi.out_t[(long long)(n + i) * epi.ld_out_t + r] = __float2bfloat16(v[i]);
         }
+        if (epi.out_t) {
+          // transposed copy: lanes r, r ^ 1 exchange so that each writes one 4-byte pair {row even, row odd} of a column
+          // (even lanes the even columns, odd lanes the odd ones) instead of two 2-byte stores
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const float o0 = __shfl_xor_sync(0xffffffffu, v[i], 1), o1 = __shfl_xor_sync(0xffffffffu, v[i + 1], 1);
+            if (pair_ok) {
+              const int col = n + i + (lane & 1);
+              const __nv_bfloat162 pr = (lane & 1) ? __floats2bfloat162_rn(o1, v[i + 1]) : __floats2bfloat162_rn(v[i], o0);
+              if (col < N) *reinterpret_cast<__nv_bfloat162*>(epi.out_t + (long long)col * epi.ld_out_t + (r & ~1)) = pr;
+            } else if (rv) {
+              if (n + i < N) epi.out_t[(long long)(n + i) * epi.ld_out_t + r] = __float2bfloat16(v[i]);
+              if (n + i + 1 < N) epi.out_t[(long long)(n + i + 1) * epi.ld_out_t + r] = __float2bfloat16(v[i + 1]);
+            }
+          }
         }
         __syncwarp();                 // the next tcgen05.ld is warp-collective
       }

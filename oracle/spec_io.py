@@ -151,6 +151,9 @@ CONFIGS = {
     "c3_mnar": dict(S=256, features=[6, 99, 242, 110, 768, 768, 1024, 1024], enc_kind="mimic",
                     enc_hidden=(32, 32), n_decoders=6, dec_hidden=(32, 32), err_penalty=1.0,
                     state_change_penalty=0.3),
+    # wide regime (BASELINE.json configs[3]): precision "bf16", 8192 rows per GPU
+    "c4_wide": dict(S=1024, features=[1024, 1024, 768, 768], enc_kind="mimic", enc_hidden=(2048, 2048), n_decoders=2,
+                    dec_hidden=(2048,), err_penalty=1.0, state_change_penalty=0.3),
 }
 
 
