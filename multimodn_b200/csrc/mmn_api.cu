@@ -281,9 +281,47 @@ int make_operand_map(CUtensorMap* m, const void* base, long long rows, long long
   return 0;
 }
 long long g_wide_launches = 0;       // kernels launched by the wide path (bench.py's gpu_launches)
+// MMN_WIDE_TIMERS=1: CUDA events around every launch of a step, summed per category and printed (development aid)
+struct WideTimers {
+  bool on = false;
+  std::vector<std::pair<const char*, std::pair<cudaEvent_t, cudaEvent_t>>> ev;
+  cudaStream_t stream = nullptr;
+  const char* cat = "other";
+  void begin(const char* c) {
+    cat = c;
+    if (!on) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, stream);
+    ev.push_back({c, {a, b}});
+  }
+  void end() {
+    if (on && !ev.empty()) cudaEventRecord(ev.back().second.second, stream);
+  }
+  void report() {
+    if (!on) return;
+    cudaStreamSynchronize(stream);
+    std::vector<std::pair<std::string, std::pair<double, int>>> tot;
+    double all = 0;
+    for (auto& e : ev) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e.second.first, e.second.second);
+      cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second);
+      all += ms;
+      bool found = false;
+      for (auto& x : tot) if (x.first == e.first) { x.second.first += ms; x.second.second++; found = true; }
+      if (!found) tot.push_back({e.first, {ms, 1}});
+    }
+    fprintf(stderr, "[mmn wide timers] %.3f ms in %zu launches:", all, ev.size());
+    for (auto& x : tot) fprintf(stderr, " %s %.3f ms (%d)", x.first.c_str(), x.second.first, x.second.second);
+    fprintf(stderr, "\n");
+    ev.clear();
+  }
+};
+WideTimers g_wt;
 // D[M x N] = A[M x K] . B[N x K]^T
 int wide_gemm(int n_sms, const void* A, long long lda, const void* B, long long ldb, long long M, long long N, long long K,
-              const wide::Epi& epi, void* stream) {
+              const wide::Epi& epi, void* stream, const char* what = "gemm") {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   alignas(64) CUtensorMap ma, mb;
   if (make_operand_map(&ma, A, M, K, lda, wide::BM) || make_operand_map(&mb, B, N, K, ldb, wide::BN)) return 1;
@@ -294,7 +332,9 @@ int wide_gemm(int n_sms, const void* A, long long lda, const void* B, long long 
   }
   const long long tiles = ((M + wide::BM - 1) / wide::BM) * ((N + wide::BN - 1) / wide::BN);
   const int grid = (int)std::min<long long>(tiles, n_sms);
+  g_wt.begin(what);
   wide::mmn_wide_gemm_kernel<<<grid, wide::kThreads, wide::kSmemBytes, (cudaStream_t)stream>>>(ma, mb, (int)M, (int)N, (int)K, epi);
+  g_wt.end();
   MMN_CUDA(cudaGetLastError());
   ++g_wide_launches;
   return 0;
@@ -357,9 +397,12 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
   const int n_sms = plan->n_sms;
   Arena ar(dry ? nullptr : ws);
   bf16* const wbase = (bf16*)plan->wide_w;
-  const dim3 tb(32, 8);
-  auto tgrid = [&](long long rows, int width) { return dim3((unsigned)((width + 31) / 32), (unsigned)((rows + 31) / 32)); };
+  const dim3 tb(256);
+  auto tgrid = [&](long long rows, int width) { return dim3((unsigned)((width + 63) / 64), (unsigned)((rows + 63) / 64)); };
+  g_wt.on = !dry && getenv("MMN_WIDE_TIMERS") != nullptr;
+  g_wt.stream = stream;
   auto launched = [&]() -> int {
+    g_wt.end();
     ++g_wide_launches;
     MMN_CUDA(cudaGetLastError());
     return 0;
@@ -371,6 +414,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
   // ---- 0. bf16 copies of the weights (both orientations) ----
   if (!dry) {
     auto cast = [&](const DevLayer& l, const mmn_plan::WL& w) -> int {
+      g_wt.begin("cast_weight");
       wide_cast_weight_kernel<<<tgrid(l.out_dim, l.ktot), tb, 0, stream>>>(a.params + l.w_off, l.out_dim, l.ktot, wbase + w.w, w.ldk,
                                                                            wbase + w.wt, w.ldo);
       return launched();
@@ -408,6 +452,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
   if (!dry) {
     MMN_CUDA(cudaMemsetAsync(present, 1, (size_t)(L + 1) * B, stream));
     MMN_CUDA(cudaMemsetAsync(sc_sum, 0, sizeof(float) * (size_t)std::max(E, 1), stream));
+    g_wt.begin("init_state");
     wide_init_state_kernel<<<tgrid(B, S), tb, 0, stream>>>(a.params + P.init_off, B, Sk[0]);
     if (launched()) return 1;
   }
@@ -439,7 +484,16 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
         } else {
           e.out_f32 = Pout; e.ld_f32 = dec.C;
         }
-        if (!dry && wide_gemm(n_sms, in.p, in.ld, wbase + w.w, w.ldk, B, ly.out_dim, ly.ktot, e, stream)) return 1;
+        if (!dry) {
+          if (last && j > 0 && dec.C <= 4) {   // decoder head: skinny, bandwidth-bound kernel instead of a tensor-core tile
+            g_wt.begin("head_fwd");
+            wide_head_fwd_kernel<4><<<(unsigned)std::min<long long>((B + 7) / 8, 8 * n_sms), 256, 0, stream>>>(
+                in, wbase + w.w, w.ldk, a.params + ly.b_off, dec.C, ly.act, B, Pout);
+            if (launched()) return 1;
+          } else if (wide_gemm(n_sms, in.p, in.ld, wbase + w.w, w.ldk, B, ly.out_dim, ly.ktot, e, stream, "gemm fwd")) {
+            return 1;
+          }
+        }
         in = out;
       }
       LossArgs la;
@@ -460,6 +514,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
         if (TRAIN) {      // the pitch padding of dz is read by the TMA unit as part of full 16-byte rows: keep it finite
           MMN_CUDA(cudaMemsetAsync(la.dz.p, 0, (size_t)B * la.dz.ld * 2, stream));
         }
+        g_wt.begin("decoder_loss");
         wide_decoder_loss_kernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>(la);
         if (launched()) return 1;
       }
@@ -469,6 +524,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
 
   if (decoders_forward(0, 0, false, nullptr)) return 1;
   if (!dry) {
+    g_wt.begin("finalize");
     wide_finalize_kernel<<<1, 256, 0, stream>>>(present, B, 0, 0, 0, nullptr, nullptr, S, a.inv_rows_global,
                                                 a.metrics ? a.metrics + met_present(P, 0) : nullptr, nullptr, nullptr);
     if (launched()) return 1;
@@ -492,9 +548,11 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
     Mat in = ar.mat(B, enc.L[0].ktot);
     enc_in[(size_t)k * MMN_MAX_LAYERS + 0] = in;
     if (!dry) {
+      g_wt.begin("input_x");
       wide_input_x_kernel<<<tgrid(B, enc.F), tb, 0, stream>>>(a.x[pos], a.x_ld[pos], B, enc.F, in, pres, drop);
       if (launched()) return 1;
       if (enc.L[0].has_state) {
+        g_wt.begin("input_state");
         wide_input_state_kernel<<<tgrid(B, S), tb, 0, stream>>>(Sk[k - 1], B, in, enc.L[0].in_dim, drop);
         if (launched()) return 1;
       }
@@ -522,6 +580,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
       if (!dry) {
         if (wide_gemm(n_sms, in.p, in.ld, wbase + w.w, w.ldk, B, ly.out_dim, ly.ktot, ep, stream)) return 1;
         if (!last && enc.L[j + 1].has_state) {
+          g_wt.begin("input_state");
           wide_input_state_kernel<<<tgrid(B, S), tb, 0, stream>>>(Sk[k - 1], B, next, enc.L[j + 1].in_dim, nodrop);
           if (launched()) return 1;
         }
@@ -529,6 +588,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
       in = next;
     }
     if (!dry) {
+      g_wt.begin("finalize");
       wide_finalize_kernel<<<1, 256, 0, stream>>>(pres, B, k, e + 1, e, skip, TRAIN ? sc_sum + e : nullptr, S, a.inv_rows_global,
                                                   a.metrics ? a.metrics + met_present(P, 0) : nullptr,
                                                   (TRAIN && a.metrics) ? a.metrics + met_sc(P, 0) : nullptr,
@@ -539,6 +599,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
     if (!TRAIN) ar.off = scratch_mark;
   }
   if (a.final_state && !dry) {
+    g_wt.begin("state_out");
     wide_state_out_kernel<<<(unsigned)std::min<long long>((B * S + 255) / 256, 4096), 256, 0, stream>>>(Sk[L], B, a.final_state);
     if (launched()) return 1;
   }
@@ -559,12 +620,13 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
     // gradients of one layer given dz (both orientations) and the layer's input
     auto layer_param_grads = [&](const DevLayer& ly, const Mat& dz, const Mat& in) -> int {
       if (dry) return 0;
+      g_wt.begin("bias_grad");
       wide_bias_grad_kernel<<<ly.out_dim, 256, 0, stream>>>(dz.t, dz.ldt, B, a.grads + ly.b_off);
       if (launched()) return 1;
       Epi e = epi0();
       e.mode = EPI_ACCUM_F32; e.accumulate = 1;
       e.out_f32 = a.grads + ly.w_off; e.ld_f32 = ly.ktot;
-      return wide_gemm(n_sms, dz.t, dz.ldt, in.t, in.ldt, ly.out_dim, ly.ktot, B, e, stream);
+      return wide_gemm(n_sms, dz.t, dz.ldt, in.t, in.ldt, ly.out_dim, ly.ktot, B, e, stream, ly.out_dim < 64 ? "gemm dec-head wgrad" : "gemm wgrad");
     };
     auto decoders_backward = [&](int k) -> int {
       for (int d = 0; d < D; ++d) {
@@ -575,6 +637,21 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
           const DevLayer& ly = dec.L[j];
           const mmn_plan::WL& w = plan->wide_dec[d][j];
           const Mat in = j == 0 ? Sk[k] : dec_h[((size_t)k * D + d) * MMN_MAX_LAYERS + j - 1];
+          if (j == dec.n_layers - 1 && j > 0 && dec.C <= 4) {       // decoder head (see decoders_forward)
+            const Mat nz = view(dzbuf[cur], ly.in_dim);
+            if (!dry) {
+              g_wt.begin("head_wgrad");
+              wide_head_wgrad_kernel<4><<<dim3((unsigned)((ly.in_dim + 2047) / 2048), (unsigned)std::max<long long>(1, std::min<long long>(2 * n_sms, B / 32))),
+                                          256, 0, stream>>>(dz, in, dec.C, B, a.grads + ly.w_off, ly.ktot, a.grads + ly.b_off);
+              if (launched()) return 1;
+              g_wt.begin("head_dgrad");
+              wide_head_dgrad_kernel<<<tgrid(B, ly.in_dim), tb, 0, stream>>>(dz, wbase + w.w, w.ldk, dec.C, in, dec.L[j - 1].act, B, nz);
+              if (launched()) return 1;
+            }
+            dz = nz;
+            cur ^= 1;
+            continue;
+          }
           if (layer_param_grads(ly, dz, in)) return 1;
           Epi e = epi0();
           if (j > 0) {
@@ -582,7 +659,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
             e.mode = EPI_DACT; e.act = dec.L[j - 1].act;
             e.aux = in.p; e.ld_aux = in.ld;
             e.out = nz.p; e.ld_out = nz.ld; e.out_t = nz.t; e.ld_out_t = nz.ldt;
-            if (!dry && wide_gemm(n_sms, dz.p, dz.ld, wbase + w.wt, w.ldo, B, ly.in_dim, ly.out_dim, e, stream)) return 1;
+            if (!dry && wide_gemm(n_sms, dz.p, dz.ld, wbase + w.wt, w.ldo, B, ly.in_dim, ly.out_dim, e, stream, ly.out_dim < 64 ? "gemm dec-head dgrad" : "gemm dgrad")) return 1;
             dz = nz;
             cur ^= 1;
           } else {
@@ -605,6 +682,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
       Mat dz = view(dzbuf[cur], S);
       cur ^= 1;
       if (!dry) {
+        g_wt.begin("state_grad");
         wide_state_grad_kernel<<<tgrid(B, S), tb, 0, stream>>>(G, Sk[k], Sk[k - 1], pres, skip, a.c_sc, enc.L[nl - 1].act, B, dz);
         if (launched()) return 1;
       }
@@ -627,6 +705,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
             ep.scale = 1.f / (1.f - enc.p_drop);
           }
           if (wide_gemm(n_sms, dz.p, dz.ld, wbase + w.wt + (long long)ly.in_dim * w.ldo, w.ldo, B, S, ly.out_dim, ep, stream)) return 1;
+          g_wt.begin("state_grad_post");
           wide_state_grad_post_kernel<<<(unsigned)std::min<long long>((B * S + 255) / 256, 4096), 256, 0, stream>>>(G, Sk[k], Sk[k - 1],
                                                                                                                    a.c_sc, B);
           if (launched()) return 1;
@@ -645,10 +724,12 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
     }
     if (decoders_backward(0)) return 1;
     if (!dry) {
+      g_wt.begin("colsum_f32");
       wide_colsum_f32_kernel<<<dim3((unsigned)((S + 31) / 32), 16), 256, 0, stream>>>(G, B, S, a.grads + P.init_off);
       if (launched()) return 1;
     }
   }
+  g_wt.report();
   if (need_out) *need_out = ar.peak + 256;
   if (!dry && ar.peak > ws_bytes) return fail("wide regime: workspace too small (need %zu bytes, got %zu)", ar.peak, ws_bytes);
   return 0;

@@ -1120,22 +1120,57 @@ __global__ void __launch_bounds__(256) mmn_adam_kernel(const DevPlan* plan, floa
                                                         float* m, float* v, const int* step_count, float lr,
                                                         float b1, float b2, float eps) {
   const DevPlan& P = *plan;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n_params;
-       i += (long long)gridDim.x * blockDim.x) {
+  // per-owner constants (owner 0 = decoders + initial state, owner e + 1 = encoder e): bias corrections in double as
+  // torch.optim.Adam computes them, once per block instead of once per element
+  __shared__ float s_step[MMN_MAX_ENCODERS + 1], s_sqrt_bc2[MMN_MAX_ENCODERS + 1];
+  __shared__ int s_live[MMN_MAX_ENCODERS + 1];
+  if ((int)threadIdx.x <= P.E) {
+    const int owner = threadIdx.x;
+    const int t = step_count[owner];
+    const double bc1 = 1.0 - pow((double)b1, (double)t), bc2 = 1.0 - pow((double)b2, (double)t);
+    s_step[owner] = (float)((double)lr / bc1);
+    s_sqrt_bc2[owner] = (float)sqrt(bc2);
+    s_live[owner] = owner == 0 || grads[P.n_params + owner - 1] > 0.f;    // `.grad is None`: untouched
+  }
+  __syncthreads();
+  auto owner_of = [&](long long i) {
     int owner = 0;
     for (int e = 0; e < P.E; ++e)
       if (i >= P.enc[e].param_lo && i < P.enc[e].param_hi) owner = e + 1;
-    if (owner && !(grads[P.n_params + owner - 1] > 0.f)) continue;    // `.grad is None`: untouched
-    const int t = step_count[owner];
-    const float g = grads[i];
-    const float mi = m[i] + (g - m[i]) * (1.f - b1);
-    const float vi = v[i] * b2 + g * g * (1.f - b2);
-    m[i] = mi;
-    v[i] = vi;
-    const double bc1 = 1.0 - pow((double)b1, (double)t), bc2 = 1.0 - pow((double)b2, (double)t);
-    const float step_size = (float)((double)lr / bc1);
-    const float denom = sqrtf(vi) / (float)sqrt(bc2) + eps;
-    params[i] = params[i] - step_size * (mi / denom);
+    return owner;
+  };
+  auto update = [&](float& p, float g, float& mi, float& vi, int owner) {
+    mi = mi + (g - mi) * (1.f - b1);
+    vi = vi * b2 + g * g * (1.f - b2);
+    const float denom = sqrtf(vi) / s_sqrt_bc2[owner] + eps;
+    p = p - s_step[owner] * (mi / denom);
+  };
+  // blocks of four: parameter blocks start on multiples of four floats, so a quad never spans two owners
+  // (the floats between a block's end and the next multiple of four are padding with zero gradient)
+  const long long n4 = P.n_params >> 2;
+  const bool vec = (((size_t)params | (size_t)grads | (size_t)m | (size_t)v) & 15) == 0;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  if (vec) {
+    for (long long q = tid; q < n4; q += stride) {
+      const int owner = owner_of(q << 2);
+      if (!s_live[owner]) continue;
+      float4 p4 = reinterpret_cast<float4*>(params)[q], m4 = reinterpret_cast<float4*>(m)[q], v4 = reinterpret_cast<float4*>(v)[q];
+      const float4 g4 = reinterpret_cast<const float4*>(grads)[q];
+      update(p4.x, g4.x, m4.x, v4.x, owner);
+      update(p4.y, g4.y, m4.y, v4.y, owner);
+      update(p4.z, g4.z, m4.z, v4.z, owner);
+      update(p4.w, g4.w, m4.w, v4.w, owner);
+      reinterpret_cast<float4*>(params)[q] = p4;
+      reinterpret_cast<float4*>(m)[q] = m4;
+      reinterpret_cast<float4*>(v)[q] = v4;
+    }
+  }
+  for (long long i = (vec ? (n4 << 2) : 0) + tid; i < P.n_params; i += stride) {
+    const int owner = owner_of(i);
+    if (!s_live[owner]) continue;
+    float pi = params[i], mi = m[i], vi = v[i];
+    update(pi, grads[i], mi, vi, owner);
+    params[i] = pi; m[i] = mi; v[i] = vi;
   }
 }
 

@@ -24,71 +24,147 @@ struct Mat {             // one [rows x width] bf16 matrix in both orientations
   int width;
 };
 
-// 32 x 32 tile: value(r, c) computed once per element, written row-major and (through shared memory) transposed
-template <typename F>
-__device__ __forceinline__ void tile32_emit(F value, long long rows, int width, bf16* dst, long long ld, bf16* dst_t, long long ldt,
-                                            int colofs) {
-  __shared__ float tile[32][33];
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const long long r0 = (long long)blockIdx.y * 32;
-  const int c0 = blockIdx.x * 32;
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const long long r = r0 + ty + 8 * i;
-    const int c = c0 + tx;
-    float v = 0.f;
-    if (r < rows && c < width) {
-      v = value(r, c);
-      if (dst) dst[r * ld + colofs + c] = __float2bfloat16(v);
+  for (int i = 0; i < 4; ++i) { const float2 x = __bfloat1622float2(hp[i]); f[2 * i] = x.x; f[2 * i + 1] = x.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) hp[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+__device__ __forceinline__ void load8(const bf16* p, int n_valid, float (&f)[8]) {      // 8 bf16, zero beyond n_valid
+  if (n_valid >= 8 && (reinterpret_cast<size_t>(p) & 15) == 0) {
+    unpack8(*reinterpret_cast<const uint4*>(p), f);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = i < n_valid ? __bfloat162float(p[i]) : 0.f;
+  }
+}
+__device__ __forceinline__ void load8(const float* p, int n_valid, float (&f)[8]) {     // 8 fp32, zero beyond n_valid
+  if (n_valid >= 8 && (reinterpret_cast<size_t>(p) & 15) == 0) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = i < n_valid ? p[i] : 0.f;
+  }
+}
+
+// 64 x 64 tile written in both orientations with 16-byte accesses: value8(r, c, n_valid, v) fills the 8 values of row r,
+// columns c .. c+7 (n_valid of them exist) exactly once; they are stored row-major and, through shared memory, transposed.
+// Launch: 256 threads, grid (ceil(width / 64), ceil(rows / 64)).
+template <typename F>
+__device__ __forceinline__ void tile64_emit(F value8, long long rows, int width, bf16* dst, long long ld, bf16* dst_t, long long ldt,
+                                            int colofs) {
+  __shared__ __align__(16) bf16 tile[64][72];
+  const int t = threadIdx.x;
+  const long long r0 = (long long)blockIdx.y * 64;
+  const int c0 = blockIdx.x * 64;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int rr = (t >> 3) + 32 * i, cc = (t & 7) * 8;
+    const long long r = r0 + rr;
+    const int c = c0 + cc;
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = 0.f;
+    const int nv = min(8, width - c);
+    if (r < rows && nv > 0) value8(r, c, nv, v);
+    const uint4 pk = pack8(v);
+    if (dst && r < rows && nv > 0) {
+      bf16* op = dst + r * ld + colofs + c;
+      if (nv == 8 && (reinterpret_cast<size_t>(op) & 15) == 0) {
+        *reinterpret_cast<uint4*>(op) = pk;
+      } else {
+        const bf16* pv = reinterpret_cast<const bf16*>(&pk);
+        for (int u = 0; u < nv; ++u) op[u] = pv[u];
+      }
     }
-    tile[ty + 8 * i][tx] = v;
+    *reinterpret_cast<uint4*>(&tile[rr][cc]) = pk;
   }
   __syncthreads();
   if (dst_t) {
+    const int kk = t >> 2, rc = (t & 3) * 16;
+    const int c = c0 + kk;
+    const long long r = r0 + rc;
+    if (c < width && r < rows) {
+      __align__(16) bf16 col[16];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int c = c0 + ty + 8 * i;
-      const long long r = r0 + tx;
-      if (r < rows && c < width) dst_t[(long long)(colofs + c) * ldt + r] = __float2bfloat16(tile[tx][ty + 8 * i]);
+      for (int j = 0; j < 16; ++j) col[j] = tile[rc + j][kk];
+      bf16* op = dst_t + (long long)(colofs + c) * ldt + r;
+      if (r + 16 <= rows && (reinterpret_cast<size_t>(op) & 15) == 0) {
+        reinterpret_cast<uint4*>(op)[0] = reinterpret_cast<const uint4*>(col)[0];
+        reinterpret_cast<uint4*>(op)[1] = reinterpret_cast<const uint4*>(col)[1];
+      } else {
+        for (int j = 0; j < 16 && r + j < rows; ++j) op[j] = col[j];
+      }
     }
   }
 }
 
 // fp32 master weight [out x ktot] -> bf16 W (pitch ldk) and W^T [ktot x out] (pitch ldo)
-__global__ void wide_cast_weight_kernel(const float* __restrict__ W, int out, int ktot, bf16* Wb, long long ldk, bf16* WbT, long long ldo) {
-  tile32_emit([&](long long r, int c) { return W[r * ktot + c]; }, out, ktot, Wb, ldk, WbT, ldo, 0);
+__global__ void __launch_bounds__(256) wide_cast_weight_kernel(const float* __restrict__ W, int out, int ktot, bf16* Wb, long long ldk,
+                                                               bf16* WbT, long long ldo) {
+  tile64_emit([&](long long r, int c, int nv, float (&v)[8]) { load8(W + r * ktot + c, nv, v); }, out, ktot, Wb, ldk, WbT, ldo, 0);
 }
 // features of one modality -> columns [0, F) of the first layer's input; NaN -> 0 and the row is marked absent
-__global__ void wide_input_x_kernel(const float* __restrict__ x, long long x_ld, long long rows, int F, Mat in, unsigned char* present,
-                                    Drop drop) {
-  tile32_emit([&](long long r, int c) {
-    float v = x[r * x_ld + c];
-    if (v != v) { present[r] = 0; v = 0.f; }
-    if (drop.enabled) v = mmn_dropout_keep(drop.seed_mix, drop.row_base + (unsigned)r, (unsigned)c, drop.thr) ? v * drop.scale : 0.f;
-    return v;
+__global__ void __launch_bounds__(256) wide_input_x_kernel(const float* __restrict__ x, long long x_ld, long long rows, int F, Mat in,
+                                                           unsigned char* present, Drop drop) {
+  tile64_emit([&](long long r, int c, int nv, float (&v)[8]) {
+    load8(x + r * x_ld + c, nv, v);
+    bool nan = false;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (v[i] != v[i]) { nan = true; v[i] = 0.f; }
+    if (nan) present[r] = 0;
+    if (drop.enabled) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        v[i] = mmn_dropout_keep(drop.seed_mix, drop.row_base + (unsigned)r, (unsigned)(c + i), drop.thr) ? v[i] * drop.scale : 0.f;
+    }
   }, rows, F, in.p, in.ld, in.t, in.ldt, 0);
 }
 // the running state -> columns [colofs, colofs + S) of a layer input (torch.cat([x, state]), mlp_encoder.py:41,78)
-__global__ void wide_input_state_kernel(Mat s, long long rows, Mat in, int colofs, Drop drop) {
-  tile32_emit([&](long long r, int c) {
-    float v = __bfloat162float(s.p[r * s.ld + c]);
-    if (drop.enabled) v = mmn_dropout_keep(drop.seed_mix, drop.row_base + (unsigned)r, (unsigned)(colofs + c), drop.thr) ? v * drop.scale : 0.f;
-    return v;
+__global__ void __launch_bounds__(256) wide_input_state_kernel(Mat s, long long rows, Mat in, int colofs, Drop drop) {
+  tile64_emit([&](long long r, int c, int nv, float (&v)[8]) {
+    load8(s.p + r * s.ld + c, nv, v);
+    if (drop.enabled) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        v[i] = mmn_dropout_keep(drop.seed_mix, drop.row_base + (unsigned)r, (unsigned)(colofs + c + i), drop.thr) ? v[i] * drop.scale : 0.f;
+    }
   }, rows, s.width, in.p, in.ld, in.t, in.ldt, colofs);
 }
 // s_0 = tile(state_value) (state.py:29-32)
-__global__ void wide_init_state_kernel(const float* __restrict__ init, long long rows, Mat s) {
-  tile32_emit([&](long long, int c) { return init[c]; }, rows, s.width, s.p, s.ld, s.t, s.ldt, 0);
+__global__ void __launch_bounds__(256) wide_init_state_kernel(const float* __restrict__ init, long long rows, Mat s) {
+  tile64_emit([&](long long, int c, int nv, float (&v)[8]) { load8(init + c, nv, v); }, rows, s.width, s.p, s.ld, s.t, s.ldt, 0);
 }
 // G += u_k ; dz = present ? G * act'(s_k) : 0      (u_k = c_sc (s_k - s_{k-1}))
-__global__ void wide_state_grad_kernel(float* G, Mat sk, Mat skm1, const unsigned char* present, const int* skip, float c_sc, int act,
-                                       long long rows, Mat dz) {
+__global__ void __launch_bounds__(256) wide_state_grad_kernel(float* G, Mat sk, Mat skm1, const unsigned char* present, const int* skip,
+                                                              float c_sc, int act, long long rows, Mat dz) {
   const bool skipped = skip && *skip != 0;
-  tile32_emit([&](long long r, int c) {
-    const float a = __bfloat162float(sk.p[r * sk.ld + c]), b = __bfloat162float(skm1.p[r * skm1.ld + c]);
-    const float g = G[r * sk.width + c] + c_sc * (a - b);
-    G[r * sk.width + c] = g;
-    return (present[r] && !skipped) ? g * wide_dact(act, a) : 0.f;
+  tile64_emit([&](long long r, int c, int nv, float (&v)[8]) {
+    float a[8], b[8], g[8];
+    load8(sk.p + r * sk.ld + c, nv, a);
+    load8(skm1.p + r * skm1.ld + c, nv, b);
+    float* gp = G + r * sk.width + c;
+    load8(gp, nv, g);
+    const bool live = present[r] && !skipped;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      g[i] += c_sc * (a[i] - b[i]);
+      v[i] = live ? g[i] * wide_dact(act, a[i]) : 0.f;
+    }
+    if (nv == 8 && (reinterpret_cast<size_t>(gp) & 15) == 0) {
+      reinterpret_cast<float4*>(gp)[0] = make_float4(g[0], g[1], g[2], g[3]);
+      reinterpret_cast<float4*>(gp)[1] = make_float4(g[4], g[5], g[6], g[7]);
+    } else {
+      for (int i = 0; i < nv; ++i) gp[i] = g[i];
+    }
   }, rows, sk.width, dz.p, dz.ld, dz.t, dz.ldt, 0);
 }
 // G -= u_k (the state-change term reaches s_{k-1} with the opposite sign)
@@ -138,6 +214,99 @@ __global__ void wide_state_out_kernel(Mat s, long long rows, float* out) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / s.width;
     out[i] = __bfloat162float(s.p[r * s.ld + (i - r * s.width)]);
+  }
+}
+
+
+// ---- decoder head: the last Linear of an MLP decoder (out = n_classes <= 32) is far too skinny for a 128 x 256 tensor-core
+// tile; three bandwidth-bound kernels replace its forward / data-gradient / weight-gradient GEMMs ----
+// p[r][c] = act(b[c] + sum_k h[r][k] W[c][k])       one warp per row, fp32 accumulation of bf16 products
+template <int CMAX>
+__global__ void __launch_bounds__(256) wide_head_fwd_kernel(Mat h, const bf16* __restrict__ Wb, long long ldk, const float* __restrict__ bias,
+                                                            int C, int act, long long rows, float* __restrict__ p_out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long r = (long long)blockIdx.x * 8 + warp; r < rows; r += (long long)gridDim.x * 8) {
+    float acc[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) acc[c] = 0.f;
+    const bf16* hr = h.p + r * h.ld;
+#pragma unroll 4
+    for (int k0 = lane * 8; k0 < h.width; k0 += 256) {
+      float hv[8];
+      load8(hr + k0, h.width - k0, hv);
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        if (c < C) {
+          float wv[8];
+          load8(Wb + (long long)c * ldk + k0, h.width - k0, wv);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[c] = fmaf(hv[i], wv[i], acc[c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      if (c < C) {
+        float s = acc[c];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) p_out[r * C + c] = wide_act(act, s + bias[c]);
+      }
+    }
+  }
+}
+// dh[r][k] = act'(h[r][k]) * sum_c dz[r][c] W[c][k]       (both orientations)
+__global__ void __launch_bounds__(256) wide_head_dgrad_kernel(Mat dz, const bf16* __restrict__ Wb, long long ldk, int C, Mat h,
+                                                              int act_prev, long long rows, Mat out) {
+  tile64_emit([&](long long r, int k, int nv, float (&v)[8]) {
+    float hv[8];
+    load8(h.p + r * h.ld + k, nv, hv);
+    for (int c = 0; c < C; ++c) {
+      float wv[8];
+      load8(Wb + (long long)c * ldk + k, nv, wv);
+      const float d = __bfloat162float(dz.p[r * dz.ld + c]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaf(d, wv[i], v[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= wide_dact(act_prev, hv[i]);
+  }, rows, h.width, out.p, out.ld, out.t, out.ldt, 0);
+}
+// dW[c][k] += sum_r dz[r][c] h[r][k],  db[c] += sum_r dz[r][c]       thread = 8 consecutive k, blockIdx.y = a slice of the rows
+template <int CMAX>
+__global__ void __launch_bounds__(256) wide_head_wgrad_kernel(Mat dz, Mat h, int C, long long rows, float* gW, long long ldw, float* gb) {
+  const int k0 = (blockIdx.x * 256 + threadIdx.x) * 8;
+  const long long per = (rows + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+  float acc[CMAX][8];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[c][i] = 0.f;
+  if (k0 < h.width) {
+#pragma unroll 4
+    for (long long r = r0; r < r1; ++r) {
+      float hv[8];
+      load8(h.p + r * h.ld + k0, h.width - k0, hv);
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        if (c < C) {
+          const float d = __bfloat162float(dz.p[r * dz.ld + c]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[c][i] = fmaf(d, hv[i], acc[c][i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (k0 + i < h.width && acc[c][i] != 0.f) atomicAdd(gW + (long long)c * ldw + k0 + i, acc[c][i]);
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < C) {
+    float s = 0.f;
+    for (long long r = r0; r < r1; ++r) s += __bfloat162float(dz.p[r * dz.ld + threadIdx.x]);
+    if (s != 0.f) atomicAdd(gb + threadIdx.x, s);
   }
 }
 

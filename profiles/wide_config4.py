@@ -52,3 +52,7 @@ fwd = lambda i: model.predict(bs[i % 2][0])
 fwd(0)
 ms_f = timed(fwd, 5)
 print(f"C4 predict: {ms_f:.3f} ms per predict() of {B} rows incl. D2H of the class ids, {B / ms_f / 1e3:.3f} M rows/s")
+if os.environ.get("MMN_WIDE_TIMERS_ONCE"):
+    os.environ["MMN_WIDE_TIMERS"] = "1"
+    step(0)
+    torch.cuda.synchronize()

@@ -30,6 +30,7 @@
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
 #define __launch_bounds__(...)
+#define __shared__ static        // blocks run one after another, the threads of a block are fibers of one OS thread
 #define __restrict__ __restrict
 
 struct dim3 {
