@@ -34,8 +34,17 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 # DRAM bytes of ONE launch of the step kernel at B = 65536 (ncu --set full; profiles/)
 DRAM_TRAFFIC_PER_LAUNCH = {"fp32-fma": 706.1e6 + 251.8e6, "tcgen05-3xtf32": 701.6e6 + 238.2e6}
 
-WORKLOAD = dict(name="c2_mimic", S=64, features=[6, 99, 1024], enc_hidden=(32, 32), n_decoders=2,
-                dec_hidden=(32, 32), dropout=0.2, err_penalty=1.0, state_change_penalty=0.3, lr=1e-3)
+WORKLOADS = {
+    # BASELINE.json configs[1] — the configuration the metric is quoted on (default)
+    "c2_mimic": dict(name="c2_mimic", S=64, features=[6, 99, 1024], enc_hidden=(32, 32), n_decoders=2,
+                     dec_hidden=(32, 32), dropout=0.2, err_penalty=1.0, state_change_penalty=0.3, lr=1e-3,
+                     precision="fp32", batch=65536, ref_batch=8192),
+    # BASELINE.json configs[3] — the wide regime: layer-wise tcgen05 bf16 GEMMs (--workload c4_wide)
+    "c4_wide": dict(name="c4_wide", S=1024, features=[1024, 1024, 768, 768], enc_hidden=(2048, 2048), n_decoders=2,
+                    dec_hidden=(2048,), dropout=0.0, err_penalty=1.0, state_change_penalty=0.3, lr=1e-4,
+                    precision="bf16", batch=8192, ref_batch=512),
+}
+WORKLOAD = WORKLOADS["c2_mimic"]
 
 
 def macs_per_row(w):
@@ -140,7 +149,7 @@ def cpu_port_rate(steps, warmup, B):
 def workload_config(B, world, **extra):
     w = WORKLOAD
     cfg = dict(workload=w["name"], state_size=w["S"], features=w["features"], enc_hidden=list(w["enc_hidden"]),
-               decoders=w["n_decoders"], dec_hidden=list(w["dec_hidden"]), dropout=w["dropout"],
+               decoders=w["n_decoders"], dec_hidden=list(w["dec_hidden"]), dropout=w["dropout"], precision=w["precision"],
                batch_per_gpu=B, global_batch=B * world, missing_mode="row", parallelism=f"dp{world}")
     cfg.update(extra)
     return cfg
@@ -172,11 +181,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=65536, help="rows per GPU per step")
-    ap.add_argument("--ref-batch", type=int, default=8192, help="rows per step of the CPU arm")
+    ap.add_argument("--workload", default="c2_mimic", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="rows per GPU per step (default: the workload's)")
+    ap.add_argument("--ref-batch", type=int, default=None, help="rows per step of the CPU arm")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = WORKLOADS[args.workload]
+    args.batch = args.batch or WORKLOAD["batch"]
+    args.ref_batch = args.ref_batch or WORKLOAD["ref_batch"]
     if args.impl == "reference":
         return run_reference(args)
 
@@ -199,7 +213,7 @@ def main():
     w = WORKLOAD
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
     torch.manual_seed(1)
-    model = model_from_spec(make_spec(), w["err_penalty"], w["state_change_penalty"], dev, "row")
+    model = model_from_spec(make_spec(), w["err_penalty"], w["state_change_penalty"], dev, "row", precision=w["precision"])
     if world > 1:
         model.enable_data_parallel()
     opt = FusedAdam(model, lr=w["lr"])
@@ -254,13 +268,16 @@ def main():
 
     for i in range(3):
         kernel_only(i)
+    wide_l0 = int(rt.lib.dll.mmn_wide_launch_count())
     kms = timed(kernel_only, K) / K
+    wide_launches_per_step = (int(rt.lib.dll.mmn_wide_launch_count()) - wide_l0) // K
     for _ in range(3):                                # keep the load on while nvidia-smi gets a few samples in
         timed(kernel_only, K)
     clk.__exit__()
     clocks = clk.summary()
     peaks, peak_kind = measured_peaks()
-    engine = {0: "fp32-fma", 1: "tcgen05-3xtf32", 2: "tcgen05-3xtf32-tmem"}[int(rt.lib.dll.mmn_plan_engine(rt.plan))]
+    engine = {0: "fp32-fma", 1: "tcgen05-3xtf32", 2: "tcgen05-3xtf32-tmem", 3: "tcgen05-bf16-layerwise"}[
+        int(rt.lib.dll.mmn_plan_engine(rt.plan))]
     macs = macs_per_row(w)
     alg_bytes = B * (2 * 4 * sum(w["features"]) + 8 * w["n_decoders"])   # x read in fwd and again for wgrad
     achieved = alg_bytes / (kms * 1e-3) / 1e9
@@ -274,6 +291,17 @@ def main():
                     fp32_fma=dict(achieved_tflops=flops / (kms * 1e-3) / 1e12, peak_tflops_nominal=fma_peak,
                                   frac=flops / (kms * 1e-3) / 1e12 / fma_peak,
                                   note="fp32 parity mode is FP32-FMA-bound, not HBM-bound (SURVEY.md 8d)"))
+
+    if w["precision"] == "bf16":
+        # the wide regime is tensor-pipe-bound: achieved = algorithmic FLOPs of one step (6 x MACs) over
+        # the duration of the step's launches (GEMMs + their elementwise companions); peak = the measured SUSTAINED
+        # dense bf16 throughput, because the launches are timed inside a long step
+        tf = flops / (kms * 1e-3) / 1e12
+        peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        roofline = dict(bound="tensor", achieved=tf, peak=peak_tf, unit="TFLOP/s", frac=tf / peak_tf, traffic=None,
+                        kernel="mmn_wide_gemm_kernel (+ elementwise companions) x %d launches per step" % wide_launches_per_step,
+                        kernel_ms=kms, peak_source=peak_kind, algorithmic_flops_per_sample=6.0 * macs,
+                        hbm=dict(achieved_gbs=achieved, peak_gbs=peaks["hbm_gbs"], frac=achieved / peaks["hbm_gbs"]))
 
     # ---- e2e: the public call on a loader of pinned HOST batches: every step copies its inputs H2D (one batch
     #      ahead, on a side stream) and reads its loss metrics back D2H (log_interval=1) ----------------------
@@ -315,11 +343,13 @@ def main():
 
     if rank == 0:
         line = dict(metric="train samples/sec", value=value, unit="samples/s", n_gpus=world, steps=K, warmup=W,
-                    ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fp32",
+                    ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype=w["precision"],
                     data="synthetic",
                     config=workload_config(B, world, optimizer="FusedAdam", engine=engine,
                                            l2_policy=f"{n_resident} resident batches of {bytes_in / 1e6:.0f} MB each (> 126 MB L2), cycled"),
-                    clocks=clocks, e2e=e2e, gpu_launches=3 * K, roofline=roofline, cpu_baseline=cpu)
+                    clocks=clocks, e2e=e2e,
+                    gpu_launches=(wide_launches_per_step + 2) * K if w["precision"] == "bf16" else 3 * K,
+                    roofline=roofline, cpu_baseline=cpu)
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

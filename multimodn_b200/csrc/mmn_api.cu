@@ -354,13 +354,14 @@ struct Arena {
     peak = std::max(peak, off);
     return p;
   }
+  bool want_t = true;        // forward-only calls need no transposed copies (they only feed weight gradients)
   wide::Mat mat(long long rows, int width) {
     wide::Mat m;
     m.width = width;
     m.ld = round8(width);
     m.ldt = round8(rows);
     m.p = (wide::bf16*)take((size_t)rows * m.ld * 2);
-    m.t = (wide::bf16*)take((size_t)width * m.ldt * 2);
+    m.t = want_t ? (wide::bf16*)take((size_t)width * m.ldt * 2) : nullptr;
     return m;
   }
 };
@@ -396,6 +397,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
   const int S = P.S, E = P.E, D = P.D, L = a.seq_len;
   const int n_sms = plan->n_sms;
   Arena ar(dry ? nullptr : ws);
+  ar.want_t = TRAIN;
   bf16* const wbase = (bf16*)plan->wide_w;
   const dim3 tb(256);
   auto tgrid = [&](long long rows, int width) { return dim3((unsigned)((width + 63) / 64), (unsigned)((rows + 63) / 64)); };
@@ -621,7 +623,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
     auto layer_param_grads = [&](const DevLayer& ly, const Mat& dz, const Mat& in) -> int {
       if (dry) return 0;
       g_wt.begin("bias_grad");
-      wide_bias_grad_kernel<<<ly.out_dim, 256, 0, stream>>>(dz.t, dz.ldt, B, a.grads + ly.b_off);
+      wide_bias_grad_kernel<<<(ly.out_dim + 1) / 2, 256, 0, stream>>>(dz.t, dz.ldt, B, ly.out_dim, a.grads + ly.b_off);
       if (launched()) return 1;
       Epi e = epi0();
       e.mode = EPI_ACCUM_F32; e.accumulate = 1;

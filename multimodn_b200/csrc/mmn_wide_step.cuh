@@ -176,21 +176,27 @@ __global__ void wide_state_grad_post_kernel(float* G, Mat sk, Mat skm1, float c_
     G[i] -= c_sc * (__bfloat162float(sk.p[r * sk.ld + c]) - __bfloat162float(skm1.p[r * skm1.ld + c]));
   }
 }
-// bias gradient: gb[n] += sum_r dz^T[n][r]          (one CTA per output)
-__global__ void wide_bias_grad_kernel(const bf16* __restrict__ dzt, long long ldt, long long rows, float* gb) {
+// bias gradient: gb[n] += sum_r dz^T[n][r]          (two outputs per CTA, four warps each, 16-byte loads)
+__global__ void __launch_bounds__(256) wide_bias_grad_kernel(const bf16* __restrict__ dzt, long long ldt, long long rows, int n_out, float* gb) {
   __shared__ float red[8];
-  const bf16* row = dzt + (long long)blockIdx.x * ldt;
+  const int half = threadIdx.x >> 7, t = threadIdx.x & 127;
+  const int n = blockIdx.x * 2 + half;
   float s = 0.f;
-  for (long long r = threadIdx.x; r < rows; r += blockDim.x) s += __bfloat162float(row[r]);
+  if (n < n_out) {
+    const bf16* row = dzt + (long long)n * ldt;
+#pragma unroll 4
+    for (long long r = t * 8; r < rows; r += 1024) {
+      float v[8];
+      load8(row + r, (int)min((long long)8, rows - r), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += v[i];
+    }
+  }
 #pragma unroll
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float tot = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
-    atomicAdd(gb + blockIdx.x, tot);
-  }
+  if (t == 0 && n < n_out) atomicAdd(gb + n, red[4 * half] + red[4 * half + 1] + red[4 * half + 2] + red[4 * half + 3]);
 }
 // column sums of the fp32 state gradient -> gradient of state_value (tile backward, state.py:30)
 __global__ void wide_colsum_f32_kernel(const float* __restrict__ G, long long rows, int S, float* out) {
