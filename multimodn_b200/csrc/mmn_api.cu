@@ -331,9 +331,17 @@ int wide_gemm(int n_sms, const void* A, long long lda, const void* B, long long 
     attr_set = true;
   }
   const long long tiles = ((M + wide::BM - 1) / wide::BM) * ((N + wide::BN - 1) / wide::BN);
-  const int grid = (int)std::min<long long>(tiles, n_sms);
+  // split-K: only for accumulating fp32 outputs (weight gradients), when the output tiles alone leave SMs idle and
+  // every split still has a long K range
+  int splits = 1;
+  if (epi.mode == wide::EPI_ACCUM_F32 && epi.accumulate && !epi.out && !epi.out_t && tiles < n_sms) {
+    const long long kb = (K + wide::BK - 1) / wide::BK;
+    splits = (int)std::max<long long>(1, std::min<long long>(std::min<long long>((2 * n_sms) / tiles, kb / 16), 16));
+    while (splits > 1 && (long long)(splits - 1) * ((kb + splits - 1) / splits) >= kb) --splits;     // no empty split
+  }
+  const int grid = (int)std::min<long long>(tiles * splits, n_sms);
   g_wt.begin(what);
-  wide::mmn_wide_gemm_kernel<<<grid, wide::kThreads, wide::kSmemBytes, (cudaStream_t)stream>>>(ma, mb, (int)M, (int)N, (int)K, epi);
+  wide::mmn_wide_gemm_kernel<<<grid, wide::kThreads, wide::kSmemBytes, (cudaStream_t)stream>>>(ma, mb, (int)M, (int)N, (int)K, splits, epi);
   g_wt.end();
   MMN_CUDA(cudaGetLastError());
   ++g_wide_launches;

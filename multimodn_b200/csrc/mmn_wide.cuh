@@ -103,7 +103,7 @@ __device__ __forceinline__ float wide_dact(int act, float a) {      // derivativ
 
 __global__ void __launch_bounds__(kThreads, 1)
 mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N, int K,
-                     const Epi epi) {
+                     int splits, const Epi epi) {
   extern __shared__ __align__(1024) char smem_raw[];
   char* base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
   unsigned long long* full = reinterpret_cast<unsigned long long*>(base + STAGES * kStageBytes);
@@ -113,8 +113,11 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   unsigned* tslot = reinterpret_cast<unsigned*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN, n_tiles = tiles_m * tiles_n;
-  const int kb_n = (K + BK - 1) / BK;
+  // work item = (output tile, K split): split-K fills the machine when a long contraction has few output tiles (weight
+  // gradients); its partial sums are added with fp32 atomics (EPI_ACCUM_F32 only)
+  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN, n_out_tiles = tiles_m * tiles_n;
+  const int n_tiles = n_out_tiles * splits;
+  const int kb_all = (K + BK - 1) / BK, kb_per = (kb_all + splits - 1) / splits;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
@@ -133,9 +136,11 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // ===== TMA producer =====
     if (elect_one()) {
       Pipe p{0, 0};
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < n_tiles; item += gridDim.x) {
+        const int tile = item % n_out_tiles, split = item / n_out_tiles;
         const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
-        for (int kb = 0; kb < kb_n; ++kb) {
+        const int kb0 = split * kb_per, kb1 = min(kb_all, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty + p.stage, p.phase ^ 1u);
           char* sa = base + p.stage * kStageBytes;
           mbar_expect_tx(full + p.stage, kStageBytes);
@@ -153,11 +158,17 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     Pipe p{0, 0};
     unsigned acc_phase[2] = {0u, 0u};
     int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < n_tiles; item += gridDim.x, ++it) {
       const int acc = it & 1;
+      const int kb_n = min(kb_all, (item / n_out_tiles) * kb_per + kb_per) - (item / n_out_tiles) * kb_per;
       mbar_wait(acc_empty + acc, acc_phase[acc] ^ 1u);
       acc_phase[acc] ^= 1u;
       tc_fence_after();
+      if (kb_n <= 0) {               // empty K range (cannot happen for splits <= kb_all; keep the pipeline consistent)
+        if (leader) umma_commit(acc_full + acc);
+        __syncwarp();
+        continue;
+      }
       for (int kb = 0; kb < kb_n; ++kb) {
         mbar_wait(full + p.stage, p.phase);
         tc_fence_after();
@@ -180,8 +191,9 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     unsigned acc_phase[2] = {0u, 0u};
     int it = 0;
     float sc = 0.f;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < n_tiles; item += gridDim.x, ++it) {
       const int acc = it & 1;
+      const int tile = item % n_out_tiles;
       const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
       const int r = m0 + 32 * q + lane;
       const bool rv = r < M;
@@ -278,6 +290,15 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 #pragma unroll
               for (int i = 0; i < 16; ++i)
                 if (n + i < N) op[i] = v[i];
+            }
+          } else if (splits > 1) {
+            if (full16 && ((epi.ld_f32 & 3) == 0) && ((reinterpret_cast<size_t>(epi.out_f32) & 15) == 0)) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) atomicAdd(reinterpret_cast<float4*>(op + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (n + i < N) atomicAdd(op + i, v[i]);
             }
           } else if (full16 && ((epi.ld_f32 & 3) == 0)) {
 #pragma unroll
