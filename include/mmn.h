@@ -201,6 +201,11 @@ int mmn_selftest_protocol(int iters, int n_mma, int flags, long long* out, void*
 int mmn_selftest_gemm_bf16(int M, int N, int K, const void* a, long long lda, const void* b, long long ldb,
                            float* out_f32, void* out_bf16, void* out_bf16_t, void* stream);
 
+/* The same GEMM with both operands used "transposed" in place, as the weight-gradient GEMMs do: out[M x N] =
+ * sum_k a[k][m] b[k][n], a: [K x M] and b: [K x N] bf16 row-major (pitches multiples of 8), out_f32: M x N. */
+int mmn_selftest_gemm_bf16_mn(int M, int N, int K, const void* a, long long lda, const void* b, long long ldb,
+                              float* out_f32, void* stream);
+
 /* Kernels launched so far by bf16 (wide-regime) plans in this process: launch accounting for benchmarks. */
 int64_t mmn_wide_launch_count(void);
 

@@ -280,6 +280,22 @@ int make_operand_map(CUtensorMap* m, const void* base, long long rows, long long
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for a %lld x %lld operand, pitch %lld", (int)r, rows, k, ld);
   return 0;
 }
+// MN-major bf16 operand: the contraction index runs over the ROWS of a row-major matrix [k_rows x mn] with pitch ld
+// (a matrix used "transposed" without a transposed copy): boxes of 64 mn x 64 k rows, SWIZZLE_128B
+int make_operand_map_mn(CUtensorMap* m, const void* base, long long mn, long long k_rows, long long ld) {
+  TmapEncodeFn enc = tmap_encoder();
+  if (!enc) return fail("cuTensorMapEncodeTiled is not available in this driver");
+  if ((reinterpret_cast<size_t>(base) & 15) || (ld & 7)) return fail("wide GEMM operand: base must be 16-byte aligned and the row pitch a multiple of 8 elements");
+  const cuuint64_t dims[2] = {(cuuint64_t)mn, (cuuint64_t)k_rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {64, (cuuint32_t)wide::BK};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for an MN-major %lld x %lld operand, pitch %lld", (int)r, k_rows, mn, ld);
+  return 0;
+}
 long long g_wide_launches = 0;       // kernels launched by the wide path (bench.py's gpu_launches)
 // MMN_WIDE_TIMERS=1: CUDA events around every launch of a step, summed per category and printed (development aid)
 struct WideTimers {
@@ -320,11 +336,13 @@ struct WideTimers {
 };
 WideTimers g_wt;
 // D[M x N] = A[M x K] . B[N x K]^T
+// a_mn / b_mn = 0: the operand is [M or N rows x K] with K contiguous.  = 1: it is [K rows x M or N] with M / N contiguous.
 int wide_gemm(int n_sms, const void* A, long long lda, const void* B, long long ldb, long long M, long long N, long long K,
-              const wide::Epi& epi, void* stream, const char* what = "gemm") {
+              const wide::Epi& epi, void* stream, const char* what = "gemm", int a_mn = 0, int b_mn = 0) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   alignas(64) CUtensorMap ma, mb;
-  if (make_operand_map(&ma, A, M, K, lda, wide::BM) || make_operand_map(&mb, B, N, K, ldb, wide::BN)) return 1;
+  if (a_mn ? make_operand_map_mn(&ma, A, M, K, lda) : make_operand_map(&ma, A, M, K, lda, wide::BM)) return 1;
+  if (b_mn ? make_operand_map_mn(&mb, B, N, K, ldb) : make_operand_map(&mb, B, N, K, ldb, wide::BN)) return 1;
   static bool attr_set = false;
   if (!attr_set) {
     MMN_CUDA(cudaFuncSetAttribute(wide::mmn_wide_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wide::kSmemBytes));
@@ -341,7 +359,7 @@ int wide_gemm(int n_sms, const void* A, long long lda, const void* B, long long 
   }
   const int grid = (int)std::min<long long>(tiles * splits, n_sms);
   g_wt.begin(what);
-  wide::mmn_wide_gemm_kernel<<<grid, wide::kThreads, wide::kSmemBytes, (cudaStream_t)stream>>>(ma, mb, (int)M, (int)N, (int)K, splits, epi);
+  wide::mmn_wide_gemm_kernel<<<grid, wide::kThreads, wide::kSmemBytes, (cudaStream_t)stream>>>(ma, mb, (int)M, (int)N, (int)K, splits, a_mn, b_mn, epi);
   g_wt.end();
   MMN_CUDA(cudaGetLastError());
   ++g_wide_launches;
@@ -405,7 +423,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
   const int S = P.S, E = P.E, D = P.D, L = a.seq_len;
   const int n_sms = plan->n_sms;
   Arena ar(dry ? nullptr : ws);
-  ar.want_t = TRAIN;
+  ar.want_t = false;         // weight gradients read dZ and the layer inputs in place (MN-major operands)
   bf16* const wbase = (bf16*)plan->wide_w;
   const dim3 tb(256);
   auto tgrid = [&](long long rows, int width) { return dim3((unsigned)((width + 63) / 64), (unsigned)((rows + 63) / 64)); };
@@ -631,12 +649,13 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
     auto layer_param_grads = [&](const DevLayer& ly, const Mat& dz, const Mat& in) -> int {
       if (dry) return 0;
       g_wt.begin("bias_grad");
-      wide_bias_grad_kernel<<<(ly.out_dim + 1) / 2, 256, 0, stream>>>(dz.t, dz.ldt, B, ly.out_dim, a.grads + ly.b_off);
+      wide_bias_grad_kernel<<<dim3((unsigned)((ly.out_dim + 63) / 64), (unsigned)std::max<long long>(1, std::min<long long>(32, B / 256))),
+                              256, 0, stream>>>(dz.p, dz.ld, B, ly.out_dim, a.grads + ly.b_off);
       if (launched()) return 1;
       Epi e = epi0();
       e.mode = EPI_ACCUM_F32; e.accumulate = 1;
       e.out_f32 = a.grads + ly.w_off; e.ld_f32 = ly.ktot;
-      return wide_gemm(n_sms, dz.t, dz.ldt, in.t, in.ldt, ly.out_dim, ly.ktot, B, e, stream, ly.out_dim < 64 ? "gemm dec-head wgrad" : "gemm wgrad");
+      return wide_gemm(n_sms, dz.p, dz.ld, in.p, in.ld, ly.out_dim, ly.ktot, B, e, stream, "gemm wgrad", 1, 1);
     };
     auto decoders_backward = [&](int k) -> int {
       for (int d = 0; d < D; ++d) {
@@ -987,6 +1006,24 @@ extern "C" int mmn_selftest_gemm_bf16(int M, int N, int K, const void* a, long l
   e.out = (__nv_bfloat16*)out_bf16; e.ld_out = N;
   e.out_t = (__nv_bfloat16*)out_bf16_t; e.ld_out_t = M;
   return wide_gemm(n_sms, a, lda, b, ldb, M, N, K, e, stream);
+#endif
+}
+
+extern "C" int mmn_selftest_gemm_bf16_mn(int M, int N, int K, const void* a, long long lda, const void* b, long long ldb,
+                                         float* out_f32, void* stream) {
+#ifdef MMN_EMU
+  (void)M; (void)N; (void)K; (void)a; (void)lda; (void)b; (void)ldb; (void)out_f32; (void)stream;
+  return fail("mmn_selftest_gemm_bf16_mn: the wide-regime GEMM is not part of the host emulator");
+#else
+  int dev = 0, n_sms = 0;
+  MMN_CUDA(cudaGetDevice(&dev));
+  MMN_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+  wide::Epi e;
+  memset(&e, 0, sizeof e);
+  e.mode = wide::EPI_ACCUM_F32;
+  e.scale = 1.f;
+  e.out_f32 = out_f32; e.ld_f32 = N;
+  return wide_gemm(n_sms, a, lda, b, ldb, M, N, K, e, stream, "selftest", 1, 1);
 #endif
 }
 

@@ -103,7 +103,7 @@ __device__ __forceinline__ float wide_dact(int act, float a) {      // derivativ
 
 __global__ void __launch_bounds__(kThreads, 1)
 mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N, int K,
-                     int splits, const Epi epi) {
+                     int splits, int a_mn, int b_mn, const Epi epi) {
   extern __shared__ __align__(1024) char smem_raw[];
   char* base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
   unsigned long long* full = reinterpret_cast<unsigned long long*>(base + STAGES * kStageBytes);
@@ -143,9 +143,20 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty + p.stage, p.phase ^ 1u);
           char* sa = base + p.stage * kStageBytes;
+          char* sb = sa + BM * BK * 2;
           mbar_expect_tx(full + p.stage, kStageBytes);
-          tma_load_2d(&map_a, full + p.stage, sa, kb * BK, m0);
-          tma_load_2d(&map_b, full + p.stage, sa + BM * BK * 2, kb * BK, n0);
+          if (a_mn) {            // MN-major operand [k rows x mn]: one 64 x 64 box (8 KB, 128-byte rows) per 64 of M
+#pragma unroll
+            for (int g = 0; g < BM / 64; ++g) tma_load_2d(&map_a, full + p.stage, sa + g * 8192, m0 + 64 * g, kb * BK);
+          } else {
+            tma_load_2d(&map_a, full + p.stage, sa, kb * BK, m0);
+          }
+          if (b_mn) {
+#pragma unroll
+            for (int g = 0; g < BN / 64; ++g) tma_load_2d(&map_b, full + p.stage, sb + g * 8192, n0 + 64 * g, kb * BK);
+          } else {
+            tma_load_2d(&map_b, full + p.stage, sb, kb * BK, n0);
+          }
           p.advance();
         }
       }
@@ -153,7 +164,7 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const bool leader = elect_one() != 0;
-    const unsigned idesc = umma_idesc_bf16(BM, BN);
+    const unsigned idesc = umma_idesc_bf16(BM, BN) | ((unsigned)(a_mn != 0) << 15) | ((unsigned)(b_mn != 0) << 16);
     const unsigned sbase = smem_u32(base);
     Pipe p{0, 0};
     unsigned acc_phase[2] = {0u, 0u};
@@ -175,8 +186,14 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         if (leader) {
           const unsigned sa = sbase + p.stage * kStageBytes, sb = sa + BM * BK * 2;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(tmem + acc * BN, umma_desc_k(sa, k), umma_desc_k(sb, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: 16 k = 32 bytes inside the swizzled 128-byte row, 8-row atoms 1024 B apart.
+            // MN-major: 64 mn = one 128-byte row per k, 8-k atoms 1024 B apart (SBO), 64-mn groups 8 KB apart (LBO);
+            //           16 k = two atoms = 2048 bytes.
+            const unsigned long long da = a_mn ? umma_smem_desc(sa + 2048u * k, 8192, 1024, 2) : umma_desc_k(sa, k);
+            const unsigned long long db = b_mn ? umma_smem_desc(sb + 2048u * k, 8192, 1024, 2) : umma_desc_k(sb, k);
+            umma_bf16(tmem + acc * BN, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
           umma_commit(empty + p.stage);
           if (kb == kb_n - 1) umma_commit(acc_full + acc);
         }

@@ -2,11 +2,11 @@
 // of mmn_wide.cuh (precision = bf16: bf16 weights / activations / layer gradients, fp32 accumulation, fp32 master
 // weights, fp32 state gradient and parameter gradients).  Included by mmn_api.cu (needs fail(), MMN_CUDA, mmn_plan).
 //
-// Every activation and every layer gradient is kept in BOTH orientations ([rows x width] and [width x rows]) so that
-// forward, data-gradient and weight-gradient GEMMs are all "A[M x K] . B[N x K]^T with K contiguous":
-//   forward   Y[B x out]   = In[B x k]      . W[out x k]^T
-//   dgrad     dIn[B x in]  = dZ[B x out]    . W^T[in x out]^T
-//   wgrad     dW[out x k]  = dZ^T[out x B]  . In^T[k x B]^T
+// One GEMM kernel serves the three contractions; operands are K-major ([rows x K], K contiguous) or MN-major (a row-major
+// matrix contracted over its ROWS, fetched as 64 x 64 TMA boxes), so no activation is ever transposed in memory:
+//   forward   Y[B x out]   = In[B x k]      . W[out x k]^T            A, B K-major
+//   dgrad     dIn[B x in]  = dZ[B x out]    . W^T[in x out]^T         A, B K-major (W^T: a second bf16 copy of the weights)
+//   wgrad     dW[out x k]  = sum_r dZ[r][out] In[r][k]                A = dZ, B = In, both MN-major
 // The GEMM epilogues fuse bias + activation, the per-row missingness select + state-change sum, act' of the data
 // gradient, the fp32 accumulation of weight / state gradients and the state carry through an encoder.
 #pragma once
@@ -176,27 +176,34 @@ __global__ void wide_state_grad_post_kernel(float* G, Mat sk, Mat skm1, float c_
     G[i] -= c_sc * (__bfloat162float(sk.p[r * sk.ld + c]) - __bfloat162float(skm1.p[r * skm1.ld + c]));
   }
 }
-// bias gradient: gb[n] += sum_r dz^T[n][r]          (two outputs per CTA, four warps each, 16-byte loads)
-__global__ void __launch_bounds__(256) wide_bias_grad_kernel(const bf16* __restrict__ dzt, long long ldt, long long rows, int n_out, float* gb) {
-  __shared__ float red[8];
-  const int half = threadIdx.x >> 7, t = threadIdx.x & 127;
-  const int n = blockIdx.x * 2 + half;
-  float s = 0.f;
-  if (n < n_out) {
-    const bf16* row = dzt + (long long)n * ldt;
-#pragma unroll 4
-    for (long long r = t * 8; r < rows; r += 1024) {
-      float v[8];
-      load8(row + r, (int)min((long long)8, rows - r), v);
+// bias gradient: gb[n] += sum_r dz[r][n]          CTA = 64 columns x a slice of the rows; thread = 8 columns, every 32nd row
+__global__ void __launch_bounds__(256) wide_bias_grad_kernel(const bf16* __restrict__ dz, long long ld, long long rows, int n_out, float* gb) {
+  __shared__ float red[32][65];
+  const int chunk = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int n0 = blockIdx.x * 64 + chunk * 8;
+  const long long per = (rows + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+  float acc[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s += v[i];
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (n0 < n_out) {
+#pragma unroll 4
+    for (long long r = r0 + rl; r < r1; r += 32) {
+      float v[8];
+      load8(dz + r * ld + n0, n_out - n0, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
     }
   }
 #pragma unroll
-  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  for (int i = 0; i < 8; ++i) red[rl][chunk * 8 + i] = acc[i];
   __syncthreads();
-  if (t == 0 && n < n_out) atomicAdd(gb + n, red[4 * half] + red[4 * half + 1] + red[4 * half + 2] + red[4 * half + 3]);
+  if (threadIdx.x < 64) {
+    float tot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) tot += red[j][threadIdx.x];
+    const int n = blockIdx.x * 64 + threadIdx.x;
+    if (n < n_out && tot != 0.f) atomicAdd(gb + n, tot);
+  }
 }
 // column sums of the fp32 state gradient -> gradient of state_value (tile backward, state.py:30)
 __global__ void wide_colsum_f32_kernel(const float* __restrict__ G, long long rows, int S, float* out) {
@@ -366,7 +373,7 @@ __global__ void wide_decoder_loss_kernel(const LossArgs a) {
         for (int c = 0; c < a.C; ++c) {
           const float g = coef * (expf(p[c] - mx) * inv - (c == y ? 1.f : 0.f)) * wide_dact(a.act, p[c]);
           a.dz.p[r * a.dz.ld + c] = __float2bfloat16(g);
-          a.dz.t[(long long)c * a.dz.ldt + r] = __float2bfloat16(g);
+          if (a.dz.t) a.dz.t[(long long)c * a.dz.ldt + r] = __float2bfloat16(g);
         }
       }
     }

@@ -48,3 +48,25 @@ def test_gemm_matches_torch(M, N, K):
 def test_gemm_pitched_operands():
     out, ob, ot, want = run_gemm(300, 520, 320, lda=512, ldb=384, seed=3)
     assert (out - want).abs().max().item() <= 1e-5 * want.abs().max().item() * 3
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 512), (2048, 1024, 8192), (100, 40, 72), (130, 258, 200),
+                                   (2, 2048, 517), (2048, 3072, 300)])
+def test_gemm_mn_major_operands(M, N, K):
+    """both operands contracted over their ROWS (the weight-gradient form dW = dZ^T . In without transposed copies)"""
+    from multimodn_b200 import _lib
+    lib = _lib.get_lib()
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    lda, ldb = (M + 7) // 8 * 8 + 8, (N + 7) // 8 * 8
+    a = torch.full((K, lda), 5.0, dtype=torch.bfloat16)
+    b = torch.full((K, ldb), -2.0, dtype=torch.bfloat16)
+    a[:, :M] = torch.randn(K, M, generator=g).to(torch.bfloat16)
+    b[:, :N] = torch.randn(K, N, generator=g).to(torch.bfloat16)
+    a, b = a.to(dev), b.to(dev)
+    out = torch.full((M, N), float("nan"), dtype=torch.float32, device=dev)
+    lib.check(lib.dll.mmn_selftest_gemm_bf16_mn(M, N, K, a.data_ptr(), lda, b.data_ptr(), ldb, out.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    want = a[:, :M].float().T @ b[:, :N].float()
+    assert (out - want).abs().max().item() <= 1e-5 * want.abs().max().item() * max(1.0, (K / 64) ** 0.5)
