@@ -1,0 +1,65 @@
+// mmn_fma.cu — the FP32-FMA engine's translation unit: step kernels for every tile configuration, the missingness scan
+// and the fused Adam step.
+#include "mmn_kernels.cuh"
+#include "mmn_launch.cuh"
+
+using namespace mmn;
+
+size_t mmn_fma_smem(const DevPlan& P, int rm, int occ) {
+  const size_t stage = occ == 2 ? FmaEngine<2, 2>::stage_bytes()
+                                : rm == 4 ? FmaEngine<4>::stage_bytes() : rm == 2 ? FmaEngine<2>::stage_bytes() : FmaEngine<1>::stage_bytes();
+  return step_smem_bytes(P, 32 * rm, stage);
+}
+
+namespace {
+template <bool TRAIN>
+int launch_fma(const mmn_plan* plan, const StepArgs& a, void* stream) {
+  if (plan->occ == 2) return launch_engine<FmaEngine<2, 2>, TRAIN>(plan, a, stream);
+  switch (plan->rm) {
+    case 4: return launch_engine<FmaEngine<4>, TRAIN>(plan, a, stream);
+    case 2: return launch_engine<FmaEngine<2>, TRAIN>(plan, a, stream);
+    case 1: return launch_engine<FmaEngine<1>, TRAIN>(plan, a, stream);
+    default: return fail("no tile configuration fits");
+  }
+}
+}  // namespace
+
+int mmn_launch_fma(const mmn_plan* plan, const StepArgs& a, void* stream, bool train) {
+  return train ? launch_fma<true>(plan, a, stream) : launch_fma<false>(plan, a, stream);
+}
+
+extern "C" int mmn_scan_missing(const mmn_plan* plan, const mmn_batch* b, int32_t* flags, void* stream) {
+  if (!plan || !b || !flags) return fail("mmn_scan_missing: null argument");
+  const DevPlan& P = plan->host;
+  if (b->seq_len < 0 || b->seq_len > P.E) return fail("seq_len must be in [0, E]");
+  ScanArgs s;
+  memset(&s, 0, sizeof s);
+  s.seq_len = b->seq_len;
+  s.n_rows = b->n_rows;
+  s.flags = flags;
+  for (int k = 0; k < b->seq_len; ++k) {
+    const int e = b->seq_enc[k], pos = b->seq_pos[k];
+    if (e < 0 || e >= P.E || pos < 0 || pos >= MMN_MAX_ENCODERS || !b->x[pos]) return fail("mmn_scan_missing: bad sequence step %d", k);
+    s.F[k] = P.enc[e].F;
+    s.x[k] = b->x[pos];
+    s.x_ld[k] = b->x_ld[pos];
+  }
+  MMN_CUDA(cudaMemsetAsync(flags, 0, sizeof(int32_t) * std::max(1, b->seq_len), (cudaStream_t)stream));
+  const int grid = std::max(1, std::min(plan->n_sms * 4, (int)((b->n_rows + 7) / 8)));
+  MMN_LAUNCH(mmn_scan_missing_kernel<0>, dim3(grid), dim3(256), 0, stream, s);
+  MMN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmn_adam_step(const mmn_plan* plan, float* params, const float* grads, float* exp_avg,
+                             float* exp_avg_sq, int32_t* step_count, float lr, float beta1, float beta2,
+                             float eps, void* stream) {
+  if (!plan || !params || !grads || !exp_avg || !exp_avg_sq || !step_count) return fail("mmn_adam_step: null argument");
+  MMN_LAUNCH(mmn_adam_tick_kernel<0>, dim3(1), dim3(32), 0, stream, plan->dev, grads, step_count);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((plan->host.n_params + 255) / 256, (int64_t)plan->n_sms * 8));
+  MMN_LAUNCH(mmn_adam_kernel<0>, dim3(grid), dim3(256), 0, stream, plan->dev, params, grads, exp_avg, exp_avg_sq,
+             step_count, lr, beta1, beta2, eps);
+  MMN_CUDA(cudaGetLastError());
+  return 0;
+}
+

@@ -1,0 +1,62 @@
+// mmn_host.h — host-side declarations shared by the translation units of libmmn.so.  Every kernel family is compiled
+// in its own translation unit (mmn_fma.cu, mmn_tc.cu, mmn_tc2.cu, mmn_wide.cu): the device code nvcc generates for one
+// kernel must not depend on which other kernels happen to share its compilation (inlining decisions are made per
+// module — the FP32-FMA step kernel lost 40 % when the TMEM-resident backward pass joined its translation unit).
+#pragma once
+
+#include "mmn_common.cuh"
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+struct mmn_plan {
+  mmn::DevPlan host;
+  mmn::DevPlan* dev = nullptr;
+  int n_sms = 0;
+  int max_smem = 0;
+  int engine = MMN_ENGINE_FMA;   // MMN_ENGINE_*
+  int rm = 0;                    // FMA engine: rows per tile / 32
+  int occ = 1;                   // FMA engine: CTAs per SM the kernel variant is built for
+  int fwd_engine = MMN_ENGINE_FMA;   // engine of the forward-only path (test / predict / get_states)
+  // wide regime (precision = bf16): bf16 copies of every weight in both orientations, refreshed every call
+  void* wide_w = nullptr;
+  long long wide_elems = 0;
+  struct WL { long long w, wt; int ldk, ldo; };
+  WL wide_enc[MMN_MAX_ENCODERS][MMN_MAX_LAYERS];
+  WL wide_dec[MMN_MAX_DECODERS][MMN_MAX_LAYERS];
+};
+
+int mmn_fail(const char* fmt, ...);       // records the calling thread's error message, returns 1
+template <class... Args>
+static inline int fail(const char* fmt, Args... args) { return mmn_fail(fmt, args...); }
+#define MMN_CUDA(call)                                                            \
+  do {                                                                            \
+    cudaError_t e_ = (call);                                                      \
+    if (e_ != cudaSuccess) return fail("%s: %s", #call, cudaGetErrorString(e_));  \
+  } while (0)
+
+inline int tile_rows(const mmn_plan* p, int engine) { return engine != MMN_ENGINE_FMA ? 128 : 32 * p->rm; }
+inline int grid_for(const mmn_plan* p, int engine, int64_t n_rows) {
+  const int tm = tile_rows(p, engine);
+  const int64_t tiles = (n_rows + tm - 1) / tm;
+  const int per_sm = engine == MMN_ENGINE_FMA ? p->occ : 1;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)p->n_sms * per_sm));
+}
+
+// per-family entry points (defined next to the kernels they launch)
+size_t mmn_fma_smem(const mmn::DevPlan& P, int rm, int occ);
+size_t mmn_tc_smem(const mmn::DevPlan& P);
+bool mmn_v2_supports(const mmn::DevPlan& P);
+size_t mmn_v2_smem(const mmn::DevPlan& P);
+int mmn_launch_fma(const mmn_plan* plan, const mmn::StepArgs& a, void* stream, bool train);
+int mmn_launch_tc(const mmn_plan* plan, const mmn::StepArgs& a, void* stream, bool train);
+int mmn_launch_v2(const mmn_plan* plan, const mmn::StepArgs& a, void* stream, bool train);
+#ifndef MMN_EMU
+int mmn_wide_plan_init(mmn_plan* p);
+int64_t mmn_wide_workspace_bytes(const mmn_plan* plan, int64_t n_rows, bool train);
+int mmn_wide_step(const mmn_plan* plan, const mmn::StepArgs& a, void* ws, size_t ws_bytes, void* stream, bool train);
+#endif

@@ -1095,6 +1095,7 @@ struct ScanArgs {
   long long x_ld[MMN_MAX_ENCODERS];
   int* flags;
 };
+template <int = 0>
 __global__ void __launch_bounds__(256) mmn_scan_missing_kernel(const ScanArgs a) {
   for (int k = 0; k < a.seq_len; ++k) {
     const long long n = a.n_rows * a.F[k];
@@ -1111,11 +1112,13 @@ __global__ void __launch_bounds__(256) mmn_scan_missing_kernel(const ScanArgs a)
 // ------------------------------------------------------------------------------------------------
 // Adam on the packed buffers (torch.optim.Adam defaults; multimodn.py:204)
 // ------------------------------------------------------------------------------------------------
+template <int = 0>
 __global__ void mmn_adam_tick_kernel(const DevPlan* plan, const float* grads, int* step_count) {
   const int i = threadIdx.x;
   if (i == 0) step_count[0] += 1;
   if (i >= 1 && i <= plan->E && grads[plan->n_params + (i - 1)] > 0.f) step_count[i] += 1;
 }
+template <int = 0>
 __global__ void __launch_bounds__(256) mmn_adam_kernel(const DevPlan* plan, float* params, const float* grads,
                                                         float* m, float* v, const int* step_count, float lr,
                                                         float b1, float b2, float eps) {

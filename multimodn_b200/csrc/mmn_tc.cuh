@@ -20,6 +20,8 @@
 // exercised on the CPU; the real instruction semantics are validated by the -m gpu tests.
 #pragma once
 
+#include "mmn_kernels.cuh"
+
 #include "mmn_common.cuh"
 
 namespace mmn {
@@ -828,6 +830,7 @@ struct TcEngine {
 // A: [128 x 32], B: [N x 32], W: [32 x N], Z: [128 x 64], X: [128 x 32]; out: [128 x N] (mode 2: N = 32,
 // rows n < 64 meaningful).
 // ------------------------------------------------------------------------------------------------
+template <int = 0>
 __global__ void __launch_bounds__(256, 1) mmn_tc_selftest_kernel(int mode, int N, const float* __restrict__ A,
                                                                 const float* __restrict__ B, float* __restrict__ out) {
   MMN_DYN_SMEM(raw);

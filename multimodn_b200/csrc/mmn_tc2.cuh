@@ -1010,6 +1010,7 @@ namespace mmn {
 //   flags bit 0: workers execute fence.proxy.async        bit 1: workers execute tcgen05.ld each round
 //   flags bit 2: only warp 0 participates as worker (full barrier of 32 arrivals)
 // ------------------------------------------------------------------------------------------------
+template <int = 0>
 __global__ void __launch_bounds__(288, 1) mmn_protocol_probe_kernel(int iters, int n_mma, int flags, long long* out) {
   MMN_DYN_SMEM(raw);
   char* base = raw + ((1024 - (smem_u32(raw) & 1023)) & 1023);
