@@ -42,8 +42,9 @@ def parse_args(argv=None):
     return p.parse_args(argv)
 
 
-def run(csv_path, epochs, seed, device, batch_size=32):
-    """The experiment of titanic_mlp_pipeline.py:24-85; returns (model, history, (train, val) subsets)."""
+def run(csv_path, epochs, seed, device, batch_size=32, on_model=None):
+    """The experiment of titanic_mlp_pipeline.py:24-85; returns (model, history, (train, val) subsets).
+    on_model(model), if given, runs after construction and before the first epoch."""
     torch.manual_seed(seed)
     datasplit = (0.8, 0.2, 0)
     state_size = 1
@@ -56,6 +57,8 @@ def run(csv_path, epochs, seed, device, batch_size=32):
     encoders = [MLPEncoder(state_size, len(FEATURES), (5, 5), F.relu)]
     decoders = [LogisticDecoder(state_size) for _ in TARGETS]
     model = MultiModN(state_size, encoders, decoders, 0.7, 0.3, device=torch.device(device))
+    if on_model is not None:
+        on_model(model)
     optimizer = torch.optim.Adam(list(model.parameters()), learning_rate)
     criterion = CrossEntropyLoss()
     history = MultiModNHistory(TARGETS)

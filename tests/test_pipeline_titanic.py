@@ -61,9 +61,9 @@ def test_seeded_construction_matches_reference(table):
     assert (got == want).all()
 
 
-def check_pipeline(fx, csv, device):
+def check_pipeline(fx, csv, device, on_model=None):
     model, history, (train, val) = pipeline.run(csv, int(fx["epochs"]), int(fx["seed"]), device,
-                                                batch_size=int(fx["batch_size"]))
+                                                batch_size=int(fx["batch_size"]), on_model=on_model)
     assert len(train) == len(fx["train_idx"]) and len(val) == len(fx["val_idx"])
     for ep in range(int(fx["epochs"])):
         for name in HIST:
@@ -102,5 +102,18 @@ def test_pipeline_artifacts(emu, tmp_path):
 
 @pytest.mark.gpu
 def test_pipeline_matches_reference_gpu(table):
+    """On a CUDA device TrainableInitState draws from the CUDA generator (as the reference's does, state.py:25-27), so the
+    seeded initial state differs from the CPU-generated golden run: start from the golden's initial weights instead."""
     fx, csv = table
-    check_pipeline(fx, csv, "cuda")
+    spec0 = golden_spec(fx)
+
+    def load_golden_weights(model):
+        with torch.no_grad():
+            model.init_state.state_value.copy_(torch.from_numpy(np.asarray(spec0["init_state"], dtype=np.float32)).reshape(1, -1))
+            lins = list(model.encoders[0].layers) + [model.decoders[0].fc]
+            pairs = list(spec0["encoders"][0]["layers"]) + list(spec0["decoders"][0]["layers"])
+            for lin, (W, b) in zip(lins, pairs):
+                lin.weight.copy_(torch.from_numpy(np.asarray(W, dtype=np.float32)))
+                lin.bias.copy_(torch.from_numpy(np.asarray(b, dtype=np.float32)))
+
+    check_pipeline(fx, csv, "cuda", on_model=load_golden_weights)
