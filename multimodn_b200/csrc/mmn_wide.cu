@@ -434,7 +434,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
             const Mat nz = view(dzbuf[cur], ly.in_dim);
             if (!dry) {
               g_wt.begin("head_wgrad");
-              wide_head_wgrad_kernel<4><<<dim3((unsigned)((ly.in_dim + 2047) / 2048), (unsigned)std::max<long long>(1, std::min<long long>(2 * n_sms, B / 32))),
+              wide_head_wgrad_kernel<4><<<dim3((unsigned)((ly.in_dim + 2047) / 2048), (unsigned)std::max<long long>(1, std::min<long long>(4 * n_sms, B / 16))),
                                           256, 0, stream>>>(dz, in, dec.C, B, a.grads + ly.w_off, ly.ktot, a.grads + ly.b_off);
               if (launched()) return 1;
               g_wt.begin("head_dgrad");

@@ -310,11 +310,19 @@ __global__ void __launch_bounds__(256) wide_head_wgrad_kernel(Mat dz, Mat h, int
       }
     }
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c)
-      if (c < C)
+    for (int c = 0; c < CMAX; ++c) {
+      if (c < C) {
+        float* dst = gW + (long long)c * ldw + k0;
+        if (k0 + 8 <= h.width && (reinterpret_cast<size_t>(dst) & 15) == 0) {      // two red.global.add.v4.f32
+          atomicAdd(reinterpret_cast<float4*>(dst), make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]));
+          atomicAdd(reinterpret_cast<float4*>(dst) + 1, make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]));
+        } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (k0 + i < h.width && acc[c][i] != 0.f) atomicAdd(gW + (long long)c * ldw + k0 + i, acc[c][i]);
+          for (int i = 0; i < 8; ++i)
+            if (k0 + i < h.width && acc[c][i] != 0.f) atomicAdd(dst + i, acc[c][i]);
+        }
+      }
+    }
   }
   if (blockIdx.x == 0 && (int)threadIdx.x < C) {
     float s = 0.f;
