@@ -202,13 +202,22 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
   Drop nodrop;
   memset(&nodrop, 0, sizeof nodrop);
   nodrop.scale = 1.f;
+  // data gradient dIn[:, col0 : col0 + n] = dZ . W[:, col0 : col0 + n] through the transposed bf16 copy of W (K-major B
+  // operand: one 256-row TMA box per stage).  Using W in place as an MN-major operand (four 64 x 64 boxes per stage) works
+  // when the sub-block starts on a 16-byte boundary but measured 10 % slower on config 4, so it is not used.
+  auto needs_wt = [](const DevLayer&) { return true; };
+  auto dgrad = [&](const Mat& dz, const DevLayer& l, const mmn_plan::WL& w, int col0, int n, const Epi& e, const char* what) -> int {
+    if (needs_wt(l)) return wide_gemm(n_sms, dz.p, dz.ld, wbase + w.wt + (long long)col0 * w.ldo, w.ldo, B, n, l.out_dim, e, stream, what);
+    return wide_gemm(n_sms, dz.p, dz.ld, wbase + w.w + col0, w.ldk, B, n, l.out_dim, e, stream, what, 0, 1);
+  };
 
   // ---- 0. bf16 copies of the weights (both orientations) ----
   if (!dry) {
     auto cast = [&](const DevLayer& l, const mmn_plan::WL& w) -> int {
       g_wt.begin("cast_weight");
+      // the transposed copy only serves data-gradient GEMMs whose weight sub-block is not 16-byte aligned in W itself
       wide_cast_weight_kernel<<<tgrid(l.out_dim, l.ktot), tb, 0, stream>>>(a.params + l.w_off, l.out_dim, l.ktot, wbase + w.w, w.ldk,
-                                                                           wbase + w.wt, w.ldo);
+                                                                           needs_wt(l) ? wbase + w.wt : nullptr, w.ldo);
       return launched();
     };
     for (int e = 0; e < E; ++e)
@@ -452,13 +461,13 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
             e.mode = EPI_DACT; e.act = dec.L[j - 1].act;
             e.aux = in.p; e.ld_aux = in.ld;
             e.out = nz.p; e.ld_out = nz.ld; e.out_t = nz.t; e.ld_out_t = nz.ldt;
-            if (!dry && wide_gemm(n_sms, dz.p, dz.ld, wbase + w.wt, w.ldo, B, ly.in_dim, ly.out_dim, e, stream, ly.out_dim < 64 ? "gemm dec-head dgrad" : "gemm dgrad")) return 1;
+            if (!dry && dgrad(dz, ly, w, 0, ly.in_dim, e, "gemm dgrad")) return 1;
             dz = nz;
             cur ^= 1;
           } else {
             e.mode = EPI_ACCUM_F32; e.accumulate = 1;
             e.out_f32 = G; e.ld_f32 = S;
-            if (!dry && wide_gemm(n_sms, dz.p, dz.ld, wbase + w.wt, w.ldo, B, S, ly.out_dim, e, stream)) return 1;
+            if (!dry && dgrad(dz, ly, w, 0, S, e, "gemm dgrad")) return 1;
           }
         }
       }
@@ -485,7 +494,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
         const Mat in = enc_in[(size_t)k * MMN_MAX_LAYERS + j];
         if (layer_param_grads(ly, dz, in)) return 1;
         if (ly.has_state && !dry) {
-          // carry into G: present rows take dz W_s (through the dropout mask), absent rows keep G; then remove u_k
+          // carry into G: present rows take dz W_s (through the dropout mask), absent rows keep G; u_k is removed in the same epilogue
           Epi ep = epi0();
           ep.mode = EPI_CARRY;
           ep.out_f32 = G; ep.ld_f32 = S;
@@ -497,11 +506,8 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
             ep.drop_col_base = (unsigned)ly.in_dim;
             ep.scale = 1.f / (1.f - enc.p_drop);
           }
-          if (wide_gemm(n_sms, dz.p, dz.ld, wbase + w.wt + (long long)ly.in_dim * w.ldo, w.ldo, B, S, ly.out_dim, ep, stream)) return 1;
-          g_wt.begin("state_grad_post");
-          wide_state_grad_post_kernel<<<(unsigned)std::min<long long>((B * S + 255) / 256, 4096), 256, 0, stream>>>(G, Sk[k], Sk[k - 1],
-                                                                                                                   a.c_sc, B);
-          if (launched()) return 1;
+          ep.aux = Sk[k].p; ep.ld_aux = Sk[k].ld; ep.aux2 = Sk[k - 1].p; ep.ld_aux2 = Sk[k - 1].ld; ep.c_sc = a.c_sc;
+          if (dgrad(dz, ly, w, ly.in_dim, S, ep, "gemm dgrad")) return 1;
         }
         if (j > 0) {
           const Mat nz = view(dzbuf[cur], ly.in_dim);
@@ -509,7 +515,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
           ep.mode = EPI_DACT; ep.act = enc.L[j - 1].act;
           ep.aux = in.p; ep.ld_aux = in.ld;
           ep.out = nz.p; ep.ld_out = nz.ld; ep.out_t = nz.t; ep.ld_out_t = nz.ldt;
-          if (!dry && wide_gemm(n_sms, dz.p, dz.ld, wbase + w.wt, w.ldo, B, ly.in_dim, ly.out_dim, ep, stream)) return 1;
+          if (!dry && dgrad(dz, ly, w, 0, ly.in_dim, ep, "gemm dgrad")) return 1;
           dz = nz;
           cur ^= 1;
         }

@@ -34,7 +34,8 @@ enum {
   EPI_SELECT = 1,      // out = present[r] ? act(acc + bias) : aux[r][n]; sc += (out - aux)^2   (encoder output = new state)
   EPI_DACT = 2,        // out = acc * act'(aux[r][n])                             (data gradient into a hidden layer)
   EPI_ACCUM_F32 = 3,   // out_f32 (+)= acc                                         (weight gradient; state gradient G += ...)
-  EPI_CARRY = 4,       // out_f32 = present[r] ? acc : out_f32                     (state carry through an encoder)
+  EPI_CARRY = 4,       // out_f32 = (present[r] ? acc : out_f32) - c_sc (aux - aux2)   (state carry through an encoder; the
+                       //                                                          state-change term changes sign for s_{k-1})
 };
 
 struct Epi {
@@ -44,6 +45,7 @@ struct Epi {
   __nv_bfloat16* out; long long ld_out;               // row-major bf16
   __nv_bfloat16* out_t; long long ld_out_t;           // transposed bf16 [N x M]
   const __nv_bfloat16* aux; long long ld_aux;         // activation for act' / previous state for the select
+  const __nv_bfloat16* aux2; long long ld_aux2; float c_sc;   // EPI_CARRY: aux = s_k, aux2 = s_{k-1}
   const unsigned char* present;                       // [M]
   const int* skip;                                    // device flag: non-zero = the step is skipped for every row
   unsigned drop_thr, drop_seed, drop_row_base, drop_col_base;   // EPI_CARRY through a dropout mask (thr 0 = none)
@@ -303,10 +305,34 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         if (epi.out_f32) {
           float* op = epi.out_f32 + (long long)r * epi.ld_f32 + n;
           if (epi.mode == EPI_CARRY) {
-            if (pres) {
+            const __nv_bfloat16* bp = epi.aux2 + (long long)r * epi.ld_aux2 + n;
+            float b[16];
+            if (full16 && ((epi.ld_aux2 & 7) == 0)) {
+              const uint4 b0 = *reinterpret_cast<const uint4*>(bp), b1 = *reinterpret_cast<const uint4*>(bp + 8);
+              const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&b0);
+              const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&b1);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f0 = __bfloat1622float2(h0[i]), f1 = __bfloat1622float2(h1[i]);
+                b[2 * i] = f0.x; b[2 * i + 1] = f0.y; b[8 + 2 * i] = f1.x; b[8 + 2 * i + 1] = f1.y;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) b[i] = n + i < N ? __bfloat162float(bp[i]) : 0.f;
+            }
+            if (full16 && ((epi.ld_f32 & 3) == 0)) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                float4 g = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                if (!pres) g = *reinterpret_cast<const float4*>(op + i);
+                g.x -= epi.c_sc * (aux[i] - b[i]); g.y -= epi.c_sc * (aux[i + 1] - b[i + 1]);
+                g.z -= epi.c_sc * (aux[i + 2] - b[i + 2]); g.w -= epi.c_sc * (aux[i + 3] - b[i + 3]);
+                *reinterpret_cast<float4*>(op + i) = g;
+              }
+            } else {
 #pragma unroll
               for (int i = 0; i < 16; ++i)
-                if (n + i < N) op[i] = v[i];
+                if (n + i < N) op[i] = (pres ? v[i] : op[i]) - epi.c_sc * (aux[i] - b[i]);
             }
           } else if (splits > 1) {
             if (full16 && ((epi.ld_f32 & 3) == 0) && ((reinterpret_cast<size_t>(epi.out_f32) & 15) == 0)) {

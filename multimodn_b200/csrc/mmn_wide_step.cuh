@@ -167,15 +167,6 @@ __global__ void __launch_bounds__(256) wide_state_grad_kernel(float* G, Mat sk, 
     }
   }, rows, sk.width, dz.p, dz.ld, dz.t, dz.ldt, 0);
 }
-// G -= u_k (the state-change term reaches s_{k-1} with the opposite sign)
-__global__ void wide_state_grad_post_kernel(float* G, Mat sk, Mat skm1, float c_sc, long long rows) {
-  const long long n = rows * sk.width;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / sk.width;
-    const int c = (int)(i - r * sk.width);
-    G[i] -= c_sc * (__bfloat162float(sk.p[r * sk.ld + c]) - __bfloat162float(skm1.p[r * skm1.ld + c]));
-  }
-}
 // bias gradient: gb[n] += sum_r dz[r][n]          CTA = 64 columns x a slice of the rows; thread = 8 columns, every 32nd row
 __global__ void __launch_bounds__(256) wide_bias_grad_kernel(const bf16* __restrict__ dz, long long ld, long long rows, int n_out, float* gb) {
   __shared__ float red[32][65];
