@@ -157,8 +157,10 @@ extern "C" int mmn_plan_create(const mmn_model_desc* desc, mmn_plan** out) {
   const bool tc_fits = tc_smem(P) <= (size_t)p->max_smem;
   const char* want = getenv("MMN_ENGINE");            // "tc" | "fma" | unset = auto
   if (want && !strcmp(want, "tc") && !tc_fits) {
+    const size_t need = tc_smem(P);
+    const int limit = p->max_smem;
     delete p;
-    return fail("MMN_ENGINE=tc: the tensor-core engine needs %zu B of shared memory for this model (limit %d)", tc_smem(P), p->max_smem);
+    return fail("MMN_ENGINE=tc: the tensor-core engine needs %zu B of shared memory for this model (limit %d)", need, limit);
   }
   // default: the FP32-FMA engine (faster at the current stage of tuning, profiles/r1_engine_timers.txt);
   // MMN_ENGINE=tc opts into the tcgen05 3xTF32 engine
