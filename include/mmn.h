@@ -149,6 +149,13 @@ void mmn_plan_destroy(mmn_plan* plan);
  * The environment variable MMN_ENGINE=fma|tc|tc2, read by mmn_plan_create, forces one. */
 enum { MMN_ENGINE_FMA = 0, MMN_ENGINE_TC = 1, MMN_ENGINE_TC2 = 2, MMN_ENGINE_WIDE = 3 /* precision = bf16 */ };
 int32_t mmn_plan_engine(const mmn_plan* plan);           /* engine of mmn_train_step */
+
+/* Data-parallel overlap (the gradient all-reduce "issued per encoder block in reverse order to overlap with
+ * the remaining backward").  events: E + 1 cudaEvent_t handles owned by the caller (n = 0 clears).  Every mmn_train_step
+ * then records events[e] on its stream as soon as encoder e's parameter gradients are final and events[E] when the whole
+ * gradient buffer is (decoders, initial state, present counts; encoders outside the sequence).  Layer-wise (bf16) plans
+ * record them between their launches; the single-launch fp32 kernels record all of them after the launch. */
+int mmn_plan_set_grad_events(mmn_plan* plan, void* const* events, int32_t n);
 int32_t mmn_plan_forward_engine(const mmn_plan* plan);   /* engine of mmn_forward */
 
 int64_t mmn_metrics_count(const mmn_plan* plan);            /* doubles in mmn_outputs.metrics */

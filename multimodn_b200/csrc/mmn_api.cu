@@ -198,6 +198,18 @@ extern "C" void mmn_plan_destroy(mmn_plan* plan) {
 extern "C" int64_t mmn_metrics_count(const mmn_plan* plan) { return plan ? plan->host.n_metrics : -1; }
 extern "C" int64_t mmn_grad_count(const mmn_plan* plan) { return plan ? plan->host.n_params + plan->host.E : -1; }
 
+extern "C" int mmn_plan_set_grad_events(mmn_plan* plan, void* const* events, int32_t n) {
+  if (!plan) return fail("mmn_plan_set_grad_events: null plan");
+  if (n != 0 && n != plan->host.E + 1) return fail("mmn_plan_set_grad_events: expected %d events (one per encoder + one), got %d", plan->host.E + 1, n);
+  if (n && !events) return fail("mmn_plan_set_grad_events: null event array");
+  for (int i = 0; i < n; ++i) {
+    if (!events[i]) return fail("mmn_plan_set_grad_events: event %d is null", i);
+    plan->grad_events[i] = events[i];
+  }
+  plan->n_grad_events = n;
+  return 0;
+}
+
 extern "C" int32_t mmn_plan_engine(const mmn_plan* plan) { return plan ? plan->engine : -1; }
 extern "C" int32_t mmn_plan_forward_engine(const mmn_plan* plan) { return plan ? plan->fwd_engine : -1; }
 
@@ -294,7 +306,12 @@ extern "C" int mmn_train_step(const mmn_plan* plan, const mmn_batch* batch, cons
 #ifndef MMN_EMU
   if (plan->engine == MMN_ENGINE_WIDE) return mmn_wide_step(plan, a, workspace, workspace_bytes, stream, true);
 #endif
-  return launch_step(plan, a, stream, true);
+  if (launch_step(plan, a, stream, true)) return 1;
+#ifndef MMN_EMU
+  for (int i = 0; i < plan->n_grad_events; ++i)          // one launch: every gradient block is final at its end
+    MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->grad_events[i], (cudaStream_t)stream));
+#endif
+  return 0;
 }
 
 

@@ -28,6 +28,9 @@ struct mmn_plan {
   struct WL { long long w, wt; int ldk, ldo; };
   WL wide_enc[MMN_MAX_ENCODERS][MMN_MAX_LAYERS];
   WL wide_dec[MMN_MAX_DECODERS][MMN_MAX_LAYERS];
+  // optional cudaEvent_t handles recorded by mmn_train_step as gradient blocks become final (mmn_plan_set_grad_events)
+  void* grad_events[MMN_MAX_ENCODERS + 1] = {};
+  int n_grad_events = 0;
 };
 
 int mmn_fail(const char* fmt, ...);       // records the calling thread's error message, returns 1

@@ -409,6 +409,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
     // =====================================================================================================
     // backward: replay the sequence in reverse
     // =====================================================================================================
+    unsigned ev_done = 0;        // encoders whose gradient-ready event has been recorded this step
     float* G = (float*)ar.take(sizeof(float) * (size_t)B * S);
     Mat dzbuf[2] = {ar.mat(B, maxW), ar.mat(B, maxW)};
     auto view = [](const Mat& m, int width) {       // same memory, narrower logical width (pitches of the narrow matrix)
@@ -520,12 +521,16 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
           cur ^= 1;
         }
       }
+      // encoder e's parameter gradients are final: let the caller start reducing them across ranks
+      if (!dry && plan->n_grad_events) { MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->grad_events[e], stream)); ev_done |= 1u << e; }
     }
     if (decoders_backward(0)) return 1;
     if (!dry) {
       g_wt.begin("colsum_f32");
       wide_colsum_f32_kernel<<<dim3((unsigned)((S + 31) / 32), 16), 256, 0, stream>>>(G, B, S, a.grads + P.init_off);
       if (launched()) return 1;
+      for (int i = 0; i < plan->n_grad_events; ++i)      // decoders, initial state, encoders that took no step
+        if (i == E || !(ev_done & (1u << i))) MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->grad_events[i], stream));
     }
   }
   g_wt.report();

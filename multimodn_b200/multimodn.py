@@ -84,6 +84,9 @@ class _Runtime:
         self._flags = torch.zeros(max(self.E, 1), dtype=torch.int32, device=self.device)
         self.step_counter = 0
         self.dropout_base_seed = int(torch.initial_seed() & 0x7FFFFFFF)
+        self.layerwise = int(self.lib.dll.mmn_plan_engine(self.plan)) == 3      # bf16 plans: many launches per step
+        self.grad_events = None
+        self.comm_stream = None
 
     def __del__(self):
         try:
@@ -92,6 +95,16 @@ class _Runtime:
                 self.plan = None
         except Exception:  # noqa: BLE001  (interpreter shutdown)
             pass
+
+    def enable_grad_events(self):
+        """E + 1 CUDA events the library records as gradient blocks become final (mmn_plan_set_grad_events)."""
+        events = [torch.cuda.Event() for _ in range(self.E + 1)]
+        for ev in events:
+            ev.record(torch.cuda.current_stream(self.device))      # creates the underlying cudaEvent_t
+        handles = (C.c_void_p * (self.E + 1))(*[ev.cuda_event for ev in events])
+        self.lib.check(self.lib.dll.mmn_plan_set_grad_events(self.plan, handles, self.E + 1))
+        self.grad_events = events
+        self.comm_stream = torch.cuda.Stream(self.device)
 
     # ------------------------------------------------------------------------------------------
     def ensure_packed(self):
@@ -317,11 +330,35 @@ class MultiModN(nn.Module):
         rt = self.runtime()
         rt.ensure_packed()
         dist.broadcast(rt.flat, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        if self._dp[0] > 1 and rt.layerwise and self.device.type == "cuda":
+            rt.enable_grad_events()
         return self
 
     def _allreduce(self, tensor):
         if self._dp and self._dp[0] > 1:
             torch.distributed.all_reduce(tensor, group=self._dp[2])
+
+    def _allreduce_grads(self, rt, seq):
+        """Gradient all-reduce of one train step.  Fused single-launch plans: one collective over the packed buffer.
+        Layer-wise (bf16) plans: one collective per encoder block, in the order the backward pass finishes them, on a side
+        stream behind the block's gradient-ready event, so that it overlaps the remaining backward GEMMs."""
+        if not (self._dp and self._dp[0] > 1):
+            return
+        if not rt.grad_events:
+            torch.distributed.all_reduce(rt.gflat, group=self._dp[2])
+            return
+        main = torch.cuda.current_stream(self.device)
+        comm = rt.comm_stream
+        in_seq = [e for _, e in reversed(seq)]
+        with torch.cuda.stream(comm):
+            for e in in_seq:
+                comm.wait_event(rt.grad_events[e])
+                lo, hi = rt.packed.encoder_range(e)
+                torch.distributed.all_reduce(rt.gflat[lo:hi], group=self._dp[2])
+            comm.wait_event(rt.grad_events[rt.E])
+            for lo, hi in rt.packed.complement_ranges(in_seq, rt.n_grads):
+                torch.distributed.all_reduce(rt.gflat[lo:hi], group=self._dp[2])
+        main.wait_stream(comm)
 
     # -- the encoding sequence (multimodn.py:509-531) --------------------------------------------
     def get_encoder_iterable(self, encoder_sequence, shuffle_mode: bool, train: bool) -> List[Tuple[int, int]]:
@@ -390,7 +427,7 @@ class MultiModN(nn.Module):
                 batch_metrics.zero_()
             rt.train_step(mb, n_rows, float(self.err_penalty), float(self.state_change_penalty), True,
                           batch_metrics if batch_metrics is not None else epoch_metrics)
-            self._allreduce(rt.gflat)
+            self._allreduce_grads(rt, seq)
             if fused_opt:
                 optimizer.step()                # reads the packed gradient on the device: no host sync
             else:

@@ -186,6 +186,23 @@ class PackedModel:
                               C.cast(encs, C.POINTER(_lib.EncoderDesc)), C.cast(decs, C.POINTER(_lib.DecoderDesc)))
         return desc, (encs, decs)
 
+    def encoder_range(self, e: int):
+        """[lo, hi) of encoder e's parameters in the packed buffer (contiguous: layers are packed in order)"""
+        offs = [(off, off + p.numel()) for p, off, owner in self.slots if owner == e]
+        return min(lo for lo, _ in offs), max(hi for _, hi in offs)
+
+    def complement_ranges(self, encoders, total: int):
+        """what is left of [0, total) once the blocks of `encoders` are removed, as a list of [lo, hi)"""
+        taken = sorted(self.encoder_range(e) for e in encoders)
+        out, at = [], 0
+        for lo, hi in taken:
+            if lo > at:
+                out.append((at, lo))
+            at = max(at, hi)
+        if at < total:
+            out.append((at, total))
+        return out
+
     # -- flat buffer management ----------------------------------------------------------------
     def pack(self, device) -> torch.Tensor:
         flat = torch.zeros(self.n_params, dtype=torch.float32, device=device)
