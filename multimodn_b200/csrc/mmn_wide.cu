@@ -101,9 +101,10 @@ WideTimers g_wt;
 int wide_gemm(int n_sms, const void* A, long long lda, const void* B, long long ldb, long long M, long long N, long long K,
               const wide::Epi& epi, void* stream, const char* what = "gemm", int a_mn = 0, int b_mn = 0) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  alignas(64) CUtensorMap ma, mb;
+  alignas(64) CUtensorMap ma, mb, mb_half;
   if (a_mn ? make_operand_map_mn(&ma, A, M, K, lda) : make_operand_map(&ma, A, M, K, lda, wide::BM)) return 1;
   if (b_mn ? make_operand_map_mn(&mb, B, N, K, ldb) : make_operand_map(&mb, B, N, K, ldb, wide::BN)) return 1;
+  mb_half = mb;
   static bool attr_set = false;
   if (!attr_set) {
     MMN_CUDA(cudaFuncSetAttribute(wide::mmn_wide_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wide::kSmemBytes));
@@ -119,8 +120,17 @@ int wide_gemm(int n_sms, const void* A, long long lda, const void* B, long long 
     while (splits > 1 && (long long)(splits - 1) * ((kb + splits - 1) / splits) >= kb) --splits;     // no empty split
   }
   const int grid = (int)std::min<long long>(tiles * splits, n_sms);
+  // last wave: if the tiles left after the last full wave occupy at most half of the CTAs, run them as 128-column halves
+  int tail_halves = 0;
+  if (splits == 1 && tiles > grid) {
+    const long long rem = tiles % grid;
+    if (rem > 0 && 2 * rem <= grid) {
+      tail_halves = 1;
+      if (!b_mn && make_operand_map(&mb_half, B, N, K, ldb, wide::BN / 2)) return 1;
+    }
+  }
   g_wt.begin(what);
-  wide::mmn_wide_gemm_kernel<<<grid, wide::kThreads, wide::kSmemBytes, (cudaStream_t)stream>>>(ma, mb, (int)M, (int)N, (int)K, splits, a_mn, b_mn, epi);
+  wide::mmn_wide_gemm_kernel<<<grid, wide::kThreads, wide::kSmemBytes, (cudaStream_t)stream>>>(ma, mb, mb_half, (int)M, (int)N, (int)K, splits, a_mn, b_mn, tail_halves, epi);
   g_wt.end();
   MMN_CUDA(cudaGetLastError());
   ++g_wide_launches;

@@ -104,8 +104,9 @@ __device__ __forceinline__ float wide_dact(int act, float a) {      // derivativ
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N, int K,
-                     int splits, int a_mn, int b_mn, const Epi epi) {
+mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                     const __grid_constant__ CUtensorMap map_b_half, int M, int N, int K, int splits, int a_mn, int b_mn,
+                     int tail_halves, const Epi epi) {
   extern __shared__ __align__(1024) char smem_raw[];
   char* base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
   unsigned long long* full = reinterpret_cast<unsigned long long*>(base + STAGES * kStageBytes);
@@ -118,8 +119,16 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   // work item = (output tile, K split): split-K fills the machine when a long contraction has few output tiles (weight
   // gradients); its partial sums are added with fp32 atomics (EPI_ACCUM_F32 only)
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN, n_out_tiles = tiles_m * tiles_n;
-  const int n_tiles = n_out_tiles * splits;
+  // last-wave balancing (tail_halves, only with splits == 1): when the output tiles left over after the last full wave
+  // would keep fewer than half of the CTAs busy, each of them is issued as two 128-column halves instead
+  const int full_items = tail_halves ? (n_out_tiles / (int)gridDim.x) * (int)gridDim.x : n_out_tiles;
+  const int n_tiles = tail_halves ? full_items + 2 * (n_out_tiles - full_items) : n_out_tiles * splits;
   const int kb_all = (K + BK - 1) / BK, kb_per = (kb_all + splits - 1) / splits;
+  // item -> (output tile, K split, column half: -1 = the whole 256-column tile)
+  auto decode = [&](int item, int& tile, int& split, int& nhalf) {
+    if (item < full_items || !tail_halves) { tile = item % n_out_tiles; split = item / n_out_tiles; nhalf = -1; }
+    else { tile = full_items + ((item - full_items) >> 1); split = 0; nhalf = (item - full_items) & 1; }
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
@@ -139,14 +148,15 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     if (elect_one()) {
       Pipe p{0, 0};
       for (int item = blockIdx.x; item < n_tiles; item += gridDim.x) {
-        const int tile = item % n_out_tiles, split = item / n_out_tiles;
-        const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+        int tile, split, nhalf;
+        decode(item, tile, split, nhalf);
+        const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN + (nhalf > 0 ? BN / 2 : 0);
         const int kb0 = split * kb_per, kb1 = min(kb_all, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty + p.stage, p.phase ^ 1u);
           char* sa = base + p.stage * kStageBytes;
           char* sb = sa + BM * BK * 2;
-          mbar_expect_tx(full + p.stage, kStageBytes);
+          mbar_expect_tx(full + p.stage, nhalf < 0 ? kStageBytes : kStageBytes - (BN / 2) * BK * 2);
           if (a_mn) {            // MN-major operand [k rows x mn]: one 64 x 64 box (8 KB, 128-byte rows) per 64 of M
 #pragma unroll
             for (int g = 0; g < BM / 64; ++g) tma_load_2d(&map_a, full + p.stage, sa + g * 8192, m0 + 64 * g, kb * BK);
@@ -155,9 +165,12 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           }
           if (b_mn) {
 #pragma unroll
-            for (int g = 0; g < BN / 64; ++g) tma_load_2d(&map_b, full + p.stage, sb + g * 8192, n0 + 64 * g, kb * BK);
-          } else {
+            for (int g = 0; g < BN / 64; ++g)
+              if (nhalf < 0 || g < BN / 128) tma_load_2d(&map_b, full + p.stage, sb + g * 8192, n0 + 64 * g, kb * BK);
+          } else if (nhalf < 0) {
             tma_load_2d(&map_b, full + p.stage, sb, kb * BK, n0);
+          } else {
+            tma_load_2d(&map_b_half, full + p.stage, sb, kb * BK, n0);
           }
           p.advance();
         }
@@ -166,14 +179,18 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const bool leader = elect_one() != 0;
-    const unsigned idesc = umma_idesc_bf16(BM, BN) | ((unsigned)(a_mn != 0) << 15) | ((unsigned)(b_mn != 0) << 16);
+    const unsigned major_bits = ((unsigned)(a_mn != 0) << 15) | ((unsigned)(b_mn != 0) << 16);
+    const unsigned idesc_full = umma_idesc_bf16(BM, BN) | major_bits, idesc_half = umma_idesc_bf16(BM, BN / 2) | major_bits;
     const unsigned sbase = smem_u32(base);
     Pipe p{0, 0};
     unsigned acc_phase[2] = {0u, 0u};
     int it = 0;
     for (int item = blockIdx.x; item < n_tiles; item += gridDim.x, ++it) {
       const int acc = it & 1;
-      const int kb_n = min(kb_all, (item / n_out_tiles) * kb_per + kb_per) - (item / n_out_tiles) * kb_per;
+      int tile_, split_, nhalf_;
+      decode(item, tile_, split_, nhalf_);
+      const unsigned idesc = nhalf_ < 0 ? idesc_full : idesc_half;
+      const int kb_n = min(kb_all, split_ * kb_per + kb_per) - split_ * kb_per;
       mbar_wait(acc_empty + acc, acc_phase[acc] ^ 1u);
       acc_phase[acc] ^= 1u;
       tc_fence_after();
@@ -212,8 +229,10 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     float sc = 0.f;
     for (int item = blockIdx.x; item < n_tiles; item += gridDim.x, ++it) {
       const int acc = it & 1;
-      const int tile = item % n_out_tiles;
-      const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+      int tile, split_e, nhalf;
+      decode(item, tile, split_e, nhalf);
+      const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN + (nhalf > 0 ? BN / 2 : 0);
+      const int cols = nhalf < 0 ? BN : BN / 2;          // accumulator columns of this item; each warp pair splits them
       const int r = m0 + 32 * q + lane;
       const bool rv = r < M;
       mbar_wait(acc_full + acc, acc_phase[acc]);
@@ -222,7 +241,7 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       const bool skipped = epi.skip && *epi.skip != 0;
       const bool pres = ((epi.present && rv) ? epi.present[r] != 0 : true) && !skipped;
       const bool pair_ok = (r | 1) < M;                // rows r and r ^ 1 both exist: packed transposed stores
-      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 16) {
+      for (int c0 = half * (cols / 2); c0 < (half + 1) * (cols / 2); c0 += 16) {
         float v[16];
         tmem_ld16(tmem + ((unsigned)(32 * q) << 16) + acc * BN + c0, v);     // warp-collective: outside every branch
         const int n = n0 + c0;
