@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MMN_ABI_VERSION 1
+#define MMN_ABI_VERSION 2   /* 2: mmn_model_desc.precision, bf16 plans, gradient-ready events */
 #define MMN_MAX_LAYERS 6      /* Linear layers per encoder / decoder */
 #define MMN_MAX_ENCODERS 16
 #define MMN_MAX_DECODERS 16

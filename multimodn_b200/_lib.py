@@ -14,7 +14,7 @@ MAX_ENCODERS = 16
 MAX_DECODERS = 16
 MAX_CLASSES = 32
 ACT_CODES = {"identity": 0, "relu": 1, "sigmoid": 2, "tanh": 3}
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libmmn.so")
 
