@@ -453,12 +453,10 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
           if (j == dec.n_layers - 1 && j > 0 && dec.C <= 4) {       // decoder head (see decoders_forward)
             const Mat nz = view(dzbuf[cur], ly.in_dim);
             if (!dry) {
-              g_wt.begin("head_wgrad");
-              wide_head_wgrad_kernel<4><<<dim3((unsigned)((ly.in_dim + 2047) / 2048), (unsigned)std::max<long long>(1, std::min<long long>(4 * n_sms, B / 16))),
-                                          256, 0, stream>>>(dz, in, dec.C, B, a.grads + ly.w_off, ly.ktot, a.grads + ly.b_off);
-              if (launched()) return 1;
-              g_wt.begin("head_dgrad");
-              wide_head_dgrad_kernel<<<tgrid(B, ly.in_dim), tb, 0, stream>>>(dz, wbase + w.w, w.ldk, dec.C, in, dec.L[j - 1].act, B, nz);
+              g_wt.begin("head_backward");
+              wide_head_backward_kernel<4><<<dim3((unsigned)((ly.in_dim + 2047) / 2048), (unsigned)std::max<long long>(1, std::min<long long>(4 * n_sms, B / 16))),
+                                             256, 0, stream>>>(dz, in, dec.C, B, a.grads + ly.w_off, ly.ktot, a.grads + ly.b_off,
+                                                               wbase + w.w, w.ldk, dec.L[j - 1].act, nz);
               if (launched()) return 1;
             }
             dz = nz;

@@ -223,7 +223,7 @@ __global__ void wide_state_out_kernel(Mat s, long long rows, float* out) {
 
 
 // ---- decoder head: the last Linear of an MLP decoder (out = n_classes <= 32) is far too skinny for a 128 x 256 tensor-core
-// tile; three bandwidth-bound kernels replace its forward / data-gradient / weight-gradient GEMMs ----
+// tile; two bandwidth-bound kernels replace its forward and its backward (data + weight gradient) GEMMs ----
 // p[r][c] = act(b[c] + sum_k h[r][k] W[c][k])       one warp per row, fp32 accumulation of bf16 products
 template <int CMAX>
 __global__ void __launch_bounds__(256) wide_head_fwd_kernel(Mat h, const bf16* __restrict__ Wb, long long ldk, const float* __restrict__ bias,
@@ -259,45 +259,46 @@ __global__ void __launch_bounds__(256) wide_head_fwd_kernel(Mat h, const bf16* _
     }
   }
 }
-// dh[r][k] = act'(h[r][k]) * sum_c dz[r][c] W[c][k]       (both orientations)
-__global__ void __launch_bounds__(256) wide_head_dgrad_kernel(Mat dz, const bf16* __restrict__ Wb, long long ldk, int C, Mat h,
-                                                              int act_prev, long long rows, Mat out) {
-  tile64_emit([&](long long r, int k, int nv, float (&v)[8]) {
-    float hv[8];
-    load8(h.p + r * h.ld + k, nv, hv);
-    for (int c = 0; c < C; ++c) {
-      float wv[8];
-      load8(Wb + (long long)c * ldk + k, nv, wv);
-      const float d = __bfloat162float(dz.p[r * dz.ld + c]);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = fmaf(d, wv[i], v[i]);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] *= wide_dact(act_prev, hv[i]);
-  }, rows, h.width, out.p, out.ld, out.t, out.ldt, 0);
-}
-// dW[c][k] += sum_r dz[r][c] h[r][k],  db[c] += sum_r dz[r][c]       thread = 8 consecutive k, blockIdx.y = a slice of the rows
+// The head's whole backward in one pass over its input h:  dW[c][k] += sum_r dz[r][c] h[r][k],  db[c] += sum_r dz[r][c]  and
+// dh[r][k] = act'(h[r][k]) * sum_c dz[r][c] W[c][k].   thread = 8 consecutive k, blockIdx.y = a slice of the rows
 template <int CMAX>
-__global__ void __launch_bounds__(256) wide_head_wgrad_kernel(Mat dz, Mat h, int C, long long rows, float* gW, long long ldw, float* gb) {
+__global__ void __launch_bounds__(256) wide_head_backward_kernel(Mat dz, Mat h, int C, long long rows, float* gW, long long ldw, float* gb,
+                                                                 const bf16* __restrict__ Wb, long long ldk, int act_prev, Mat out) {
   const int k0 = (blockIdx.x * 256 + threadIdx.x) * 8;
   const long long per = (rows + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
-  float acc[CMAX][8];
+  float acc[CMAX][8], wv[CMAX][8];
 #pragma unroll
-  for (int c = 0; c < CMAX; ++c)
+  for (int c = 0; c < CMAX; ++c) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[c][i] = 0.f;
+    for (int i = 0; i < 8; ++i) acc[c][i] = wv[c][i] = 0.f;
+    if (c < C && k0 < h.width) load8(Wb + (long long)c * ldk + k0, h.width - k0, wv[c]);
+  }
   if (k0 < h.width) {
+    const int nv = min(8, h.width - k0);
 #pragma unroll 4
     for (long long r = r0; r < r1; ++r) {
-      float hv[8];
-      load8(h.p + r * h.ld + k0, h.width - k0, hv);
+      float hv[8], dh[8];
+      load8(h.p + r * h.ld + k0, nv, hv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dh[i] = 0.f;
 #pragma unroll
       for (int c = 0; c < CMAX; ++c) {
         if (c < C) {
           const float d = __bfloat162float(dz.p[r * dz.ld + c]);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[c][i] = fmaf(d, hv[i], acc[c][i]);
+          for (int i = 0; i < 8; ++i) {
+            acc[c][i] = fmaf(d, hv[i], acc[c][i]);
+            dh[i] = fmaf(d, wv[c][i], dh[i]);
+          }
         }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dh[i] *= wide_dact(act_prev, hv[i]);
+      bf16* op = out.p + r * out.ld + k0;
+      if (nv == 8 && (reinterpret_cast<size_t>(op) & 15) == 0) {
+        *reinterpret_cast<uint4*>(op) = pack8(dh);
+      } else {
+        for (int i = 0; i < nv; ++i) op[i] = __float2bfloat16(dh[i]);
       }
     }
 #pragma unroll
