@@ -115,9 +115,14 @@ int wide_gemm(int n_sms, const void* A, long long lda, const void* B, long long 
   // every split still has a long K range
   int splits = 1;
   if (epi.mode == wide::EPI_ACCUM_F32 && epi.accumulate && !epi.out && !epi.out_t && tiles < n_sms) {
+    // time ~ ceil(tiles * s / SMs) / s waves of the unsplit tile, plus one more fp32 atomic pass over the output per split
     const long long kb = (K + wide::BK - 1) / wide::BK;
-    splits = (int)std::max<long long>(1, std::min<long long>(std::min<long long>((2 * n_sms) / tiles, kb / 16), 16));
-    while (splits > 1 && (long long)(splits - 1) * ((kb + splits - 1) / splits) >= kb) --splits;     // no empty split
+    double best = 1.0;
+    for (int s = 2; s <= 16 && kb / s >= 16; ++s) {
+      if ((long long)(s - 1) * ((kb + s - 1) / s) >= kb) continue;                 // no empty split
+      const double cost = (double)((tiles * s + n_sms - 1) / n_sms) / s + 0.03 * (s - 1);
+      if (cost < best - 1e-9) { best = cost; splits = s; }
+    }
   }
   const int grid = (int)std::min<long long>(tiles * splits, n_sms);
   // last wave: if the tiles left after the last full wave occupy at most half of the CTAs, run them as 128-column halves
