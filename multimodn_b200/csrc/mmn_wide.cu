@@ -107,12 +107,11 @@ int wide_gemm(int n_sms, const void* A, long long lda, const void* B, long long 
   mb_half = mb;
   static bool attr_set = false;
   if (!attr_set) {
-    MMN_CUDA(cudaFuncSetAttribute(wide::mmn_wide_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wide::kSmemBytes));
+    MMN_CUDA(cudaFuncSetAttribute(wide::mmn_wide_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wide::kSmemBytes));
+    MMN_CUDA(cudaFuncSetAttribute(wide::mmn_wide_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wide::kSmemBytes));
     attr_set = true;
   }
   const long long tiles = ((M + wide::BM - 1) / wide::BM) * ((N + wide::BN - 1) / wide::BN);
-  // split-K: only for accumulating fp32 outputs (weight gradients), when the output tiles alone leave SMs idle and
-  // every split still has a long K range
   int splits = 1;
   if (epi.mode == wide::EPI_ACCUM_F32 && epi.accumulate && !epi.out && !epi.out_t && tiles < n_sms) {
     // time ~ ceil(tiles * s / SMs) / s waves of the unsplit tile, plus one more fp32 atomic pass over the output per split
@@ -123,6 +122,32 @@ int wide_gemm(int n_sms, const void* A, long long lda, const void* B, long long 
       const double cost = (double)((tiles * s + n_sms - 1) / n_sms) / s + 0.03 * (s - 1);
       if (cost < best - 1e-9) { best = cost; splits = s; }
     }
+  }
+  // CTA pairs (cta_group::2): 256 x 256 tiles for K-major operands without split-K when there is at least a wave of them;
+  // each CTA then moves 32 KB instead of 48 KB per k-step through the L2 -> SM path that bounds the main loop.
+  // MMN_WIDE_PAIR=0 keeps every GEMM on single CTAs.
+  static const bool no_pair = getenv("MMN_WIDE_PAIR") && !strcmp(getenv("MMN_WIDE_PAIR"), "0");
+  if (!no_pair && !a_mn && !b_mn && splits == 1 && M >= 256 && tiles >= n_sms) {
+    alignas(64) CUtensorMap mb_quarter;
+    if (make_operand_map(&mb_half, B, N, K, ldb, wide::BN / 2) || make_operand_map(&mb_quarter, B, N, K, ldb, wide::BN / 4)) return 1;
+    const long long ptiles = ((M + 2 * wide::BM - 1) / (2 * wide::BM)) * ((N + wide::BN - 1) / wide::BN);
+    const int pairs = (int)std::min<long long>(ptiles, n_sms / 2);
+    const long long prem = ptiles % pairs;
+    const int pair_tail = ptiles > pairs && prem > 0 && 2 * prem <= pairs;        // last wave as 256 x 128 halves
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(wide::kThreads); cfg.dynamicSmemBytes = wide::kSmemBytes;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    g_wt.begin(what);
+    MMN_CUDA(cudaLaunchKernelEx(&cfg, wide::mmn_wide_gemm_kernel<true>, ma, mb_quarter, mb_half, (int)M, (int)N, (int)K, 1, 0, 0, pair_tail, epi));
+    g_wt.end();
+    MMN_CUDA(cudaGetLastError());
+    ++g_wide_launches;
+    return 0;
   }
   const int grid = (int)std::min<long long>(tiles * splits, n_sms);
   // last wave: if the tiles left after the last full wave occupy at most half of the CTAs, run them as 128-column halves
@@ -135,7 +160,7 @@ int wide_gemm(int n_sms, const void* A, long long lda, const void* B, long long 
     }
   }
   g_wt.begin(what);
-  wide::mmn_wide_gemm_kernel<<<grid, wide::kThreads, wide::kSmemBytes, (cudaStream_t)stream>>>(ma, mb, mb_half, (int)M, (int)N, (int)K, splits, a_mn, b_mn, tail_halves, epi);
+  wide::mmn_wide_gemm_kernel<false><<<grid, wide::kThreads, wide::kSmemBytes, (cudaStream_t)stream>>>(ma, mb, mb_half, (int)M, (int)N, (int)K, splits, a_mn, b_mn, tail_halves, epi);
   g_wt.end();
   MMN_CUDA(cudaGetLastError());
   ++g_wide_launches;

@@ -78,11 +78,54 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(map)) : "memory");
 }
 
+
+// ---- CTA pair (cta_group::2): two CTAs of a cluster share one M256 x N256 MMA; each holds its own 128 rows of A and one
+//      half (128 rows) of B in shared memory, the leader (cluster rank 0) issues the MMAs, accumulators stay per CTA ----
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the same shared-memory offset in the leader CTA (bit 24 of a shared::cluster address selects the CTA of the pair)
+constexpr unsigned kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, unsigned long long* leader_bar, void* dst, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0),
+               "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc, unsigned idesc,
+                                               unsigned accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
+      "r"(accumulate) : "memory");
+}
+// tcgen05.commit arriving on the same barrier offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((unsigned short)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(unsigned long long* bar) {      // arrive on the LEADER CTA's copy of `bar`
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, 0;\n\t"
+               "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(unsigned* slot, unsigned ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(unsigned taddr, unsigned ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
 struct Pipe {
   int stage;
   unsigned phase;
-  __device__ __forceinline__ void advance() {
-    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+  __device__ __forceinline__ void advance(int n_stages = STAGES) {
+    if (++stage == n_stages) { stage = 0; phase ^= 1u; }
   }
 };
 
@@ -103,25 +146,33 @@ __device__ __forceinline__ float wide_dact(int act, float a) {      // derivativ
   }
 }
 
+// PAIR = true: launched as clusters of two CTAs working on one 256 x 256 output tile (K-major operands, no split-K);
+// each CTA stages 16 KB of A + 16 KB of B per k-step instead of 16 + 32 and the ring is 6 stages deep.
+constexpr int kPairStages = 6, kPairStageBytes = (BM + BN / 2) * BK * 2;       // 32 KB
+template <bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const __grid_constant__ CUtensorMap map_b_half, int M, int N, int K, int splits, int a_mn, int b_mn,
                      int tail_halves, const Epi epi) {
+  constexpr int NSTG = PAIR ? kPairStages : STAGES, STG = PAIR ? kPairStageBytes : kStageBytes;
   extern __shared__ __align__(1024) char smem_raw[];
   char* base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
-  unsigned long long* full = reinterpret_cast<unsigned long long*>(base + STAGES * kStageBytes);
-  unsigned long long* empty = full + STAGES;
-  unsigned long long* acc_full = empty + STAGES;      // [2]
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(base + NSTG * STG);
+  unsigned long long* empty = full + NSTG;
+  unsigned long long* acc_full = empty + NSTG;      // [2]
   unsigned long long* acc_empty = acc_full + 2;       // [2]
   unsigned* tslot = reinterpret_cast<unsigned*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned pair_rank = PAIR ? cluster_ctarank() : 0u;
+  const int cta_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, n_ctas = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int TILE_M = PAIR ? 2 * BM : BM;
   // work item = (output tile, K split): split-K fills the machine when a long contraction has few output tiles (weight
   // gradients); its partial sums are added with fp32 atomics (EPI_ACCUM_F32 only)
-  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN, n_out_tiles = tiles_m * tiles_n;
+  const int tiles_m = (M + TILE_M - 1) / TILE_M, tiles_n = (N + BN - 1) / BN, n_out_tiles = tiles_m * tiles_n;
   // last-wave balancing (tail_halves, only with splits == 1): when the output tiles left over after the last full wave
   // would keep fewer than half of the CTAs busy, each of them is issued as two 128-column halves instead
-  const int full_items = tail_halves ? (n_out_tiles / (int)gridDim.x) * (int)gridDim.x : n_out_tiles;
+  const int full_items = tail_halves ? (n_out_tiles / n_ctas) * n_ctas : n_out_tiles;
   const int n_tiles = tail_halves ? full_items + 2 * (n_out_tiles - full_items) : n_out_tiles * splits;
   const int kb_all = (K + BK - 1) / BK, kb_per = (kb_all + splits - 1) / splits;
   // item -> (output tile, K split, column half: -1 = the whole 256-column tile)
@@ -131,15 +182,19 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 256); }
+    for (int s = 0; s < NSTG; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, PAIR ? 512 : 256); }
     mbar_fence_init();
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
   }
-  if (warp == 2) tmem_alloc(tslot, 512);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_pair(tslot, 512);
+    else tmem_alloc(tslot, 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();            // barriers of both CTAs are initialised before anyone signals them
+  else __syncthreads();
   tc_fence_after();
   const unsigned tmem = *tslot;
 
@@ -147,15 +202,25 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // ===== TMA producer =====
     if (elect_one()) {
       Pipe p{0, 0};
-      for (int item = blockIdx.x; item < n_tiles; item += gridDim.x) {
+      for (int item = cta_id; item < n_tiles; item += n_ctas) {
         int tile, split, nhalf;
         decode(item, tile, split, nhalf);
-        const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN + (nhalf > 0 ? BN / 2 : 0);
+        const int m0 = (tile % tiles_m) * TILE_M + (int)pair_rank * BM, n0 = (tile / tiles_m) * BN + (nhalf > 0 ? BN / 2 : 0);
         const int kb0 = split * kb_per, kb1 = min(kb_all, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty + p.stage, p.phase ^ 1u);
-          char* sa = base + p.stage * kStageBytes;
+          char* sa = base + p.stage * STG;
           char* sb = sa + BM * BK * 2;
+          if (PAIR) {         // both CTAs load their share; every byte is counted on the leader's barrier
+            // (in a pair launch map_b_half has 128-row boxes = half of a 256-column tile, map_b 64-row boxes = half of a
+            //  128-column tail item)
+            if (pair_rank == 0) mbar_expect_tx(full + p.stage, nhalf < 0 ? 2 * STG : 2 * (STG - (BN / 4) * BK * 2));
+            tma_load_2d_pair(&map_a, full + p.stage, sa, kb * BK, m0);
+            if (nhalf < 0) tma_load_2d_pair(&map_b_half, full + p.stage, sb, kb * BK, n0 + (int)pair_rank * (BN / 2));
+            else tma_load_2d_pair(&map_b, full + p.stage, sb, kb * BK, n0 + (int)pair_rank * (BN / 4));
+            p.advance(NSTG);
+            continue;
+          }
           mbar_expect_tx(full + p.stage, nhalf < 0 ? kStageBytes : kStageBytes - (BN / 2) * BK * 2);
           if (a_mn) {            // MN-major operand [k rows x mn]: one 64 x 64 box (8 KB, 128-byte rows) per 64 of M
 #pragma unroll
@@ -176,16 +241,16 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
+  } else if (warp == 1 && pair_rank == 0) {
+    // ===== MMA issuer (the leader CTA of a pair) =====
     const bool leader = elect_one() != 0;
     const unsigned major_bits = ((unsigned)(a_mn != 0) << 15) | ((unsigned)(b_mn != 0) << 16);
-    const unsigned idesc_full = umma_idesc_bf16(BM, BN) | major_bits, idesc_half = umma_idesc_bf16(BM, BN / 2) | major_bits;
+    const unsigned idesc_full = umma_idesc_bf16(TILE_M, BN) | major_bits, idesc_half = umma_idesc_bf16(TILE_M, BN / 2) | major_bits;
     const unsigned sbase = smem_u32(base);
     Pipe p{0, 0};
     unsigned acc_phase[2] = {0u, 0u};
     int it = 0;
-    for (int item = blockIdx.x; item < n_tiles; item += gridDim.x, ++it) {
+    for (int item = cta_id; item < n_tiles; item += n_ctas, ++it) {
       const int acc = it & 1;
       int tile_, split_, nhalf_;
       decode(item, tile_, split_, nhalf_);
@@ -203,7 +268,7 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         mbar_wait(full + p.stage, p.phase);
         tc_fence_after();
         if (leader) {
-          const unsigned sa = sbase + p.stage * kStageBytes, sb = sa + BM * BK * 2;
+          const unsigned sa = sbase + p.stage * STG, sb = sa + BM * BK * 2;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // K-major: 16 k = 32 bytes inside the swizzled 128-byte row, 8-row atoms 1024 B apart.
@@ -211,13 +276,19 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             //           16 k = two atoms = 2048 bytes.
             const unsigned long long da = a_mn ? umma_smem_desc(sa + 2048u * k, 8192, 1024, 2) : umma_desc_k(sa, k);
             const unsigned long long db = b_mn ? umma_smem_desc(sb + 2048u * k, 8192, 1024, 2) : umma_desc_k(sb, k);
-            umma_bf16(tmem + acc * BN, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (PAIR) umma_bf16_pair(tmem + acc * BN, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else umma_bf16(tmem + acc * BN, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty + p.stage);
-          if (kb == kb_n - 1) umma_commit(acc_full + acc);
+          if (PAIR) {
+            umma_commit_pair(empty + p.stage);
+            if (kb == kb_n - 1) umma_commit_pair(acc_full + acc);
+          } else {
+            umma_commit(empty + p.stage);
+            if (kb == kb_n - 1) umma_commit(acc_full + acc);
+          }
         }
         __syncwarp();
-        p.advance();
+        p.advance(NSTG);
       }
     }
   } else if (warp >= 4) {
@@ -227,11 +298,11 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     unsigned acc_phase[2] = {0u, 0u};
     int it = 0;
     float sc = 0.f;
-    for (int item = blockIdx.x; item < n_tiles; item += gridDim.x, ++it) {
+    for (int item = cta_id; item < n_tiles; item += n_ctas, ++it) {
       const int acc = it & 1;
       int tile, split_e, nhalf;
       decode(item, tile, split_e, nhalf);
-      const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN + (nhalf > 0 ? BN / 2 : 0);
+      const int m0 = (tile % tiles_m) * TILE_M + (int)pair_rank * BM, n0 = (tile / tiles_m) * BN + (nhalf > 0 ? BN / 2 : 0);
       const int cols = nhalf < 0 ? BN : BN / 2;          // accumulator columns of this item; each warp pair splits them
       const int r = m0 + 32 * q + lane;
       const bool rv = r < M;
@@ -413,7 +484,8 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         __syncwarp();                 // the next tcgen05.ld is warp-collective
       }
       tc_fence_before();
-      mbar_arrive(acc_empty + acc);
+      if (PAIR) mbar_arrive_leader(acc_empty + acc);       // the leader's issuer waits for both CTAs' epilogues
+      else mbar_arrive(acc_empty + acc);
     }
     if (epi.sc_sum) {
 #pragma unroll
@@ -422,8 +494,12 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, 512);
+  if (PAIR) cluster_sync_all();            // no CTA leaves while its peer may still signal its barriers / read its smem
+  else __syncthreads();
+  if (warp == 2) {
+    if (PAIR) tmem_dealloc_pair(tmem, 512);
+    else tmem_dealloc(tmem, 512);
+  }
 }
 
 }  // namespace wide

@@ -42,7 +42,9 @@ def test_library_is_sm100a_with_tcgen05(lib_path):
     out = subprocess.run(["cuobjdump", "-lelf", lib_path], capture_output=True, text=True).stdout
     assert "sm_100a" in out
     sass = subprocess.run(["cuobjdump", "-sass", lib_path], capture_output=True, text=True).stdout
-    assert "UTCHMMA" in sass and "LDTM" in sass         # tcgen05.mma / tcgen05.ld of the tensor-core engine
+    assert "UTCHMMA" in sass and "LDTM" in sass         # tcgen05.mma / tcgen05.ld of the tensor-core engines
+    assert "UTMALDG" in sass                            # cp.async.bulk.tensor (TMA) of the wide-regime GEMM
+    assert "UTCHMMA.2CTA" in sass and "UTCBAR.2CTA.MULTICAST" in sass      # its CTA-pair (cta_group::2) variant
 
 
 def test_ctypes_struct_sizes_match_header(tmp_path, lib_path):
