@@ -112,28 +112,35 @@ int wide_gemm(int n_sms, const void* A, long long lda, const void* B, long long 
     attr_set = true;
   }
   const long long tiles = ((M + wide::BM - 1) / wide::BM) * ((N + wide::BN - 1) / wide::BN);
-  int splits = 1;
-  if (epi.mode == wide::EPI_ACCUM_F32 && epi.accumulate && !epi.out && !epi.out_t && tiles < n_sms) {
-    // time ~ ceil(tiles * s / SMs) / s waves of the unsplit tile, plus one more fp32 atomic pass over the output per split
+  const bool splittable = epi.mode == wide::EPI_ACCUM_F32 && epi.accumulate && !epi.out && !epi.out_t;
+  // split-K factor for `n_tiles` output tiles on `n_units` CTAs (or CTA pairs): time ~ ceil(tiles * s / units) / s waves of
+  // the unsplit tile, plus one more fp32 atomic pass over the output per split
+  auto pick_splits = [&](long long n_tiles, int n_units) {
+    int best_s = 1;
+    if (!splittable || n_tiles >= n_units) return best_s;
     const long long kb = (K + wide::BK - 1) / wide::BK;
     double best = 1.0;
     for (int s = 2; s <= 16 && kb / s >= 16; ++s) {
       if ((long long)(s - 1) * ((kb + s - 1) / s) >= kb) continue;                 // no empty split
-      const double cost = (double)((tiles * s + n_sms - 1) / n_sms) / s + 0.03 * (s - 1);
-      if (cost < best - 1e-9) { best = cost; splits = s; }
+      const double cost = (double)((n_tiles * s + n_units - 1) / n_units) / s + 0.03 * (s - 1);
+      if (cost < best - 1e-9) { best = cost; best_s = s; }
     }
-  }
-  // CTA pairs (cta_group::2): 256 x 256 tiles for K-major operands without split-K when there is at least a wave of them;
+    return best_s;
+  };
+  // CTA pairs (cta_group::2): 256 x 256 tiles when both operands have the same orientation and the pairs can be kept busy;
   // each CTA then moves 32 KB instead of 48 KB per k-step through the L2 -> SM path that bounds the main loop.
   // MMN_WIDE_PAIR=0 keeps every GEMM on single CTAs.
   static const bool no_pair = getenv("MMN_WIDE_PAIR") && !strcmp(getenv("MMN_WIDE_PAIR"), "0");
-  if (!no_pair && !a_mn && !b_mn && splits == 1 && M >= 256 && tiles >= n_sms) {
-    alignas(64) CUtensorMap mb_quarter;
-    if (make_operand_map(&mb_half, B, N, K, ldb, wide::BN / 2) || make_operand_map(&mb_quarter, B, N, K, ldb, wide::BN / 4)) return 1;
-    const long long ptiles = ((M + 2 * wide::BM - 1) / (2 * wide::BM)) * ((N + wide::BN - 1) / wide::BN);
-    const int pairs = (int)std::min<long long>(ptiles, n_sms / 2);
+  const long long ptiles = ((M + 2 * wide::BM - 1) / (2 * wide::BM)) * ((N + wide::BN - 1) / wide::BN);
+  const int n_pairs = n_sms / 2;
+  if (!no_pair && a_mn == b_mn && M >= 256 && (tiles >= n_sms || (splittable && 2 * ptiles >= n_pairs))) {
+    alignas(64) CUtensorMap mb_quarter = mb;
+    if (!b_mn && (make_operand_map(&mb_half, B, N, K, ldb, wide::BN / 2) || make_operand_map(&mb_quarter, B, N, K, ldb, wide::BN / 4)))
+      return 1;
+    const int psplits = pick_splits(ptiles, n_pairs);
+    const int pairs = (int)std::min<long long>(ptiles * psplits, n_pairs);
     const long long prem = ptiles % pairs;
-    const int pair_tail = ptiles > pairs && prem > 0 && 2 * prem <= pairs;        // last wave as 256 x 128 halves
+    const int pair_tail = psplits == 1 && ptiles > pairs && prem > 0 && 2 * prem <= pairs;        // last wave as 256 x 128 halves
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(wide::kThreads); cfg.dynamicSmemBytes = wide::kSmemBytes;
@@ -143,12 +150,14 @@ int wide_gemm(int n_sms, const void* A, long long lda, const void* B, long long 
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     g_wt.begin(what);
-    MMN_CUDA(cudaLaunchKernelEx(&cfg, wide::mmn_wide_gemm_kernel<true>, ma, mb_quarter, mb_half, (int)M, (int)N, (int)K, 1, 0, 0, pair_tail, epi));
+    MMN_CUDA(cudaLaunchKernelEx(&cfg, wide::mmn_wide_gemm_kernel<true>, ma, mb_quarter, mb_half, (int)M, (int)N, (int)K, psplits, a_mn, b_mn,
+                                pair_tail, epi));
     g_wt.end();
     MMN_CUDA(cudaGetLastError());
     ++g_wide_launches;
     return 0;
   }
+  const int splits = pick_splits(tiles, n_sms);
   const int grid = (int)std::min<long long>(tiles * splits, n_sms);
   // last wave: if the tiles left after the last full wave occupy at most half of the CTAs, run them as 128-column halves
   int tail_halves = 0;

@@ -215,9 +215,22 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             // (in a pair launch map_b_half has 128-row boxes = half of a 256-column tile, map_b 64-row boxes = half of a
             //  128-column tail item)
             if (pair_rank == 0) mbar_expect_tx(full + p.stage, nhalf < 0 ? 2 * STG : 2 * (STG - (BN / 4) * BK * 2));
-            tma_load_2d_pair(&map_a, full + p.stage, sa, kb * BK, m0);
-            if (nhalf < 0) tma_load_2d_pair(&map_b_half, full + p.stage, sb, kb * BK, n0 + (int)pair_rank * (BN / 2));
-            else tma_load_2d_pair(&map_b, full + p.stage, sb, kb * BK, n0 + (int)pair_rank * (BN / 4));
+            if (a_mn) {
+#pragma unroll
+              for (int g = 0; g < BM / 64; ++g) tma_load_2d_pair(&map_a, full + p.stage, sa + g * 8192, m0 + 64 * g, kb * BK);
+            } else {
+              tma_load_2d_pair(&map_a, full + p.stage, sa, kb * BK, m0);
+            }
+            const int nb0 = n0 + (int)pair_rank * (nhalf < 0 ? BN / 2 : BN / 4);      // this CTA's share of the B columns
+            if (b_mn) {
+#pragma unroll
+              for (int g = 0; g < BN / 128; ++g)
+                if (nhalf < 0 || g == 0) tma_load_2d_pair(&map_b, full + p.stage, sb + g * 8192, nb0 + 64 * g, kb * BK);
+            } else if (nhalf < 0) {
+              tma_load_2d_pair(&map_b_half, full + p.stage, sb, kb * BK, nb0);
+            } else {
+              tma_load_2d_pair(&map_b, full + p.stage, sb, kb * BK, nb0);
+            }
             p.advance(NSTG);
             continue;
           }
