@@ -36,7 +36,8 @@ def run_gemm(M, N, K, lda=None, ldb=None, seed=0):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 256), (256, 512, 2048), (384, 768, 1024),
-                                   (100, 40, 72), (8192, 2048, 2048), (130, 258, 200), (2, 2048, 2048), (2048, 2, 512)])
+                                   (100, 40, 72), (8192, 2048, 2048), (130, 258, 200), (2, 2048, 2048), (2048, 2, 512),
+                                   (1000, 5000, 200), (4096 + 130, 1024 + 24, 136)])     # ragged tiles on CTA pairs
 def test_gemm_matches_torch(M, N, K):
     out, ob, ot, want = run_gemm(M, N, K, lda=(K + 7) // 8 * 8, ldb=(K + 7) // 8 * 8)
     scale = want.abs().max().item() + 1e-30
@@ -51,7 +52,7 @@ def test_gemm_pitched_operands():
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 512), (2048, 1024, 8192), (100, 40, 72), (130, 258, 200),
-                                   (2, 2048, 517), (2048, 3072, 300)])
+                                   (2, 2048, 517), (2048, 3072, 300), (1000, 5000, 200)])
 def test_gemm_mn_major_operands(M, N, K):
     """both operands contracted over their ROWS (the weight-gradient form dW = dZ^T . In without transposed copies)"""
     from multimodn_b200 import _lib
@@ -70,3 +71,4 @@ def test_gemm_mn_major_operands(M, N, K):
     torch.cuda.synchronize()
     want = a[:, :M].float().T @ b[:, :N].float()
     assert (out - want).abs().max().item() <= 1e-5 * want.abs().max().item() * max(1.0, (K / 64) ** 0.5)
+
