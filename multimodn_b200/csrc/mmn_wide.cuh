@@ -153,7 +153,7 @@ template <bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const __grid_constant__ CUtensorMap map_b_half, int M, int N, int K, int splits, int a_mn, int b_mn,
-                     int tail_halves, const Epi epi) {
+                     int tail_div, const Epi epi) {
   constexpr int NSTG = PAIR ? kPairStages : STAGES, STG = PAIR ? kPairStageBytes : kStageBytes;
   extern __shared__ __align__(1024) char smem_raw[];
   char* base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
@@ -170,15 +170,16 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   // work item = (output tile, K split): split-K fills the machine when a long contraction has few output tiles (weight
   // gradients); its partial sums are added with fp32 atomics (EPI_ACCUM_F32 only)
   const int tiles_m = (M + TILE_M - 1) / TILE_M, tiles_n = (N + BN - 1) / BN, n_out_tiles = tiles_m * tiles_n;
-  // last-wave balancing (tail_halves, only with splits == 1): when the output tiles left over after the last full wave
-  // would keep fewer than half of the CTAs busy, each of them is issued as two 128-column halves instead
-  const int full_items = tail_halves ? (n_out_tiles / n_ctas) * n_ctas : n_out_tiles;
-  const int n_tiles = tail_halves ? full_items + 2 * (n_out_tiles - full_items) : n_out_tiles * splits;
+  // last-wave balancing (tail_div = 2 or 4, only with splits == 1): the output tiles left over after the last full wave are
+  // issued as tail_div column slices of BN / tail_div columns each, so that the last wave is shorter instead of emptier
+  const int full_items = tail_div > 1 ? (n_out_tiles / n_ctas) * n_ctas : n_out_tiles;
+  const int n_tiles = tail_div > 1 ? full_items + tail_div * (n_out_tiles - full_items) : n_out_tiles * splits;
+  const int tail_w = tail_div > 1 ? BN / tail_div : BN;
   const int kb_all = (K + BK - 1) / BK, kb_per = (kb_all + splits - 1) / splits;
-  // item -> (output tile, K split, column half: -1 = the whole 256-column tile)
+  // item -> (output tile, K split, column slice: -1 = the whole 256-column tile)
   auto decode = [&](int item, int& tile, int& split, int& nhalf) {
-    if (item < full_items || !tail_halves) { tile = item % n_out_tiles; split = item / n_out_tiles; nhalf = -1; }
-    else { tile = full_items + ((item - full_items) >> 1); split = 0; nhalf = (item - full_items) & 1; }
+    if (item < full_items || tail_div <= 1) { tile = item % n_out_tiles; split = item / n_out_tiles; nhalf = -1; }
+    else { tile = full_items + (item - full_items) / tail_div; split = 0; nhalf = (item - full_items) % tail_div; }
   };
 
   if (threadIdx.x == 0) {
@@ -205,7 +206,7 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       for (int item = cta_id; item < n_tiles; item += n_ctas) {
         int tile, split, nhalf;
         decode(item, tile, split, nhalf);
-        const int m0 = (tile % tiles_m) * TILE_M + (int)pair_rank * BM, n0 = (tile / tiles_m) * BN + (nhalf > 0 ? BN / 2 : 0);
+        const int m0 = (tile % tiles_m) * TILE_M + (int)pair_rank * BM, n0 = (tile / tiles_m) * BN + (nhalf > 0 ? nhalf * tail_w : 0);
         const int kb0 = split * kb_per, kb1 = min(kb_all, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty + p.stage, p.phase ^ 1u);
@@ -214,18 +215,19 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           if (PAIR) {         // both CTAs load their share; every byte is counted on the leader's barrier
             // (in a pair launch map_b_half has 128-row boxes = half of a 256-column tile, map_b 64-row boxes = half of a
             //  128-column tail item)
-            if (pair_rank == 0) mbar_expect_tx(full + p.stage, nhalf < 0 ? 2 * STG : 2 * (STG - (BN / 4) * BK * 2));
+            // a pair launch gets map_b_half with 128-row boxes (half of a full tile) and map_b with tail_w / 2-row boxes
+            if (pair_rank == 0) mbar_expect_tx(full + p.stage, 2 * (BM * BK * 2 + (nhalf < 0 ? BN / 2 : tail_w / 2) * BK * 2));
             if (a_mn) {
 #pragma unroll
               for (int g = 0; g < BM / 64; ++g) tma_load_2d_pair(&map_a, full + p.stage, sa + g * 8192, m0 + 64 * g, kb * BK);
             } else {
               tma_load_2d_pair(&map_a, full + p.stage, sa, kb * BK, m0);
             }
-            const int nb0 = n0 + (int)pair_rank * (nhalf < 0 ? BN / 2 : BN / 4);      // this CTA's share of the B columns
+            const int nb0 = n0 + (int)pair_rank * (nhalf < 0 ? BN / 2 : tail_w / 2);      // this CTA's share of the B columns
             if (b_mn) {
 #pragma unroll
               for (int g = 0; g < BN / 128; ++g)
-                if (nhalf < 0 || g == 0) tma_load_2d_pair(&map_b, full + p.stage, sb + g * 8192, nb0 + 64 * g, kb * BK);
+                if (nhalf < 0 || g < tail_w / 128) tma_load_2d_pair(&map_b, full + p.stage, sb + g * 8192, nb0 + 64 * g, kb * BK);
             } else if (nhalf < 0) {
               tma_load_2d_pair(&map_b_half, full + p.stage, sb, kb * BK, nb0);
             } else {
@@ -234,7 +236,7 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             p.advance(NSTG);
             continue;
           }
-          mbar_expect_tx(full + p.stage, nhalf < 0 ? kStageBytes : kStageBytes - (BN / 2) * BK * 2);
+          mbar_expect_tx(full + p.stage, nhalf < 0 ? kStageBytes : (BM + tail_w) * BK * 2);
           if (a_mn) {            // MN-major operand [k rows x mn]: one 64 x 64 box (8 KB, 128-byte rows) per 64 of M
 #pragma unroll
             for (int g = 0; g < BM / 64; ++g) tma_load_2d(&map_a, full + p.stage, sa + g * 8192, m0 + 64 * g, kb * BK);
@@ -244,7 +246,7 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           if (b_mn) {
 #pragma unroll
             for (int g = 0; g < BN / 64; ++g)
-              if (nhalf < 0 || g < BN / 128) tma_load_2d(&map_b, full + p.stage, sb + g * 8192, n0 + 64 * g, kb * BK);
+              if (nhalf < 0 || g < tail_w / 64) tma_load_2d(&map_b, full + p.stage, sb + g * 8192, n0 + 64 * g, kb * BK);
           } else if (nhalf < 0) {
             tma_load_2d(&map_b, full + p.stage, sb, kb * BK, n0);
           } else {
@@ -258,7 +260,7 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // ===== MMA issuer (the leader CTA of a pair) =====
     const bool leader = elect_one() != 0;
     const unsigned major_bits = ((unsigned)(a_mn != 0) << 15) | ((unsigned)(b_mn != 0) << 16);
-    const unsigned idesc_full = umma_idesc_bf16(TILE_M, BN) | major_bits, idesc_half = umma_idesc_bf16(TILE_M, BN / 2) | major_bits;
+    const unsigned idesc_full = umma_idesc_bf16(TILE_M, BN) | major_bits, idesc_half = umma_idesc_bf16(TILE_M, tail_w) | major_bits;
     const unsigned sbase = smem_u32(base);
     Pipe p{0, 0};
     unsigned acc_phase[2] = {0u, 0u};
@@ -315,8 +317,8 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       const int acc = it & 1;
       int tile, split_e, nhalf;
       decode(item, tile, split_e, nhalf);
-      const int m0 = (tile % tiles_m) * TILE_M + (int)pair_rank * BM, n0 = (tile / tiles_m) * BN + (nhalf > 0 ? BN / 2 : 0);
-      const int cols = nhalf < 0 ? BN : BN / 2;          // accumulator columns of this item; each warp pair splits them
+      const int m0 = (tile % tiles_m) * TILE_M + (int)pair_rank * BM, n0 = (tile / tiles_m) * BN + (nhalf > 0 ? nhalf * tail_w : 0);
+      const int cols = nhalf < 0 ? BN : tail_w;          // accumulator columns of this item; each warp pair splits them
       const int r = m0 + 32 * q + lane;
       const bool rv = r < M;
       mbar_wait(acc_full + acc, acc_phase[acc]);
