@@ -172,3 +172,23 @@ def test_wide_shard_additivity():
     assert_close(g2[:rt.packed.n_params], g1[:rt.packed.n_params], rtol=1e-4, what="sharded grads == full-batch grads")
     assert (g2[rt.packed.n_params:] == g1[rt.packed.n_params:]).all()          # present-row counts
     assert_close(m2, m1, rtol=1e-5, what="sharded metrics == full-batch metrics")
+
+
+def test_wide_test_epoch_history_and_outputs():
+    """MultiModN.test() on a bf16 plan: the 'val' history row and the collected last-step outputs follow the oracle"""
+    S, feats, B = 48, [64, 40], 384
+    rng = np.random.default_rng(21)
+    spec = random_spec(rng, S, feats, enc_kind="mimic", enc_hidden=(96, 64), dropout=0.0, n_decoders=2, dec_hidden=(32,), n_classes=2)
+    data, y = synthetic_batch(rng, feats, 2, B, mnar=True)
+    model = model_from_spec(spec, 1.0, 0.3, DEV, "row", precision="bf16")
+    hist = MultiModNHistory(["a", "b"])
+    loader = [([torch.from_numpy(x[i:i + 128]).to(DEV) for x in data], torch.from_numpy(y[i:i + 128]).to(DEV)) for i in range(0, B, 128)]
+    results = model.test(loader, CrossEntropyLoss(), hist, tag="val")
+    assert len(results) == 2
+    ospec = dict(O.cast_spec(spec, np.float32), precision="bf16")
+    acc = O.EpochAccumulator(len(feats), 2)
+    for i in range(0, B, 128):
+        acc.add(O.forward(ospec, [x[i:i + 128] for x in data], y[i:i + 128], None, "row"))
+    fin = acc.finalize()
+    assert_close(hist.loss["val"][0], fin["loss"], rtol=1e-4, what="val loss")
+    np.testing.assert_allclose(np.nan_to_num(hist.accuracy["val"][0]), np.nan_to_num(fin["accuracy"]), atol=0.01)
