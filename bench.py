@@ -325,7 +325,8 @@ def main():
     wide_l0 = int(rt.lib.dll.mmn_wide_launch_count())
     kms = timed(kernel_only, K) / K
     wide_launches_per_step = (int(rt.lib.dll.mmn_wide_launch_count()) - wide_l0) // K
-    for _ in range(3):                                # keep the load on while nvidia-smi gets a few samples in
+    t_load = time.perf_counter()                      # keep the load on until nvidia-smi has a few samples in
+    while len(clk.rows) < 6 and time.perf_counter() - t_load < 4.0:
         timed(kernel_only, K)
     clk.__exit__()
     clocks = clk.summary()
