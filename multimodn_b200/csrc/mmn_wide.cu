@@ -268,21 +268,27 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
     return wide_gemm(n_sms, dz.p, dz.ld, wbase + w.w + col0, w.ldk, B, n, l.out_dim, e, stream, what, 0, 1);
   };
 
+  void* cast_jobs_dev = ar.take(sizeof(CastJobs));
   // ---- 0. bf16 copies of the weights (both orientations) ----
   if (!dry) {
-    auto cast = [&](const DevLayer& l, const mmn_plan::WL& w) -> int {
-      g_wt.begin("cast_weight");
-      // the transposed copy only serves data-gradient GEMMs whose weight sub-block is not 16-byte aligned in W itself
-      wide_cast_weight_kernel<<<tgrid(l.out_dim, l.ktot), tb, 0, stream>>>(a.params + l.w_off, l.out_dim, l.ktot, wbase + w.w, w.ldk,
-                                                                           needs_wt(l) ? wbase + w.wt : nullptr, w.ldo);
-      return launched();
+    CastJobs jobs;
+    int n_jobs = 0, max_out = 0, max_k = 0;
+    auto add = [&](const DevLayer& l, const mmn_plan::WL& w) {
+      CastJob& j = jobs.job[n_jobs++];
+      j.W = a.params + l.w_off; j.Wb = wbase + w.w; j.WbT = needs_wt(l) ? wbase + w.wt : nullptr;
+      j.out = l.out_dim; j.ktot = l.ktot; j.ldk = w.ldk; j.ldo = w.ldo;
+      max_out = std::max(max_out, l.out_dim); max_k = std::max(max_k, l.ktot);
     };
     for (int e = 0; e < E; ++e)
-      for (int j = 0; j < P.enc[e].n_layers; ++j)
-        if (cast(P.enc[e].L[j], plan->wide_enc[e][j])) return 1;
+      for (int j = 0; j < P.enc[e].n_layers; ++j) add(P.enc[e].L[j], plan->wide_enc[e][j]);
     for (int d = 0; d < D; ++d)
-      for (int j = 0; j < P.dec[d].n_layers; ++j)
-        if (cast(P.dec[d].L[j], plan->wide_dec[d][j])) return 1;
+      for (int j = 0; j < P.dec[d].n_layers; ++j) add(P.dec[d].L[j], plan->wide_dec[d][j]);
+    // the job table travels through the head of the workspace (re-sent every call: params may move between calls)
+    MMN_CUDA(cudaMemcpyAsync(cast_jobs_dev, &jobs, sizeof(CastJob) * n_jobs, cudaMemcpyHostToDevice, stream));
+    g_wt.begin("cast_weight");
+    wide_cast_weights_kernel<<<dim3((unsigned)((max_k + 63) / 64), (unsigned)((max_out + 63) / 64), (unsigned)n_jobs), 256, 0, stream>>>(
+        (const CastJobs*)cast_jobs_dev);
+    if (launched()) return 1;
   }
 
   // ---- persistent buffers ----

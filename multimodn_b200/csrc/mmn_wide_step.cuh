@@ -106,10 +106,16 @@ __device__ __forceinline__ void tile64_emit(F value8, long long rows, int width,
   }
 }
 
-// fp32 master weight [out x ktot] -> bf16 W (pitch ldk) and W^T [ktot x out] (pitch ldo)
-__global__ void __launch_bounds__(256) wide_cast_weight_kernel(const float* __restrict__ W, int out, int ktot, bf16* Wb, long long ldk,
-                                                               bf16* WbT, long long ldo) {
-  tile64_emit([&](long long r, int c, int nv, float (&v)[8]) { load8(W + r * ktot + c, nv, v); }, out, ktot, Wb, ldk, WbT, ldo, 0);
+// fp32 master weights -> bf16 W (pitch ldk) and W^T [ktot x out] (pitch ldo), every layer of the model in ONE launch:
+// blockIdx.z selects the layer, blocks outside its extent leave at once
+struct CastJob { const float* W; bf16* Wb; bf16* WbT; int out, ktot; long long ldk, ldo; };
+constexpr int kMaxCastJobs = (MMN_MAX_ENCODERS + MMN_MAX_DECODERS) * MMN_MAX_LAYERS;
+struct CastJobs { CastJob job[kMaxCastJobs]; };
+__global__ void __launch_bounds__(256) wide_cast_weights_kernel(const CastJobs* __restrict__ jobs) {
+  const CastJob j = jobs->job[blockIdx.z];
+  if ((int)blockIdx.x * 64 >= j.ktot || (int)blockIdx.y * 64 >= j.out) return;
+  tile64_emit([&](long long r, int c, int nv, float (&v)[8]) { load8(j.W + r * j.ktot + c, nv, v); }, j.out, j.ktot, j.Wb, j.ldk,
+              j.WbT, j.ldo, 0);
 }
 // features of one modality -> columns [0, F) of the first layer's input; NaN -> 0 and the row is marked absent
 __global__ void __launch_bounds__(256) wide_input_x_kernel(const float* __restrict__ x, long long x_ld, long long rows, int F, Mat in,
