@@ -192,6 +192,11 @@ extern "C" void mmn_plan_destroy(mmn_plan* plan) {
   if (!plan) return;
   if (plan->dev) cudaFree(plan->dev);
   if (plan->wide_w) cudaFree(plan->wide_w);
+#ifndef MMN_EMU
+  if (plan->side_stream) cudaStreamDestroy((cudaStream_t)plan->side_stream);
+  if (plan->side_fork) cudaEventDestroy((cudaEvent_t)plan->side_fork);
+  if (plan->side_done) cudaEventDestroy((cudaEvent_t)plan->side_done);
+#endif
   delete plan;
 }
 

@@ -28,6 +28,11 @@ struct mmn_plan {
   struct WL { long long w, wt; int ldk, ldo; };
   WL wide_enc[MMN_MAX_ENCODERS][MMN_MAX_LAYERS];
   WL wide_dec[MMN_MAX_DECODERS][MMN_MAX_LAYERS];
+  // layer-wise plans: an internal side stream (forked from / joined to the caller's stream with events) on which the small
+  // bias-gradient reductions run concurrently with the weight-gradient GEMMs
+  void* side_stream = nullptr;
+  void* side_fork = nullptr;     // cudaEvent_t: caller's stream -> side stream
+  void* side_done = nullptr;     // cudaEvent_t: side stream -> caller's stream
   // optional cudaEvent_t handles recorded by mmn_train_step as gradient blocks become final (mmn_plan_set_grad_events)
   void* grad_events[MMN_MAX_ENCODERS + 1] = {};
   int n_grad_events = 0;

@@ -228,6 +228,12 @@ int mmn_wide_plan_init(mmn_plan* p) {
   for (int d = 0; d < P.D; ++d)
     for (int j = 0; j < P.dec[d].n_layers; ++j) place(P.dec[d].L[j], p->wide_dec[d][j]);
   p->wide_elems = off;
+  cudaStream_t side;
+  cudaEvent_t fork, done;
+  MMN_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+  MMN_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+  MMN_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+  p->side_stream = side; p->side_fork = fork; p->side_done = done;
   MMN_CUDA(cudaMalloc(&p->wide_w, (size_t)off * 2));
   MMN_CUDA(cudaMemset(p->wide_w, 0, (size_t)off * 2));
   return 0;
@@ -483,12 +489,31 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
     };
     if (!dry) MMN_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * (size_t)B * S, stream));
     // gradients of one layer given dz (both orientations) and the layer's input
+    // the bias-gradient reductions only read dz: they run on the plan's side stream, next to the weight-gradient GEMM of
+    // the same layer; the caller's stream waits for them before anything may overwrite a dz buffer (join_side)
+    const cudaStream_t side = (cudaStream_t)plan->side_stream;
+    const bool use_side = side && !g_wt.on;
+    bool side_pending = false;
+    auto join_side = [&]() -> int {
+      if (side_pending) { MMN_CUDA(cudaStreamWaitEvent(stream, (cudaEvent_t)plan->side_done, 0)); side_pending = false; }
+      return 0;
+    };
     auto layer_param_grads = [&](const DevLayer& ly, const Mat& dz, const Mat& in) -> int {
       if (dry) return 0;
-      g_wt.begin("bias_grad");
-      wide_bias_grad_kernel<<<dim3((unsigned)((ly.out_dim + 63) / 64), (unsigned)std::max<long long>(1, std::min<long long>(32, B / 256))),
-                              256, 0, stream>>>(dz.p, dz.ld, B, ly.out_dim, a.grads + ly.b_off);
-      if (launched()) return 1;
+      const dim3 bgrid((unsigned)((ly.out_dim + 63) / 64), (unsigned)std::max<long long>(1, std::min<long long>(32, B / 256)));
+      if (use_side) {
+        MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->side_fork, stream));
+        MMN_CUDA(cudaStreamWaitEvent(side, (cudaEvent_t)plan->side_fork, 0));
+        wide_bias_grad_kernel<<<bgrid, 256, 0, side>>>(dz.p, dz.ld, B, ly.out_dim, a.grads + ly.b_off);
+        MMN_CUDA(cudaGetLastError());
+        ++g_wide_launches;
+        MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->side_done, side));
+        side_pending = true;
+      } else {
+        g_wt.begin("bias_grad");
+        wide_bias_grad_kernel<<<bgrid, 256, 0, stream>>>(dz.p, dz.ld, B, ly.out_dim, a.grads + ly.b_off);
+        if (launched()) return 1;
+      }
       Epi e = epi0();
       e.mode = EPI_ACCUM_F32; e.accumulate = 1;
       e.out_f32 = a.grads + ly.w_off; e.ld_f32 = ly.ktot;
@@ -506,6 +531,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
           if (j == dec.n_layers - 1 && j > 0 && dec.C <= 4) {       // decoder head (see decoders_forward)
             const Mat nz = view(dzbuf[cur], ly.in_dim);
             if (!dry) {
+              if (join_side()) return 1;
               g_wt.begin("head_backward");
               wide_head_backward_kernel<4><<<dim3((unsigned)((ly.in_dim + 2047) / 2048), (unsigned)std::max<long long>(1, std::min<long long>(4 * n_sms, B / 16))),
                                              256, 0, stream>>>(dz, in, dec.C, B, a.grads + ly.w_off, ly.ktot, a.grads + ly.b_off,
@@ -520,6 +546,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
           Epi e = epi0();
           if (j > 0) {
             const Mat nz = view(dzbuf[cur], ly.in_dim);
+            if (!dry && join_side()) return 1;
             e.mode = EPI_DACT; e.act = dec.L[j - 1].act;
             e.aux = in.p; e.ld_aux = in.ld;
             e.out = nz.p; e.ld_out = nz.ld; e.out_t = nz.t; e.ld_out_t = nz.ldt;
@@ -546,6 +573,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
       Mat dz = view(dzbuf[cur], S);
       cur ^= 1;
       if (!dry) {
+        if (join_side()) return 1;
         g_wt.begin("state_grad");
         wide_state_grad_kernel<<<tgrid(B, S), tb, 0, stream>>>(G, Sk[k], Sk[k - 1], pres, skip, a.c_sc, enc.L[nl - 1].act, B, dz);
         if (launched()) return 1;
@@ -574,6 +602,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
         if (j > 0) {
           const Mat nz = view(dzbuf[cur], ly.in_dim);
           Epi ep = epi0();
+          if (!dry && join_side()) return 1;
           ep.mode = EPI_DACT; ep.act = enc.L[j - 1].act;
           ep.aux = in.p; ep.ld_aux = in.ld;
           ep.out = nz.p; ep.ld_out = nz.ld; ep.out_t = nz.t; ep.ld_out_t = nz.ldt;
@@ -583,10 +612,15 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
         }
       }
       // encoder e's parameter gradients are final: let the caller start reducing them across ranks
-      if (!dry && plan->n_grad_events) { MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->grad_events[e], stream)); ev_done |= 1u << e; }
+      if (!dry && plan->n_grad_events) {
+        if (join_side()) return 1;
+        MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->grad_events[e], stream));
+        ev_done |= 1u << e;
+      }
     }
     if (decoders_backward(0)) return 1;
     if (!dry) {
+      if (join_side()) return 1;
       g_wt.begin("colsum_f32");
       wide_colsum_f32_kernel<<<dim3((unsigned)((S + 31) / 32), 16), 256, 0, stream>>>(G, B, S, a.grads + P.init_off);
       if (launched()) return 1;
