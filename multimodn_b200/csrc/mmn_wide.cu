@@ -336,7 +336,16 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
   };
 
   // ---- decoders on s_k ----
+  // Training: the decoders of step k only need s_k, and so does the encoder of step k + 1 — the decoder chains run on the
+  // plan's side stream (forked after s_k is final, joined before the backward pass) next to the following encoder's GEMMs,
+  // which fills the tails of both and hides the small head / loss kernels.
+  const bool fwd_side = TRAIN && !dry && plan->side_stream && !g_wt.on;
+  const cudaStream_t ds = fwd_side ? (cudaStream_t)plan->side_stream : stream;
   auto decoders_forward = [&](int k, int hist_row, bool is_last_enc, const int* skip) -> int {
+    if (fwd_side) {
+      MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->side_fork, stream));
+      MMN_CUDA(cudaStreamWaitEvent(ds, (cudaEvent_t)plan->side_fork, 0));
+    }
     for (int d = 0; d < D; ++d) {
       const DevDecoder& dec = P.dec[d];
       Mat in = Sk[k];
@@ -357,10 +366,10 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
         if (!dry) {
           if (last && j > 0 && dec.C <= 4) {   // decoder head: skinny, bandwidth-bound kernel instead of a tensor-core tile
             g_wt.begin("head_fwd");
-            wide_head_fwd_kernel<4><<<(unsigned)std::min<long long>((B + 7) / 8, 8 * n_sms), 256, 0, stream>>>(
+            wide_head_fwd_kernel<4><<<(unsigned)std::min<long long>((B + 7) / 8, 8 * n_sms), 256, 0, ds>>>(
                 in, wbase + w.w, w.ldk, a.params + ly.b_off, dec.C, ly.act, B, Pout);
             if (launched()) return 1;
-          } else if (wide_gemm(n_sms, in.p, in.ld, wbase + w.w, w.ldk, B, ly.out_dim, ly.ktot, e, stream, "gemm fwd")) {
+          } else if (wide_gemm(n_sms, in.p, in.ld, wbase + w.w, w.ldk, B, ly.out_dim, ly.ktot, e, ds, "gemm fwd")) {
             return 1;
           }
         }
@@ -382,10 +391,10 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
       }
       if (!dry) {
         if (TRAIN) {      // the pitch padding of dz is read by the TMA unit as part of full 16-byte rows: keep it finite
-          MMN_CUDA(cudaMemsetAsync(la.dz.p, 0, (size_t)B * la.dz.ld * 2, stream));
+          MMN_CUDA(cudaMemsetAsync(la.dz.p, 0, (size_t)B * la.dz.ld * 2, ds));
         }
         g_wt.begin("decoder_loss");
-        wide_decoder_loss_kernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>(la);
+        wide_decoder_loss_kernel<<<(unsigned)((B + 255) / 256), 256, 0, ds>>>(la);
         if (launched()) return 1;
       }
     }
@@ -472,6 +481,11 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
     g_wt.begin("state_out");
     wide_state_out_kernel<<<(unsigned)std::min<long long>((B * S + 255) / 256, 4096), 256, 0, stream>>>(Sk[L], B, a.final_state);
     if (launched()) return 1;
+  }
+
+  if (fwd_side) {          // join: the backward pass needs every decoder's activations and loss gradient
+    MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->side_done, ds));
+    MMN_CUDA(cudaStreamWaitEvent(stream, (cudaEvent_t)plan->side_done, 0));
   }
 
   if (TRAIN) {
