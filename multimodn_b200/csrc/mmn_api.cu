@@ -196,6 +196,10 @@ extern "C" void mmn_plan_destroy(mmn_plan* plan) {
   if (plan->side_stream) cudaStreamDestroy((cudaStream_t)plan->side_stream);
   if (plan->side_fork) cudaEventDestroy((cudaEvent_t)plan->side_fork);
   if (plan->side_done) cudaEventDestroy((cudaEvent_t)plan->side_done);
+  if (plan->dec_stream) cudaStreamDestroy((cudaStream_t)plan->dec_stream);
+  if (plan->dec_fork) cudaEventDestroy((cudaEvent_t)plan->dec_fork);
+  for (void* ev : plan->dec_done)
+    if (ev) cudaEventDestroy((cudaEvent_t)ev);
 #endif
   delete plan;
 }

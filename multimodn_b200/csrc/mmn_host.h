@@ -33,6 +33,9 @@ struct mmn_plan {
   void* side_stream = nullptr;
   void* side_fork = nullptr;     // cudaEvent_t: caller's stream -> side stream
   void* side_done = nullptr;     // cudaEvent_t: side stream -> caller's stream
+  void* dec_stream = nullptr;    // second side stream: the decoders' backward chains, next to the encoders' backward GEMMs
+  void* dec_fork = nullptr;
+  void* dec_done[MMN_MAX_ENCODERS + 1] = {};   // cudaEvent_t per step: that step's decoder chains are done
   // optional cudaEvent_t handles recorded by mmn_train_step as gradient blocks become final (mmn_plan_set_grad_events)
   void* grad_events[MMN_MAX_ENCODERS + 1] = {};
   int n_grad_events = 0;

@@ -234,6 +234,16 @@ int mmn_wide_plan_init(mmn_plan* p) {
   MMN_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
   MMN_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
   p->side_stream = side; p->side_fork = fork; p->side_done = done;
+  cudaStream_t dstr;
+  cudaEvent_t dfork;
+  MMN_CUDA(cudaStreamCreateWithFlags(&dstr, cudaStreamNonBlocking));
+  MMN_CUDA(cudaEventCreateWithFlags(&dfork, cudaEventDisableTiming));
+  p->dec_stream = dstr; p->dec_fork = dfork;
+  for (int k = 0; k <= P.E; ++k) {
+    cudaEvent_t ev;
+    MMN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    p->dec_done[k] = ev;
+  }
   MMN_CUDA(cudaMalloc(&p->wide_w, (size_t)off * 2));
   MMN_CUDA(cudaMemset(p->wide_w, 0, (size_t)off * 2));
   return 0;
@@ -533,7 +543,19 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
       e.out_f32 = a.grads + ly.w_off; e.ld_f32 = ly.ktot;
       return wide_gemm(n_sms, dz.p, dz.ld, in.p, in.ld, ly.out_dim, ly.ktot, B, e, stream, "gemm wgrad", 1, 1);
     };
-    auto decoders_backward = [&](int k) -> int {
+    // Decoders, backward.  Everything except the last step — the first layer's data gradient, which lands in G — depends
+    // only on what the forward pass left behind, so the chains of ALL steps are enqueued up front on the plan's decoder
+    // stream and run next to the encoders' backward GEMMs (part A); the caller's stream adds each step's contribution to G
+    // where the reverse replay needs it (part B), behind that step's event.
+    const bool dec_side = !dry && plan->dec_stream && !g_wt.on;
+    const cudaStream_t dstream = dec_side ? (cudaStream_t)plan->dec_stream : stream;
+    std::vector<Mat> dz0((size_t)(L + 1) * D);          // dz of every decoder's first layer, kept for part B
+    Mat dzdec[2] = {ar.mat(B, maxW), ar.mat(B, maxW)};  // intermediates of decoders deeper than two layers
+    for (int k = 0; k <= L; ++k)
+      for (int d = 0; d < D; ++d)
+        dz0[(size_t)k * D + d] = P.dec[d].n_layers > 1 ? ar.mat(B, P.dec[d].L[0].out_dim) : dec_dz[(size_t)k * D + d];
+    auto decoders_backward_a = [&](int k) -> int {
+      if (dry) return 0;
       for (int d = 0; d < D; ++d) {
         const DevDecoder& dec = P.dec[d];
         Mat dz = dec_dz[(size_t)k * D + d];
@@ -542,40 +564,63 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
           const DevLayer& ly = dec.L[j];
           const mmn_plan::WL& w = plan->wide_dec[d][j];
           const Mat in = j == 0 ? Sk[k] : dec_h[((size_t)k * D + d) * MMN_MAX_LAYERS + j - 1];
+          // dz of the layer below: the kept buffer when that layer is the first one
+          const Mat nz = j == 1 ? dz0[(size_t)k * D + d] : (j > 1 ? view(dzdec[cur], ly.in_dim) : Mat());
           if (j == dec.n_layers - 1 && j > 0 && dec.C <= 4) {       // decoder head (see decoders_forward)
-            const Mat nz = view(dzbuf[cur], ly.in_dim);
-            if (!dry) {
-              if (join_side()) return 1;
-              g_wt.begin("head_backward");
-              wide_head_backward_kernel<4><<<dim3((unsigned)((ly.in_dim + 2047) / 2048), (unsigned)std::max<long long>(1, std::min<long long>(4 * n_sms, B / 16))),
-                                             256, 0, stream>>>(dz, in, dec.C, B, a.grads + ly.w_off, ly.ktot, a.grads + ly.b_off,
-                                                               wbase + w.w, w.ldk, dec.L[j - 1].act, nz);
-              if (launched()) return 1;
-            }
+            g_wt.begin("head_backward");
+            wide_head_backward_kernel<4><<<dim3((unsigned)((ly.in_dim + 2047) / 2048), (unsigned)std::max<long long>(1, std::min<long long>(4 * n_sms, B / 16))),
+                                           256, 0, dstream>>>(dz, in, dec.C, B, a.grads + ly.w_off, ly.ktot, a.grads + ly.b_off,
+                                                              wbase + w.w, w.ldk, dec.L[j - 1].act, nz);
+            if (launched()) return 1;
             dz = nz;
             cur ^= 1;
             continue;
           }
-          if (layer_param_grads(ly, dz, in)) return 1;
+          g_wt.begin("bias_grad");
+          wide_bias_grad_kernel<<<dim3((unsigned)((ly.out_dim + 63) / 64), (unsigned)std::max<long long>(1, std::min<long long>(32, B / 256))),
+                                  256, 0, dstream>>>(dz.p, dz.ld, B, ly.out_dim, a.grads + ly.b_off);
+          if (launched()) return 1;
           Epi e = epi0();
+          e.mode = EPI_ACCUM_F32; e.accumulate = 1;
+          e.out_f32 = a.grads + ly.w_off; e.ld_f32 = ly.ktot;
+          if (wide_gemm(n_sms, dz.p, dz.ld, in.p, in.ld, ly.out_dim, ly.ktot, B, e, dstream, "gemm wgrad", 1, 1)) return 1;
           if (j > 0) {
-            const Mat nz = view(dzbuf[cur], ly.in_dim);
-            if (!dry && join_side()) return 1;
-            e.mode = EPI_DACT; e.act = dec.L[j - 1].act;
-            e.aux = in.p; e.ld_aux = in.ld;
-            e.out = nz.p; e.ld_out = nz.ld; e.out_t = nz.t; e.ld_out_t = nz.ldt;
-            if (!dry && dgrad(dz, ly, w, 0, ly.in_dim, e, "gemm dgrad")) return 1;
+            Epi ed = epi0();
+            ed.mode = EPI_DACT; ed.act = dec.L[j - 1].act;
+            ed.aux = in.p; ed.ld_aux = in.ld;
+            ed.out = nz.p; ed.ld_out = nz.ld;
+            if (wide_gemm(n_sms, dz.p, dz.ld, wbase + w.wt, w.ldo, B, ly.in_dim, ly.out_dim, ed, dstream, "gemm dgrad")) return 1;
             dz = nz;
             cur ^= 1;
-          } else {
-            e.mode = EPI_ACCUM_F32; e.accumulate = 1;
-            e.out_f32 = G; e.ld_f32 = S;
-            if (!dry && dgrad(dz, ly, w, 0, S, e, "gemm dgrad")) return 1;
           }
         }
       }
+      if (dec_side) MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->dec_done[k], dstream));
       return 0;
     };
+    auto decoders_backward_b = [&](int k) -> int {       // G += dz_0 . W_0 for every decoder of step k
+      if (dry) return 0;
+      if (dec_side) MMN_CUDA(cudaStreamWaitEvent(stream, (cudaEvent_t)plan->dec_done[k], 0));
+      for (int d = 0; d < D; ++d) {
+        const DevLayer& ly = P.dec[d].L[0];
+        const mmn_plan::WL& w = plan->wide_dec[d][0];
+        Epi e = epi0();
+        e.mode = EPI_ACCUM_F32; e.accumulate = 1;
+        e.out_f32 = G; e.ld_f32 = S;
+        if (dgrad(dz0[(size_t)k * D + d], ly, w, 0, S, e, "gemm dgrad")) return 1;
+      }
+      return 0;
+    };
+    auto decoders_backward = [&](int k) -> int {
+      if (!dec_side && decoders_backward_a(k)) return 1;
+      return decoders_backward_b(k);
+    };
+    if (dec_side) {            // every step's part A, in the order part B will ask for them
+      MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->dec_fork, stream));
+      MMN_CUDA(cudaStreamWaitEvent(dstream, (cudaEvent_t)plan->dec_fork, 0));
+      for (int k = L; k >= 0; --k)
+        if (decoders_backward_a(k)) return 1;
+    }
     for (int k = L; k >= 1; --k) {
       const int e = a.seq_enc[k - 1];
       const DevEncoder& enc = P.enc[e];
