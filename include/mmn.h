@@ -15,8 +15,10 @@
  *   - every function returns 0 on success, non-zero on failure; mmn_last_error() returns the
  *     message of the calling thread's last failure.  No C++ exception crosses the boundary.
  *   - the caller (PyTorch) owns every buffer; the library owns only the opaque plan.
- *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*); no call
- *     synchronises the device.
+ *   - all work is ordered on the caller's stream (a cudaStream_t passed as void*); no call
+ *     synchronises the device.  bf16 plans fork two plan-owned streams from the caller's stream
+ *     inside mmn_train_step (cudaEventRecord / cudaStreamWaitEvent) and join them before the call
+ *     returns: whatever the caller enqueues next on its stream sees every result.
  *   - "device" pointers are CUDA device memory; "host" pointers are ordinary host memory read
  *     before the call returns.
  *   - one host thread per plan at a time.
