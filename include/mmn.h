@@ -215,6 +215,12 @@ int mmn_selftest_gemm_bf16(int M, int N, int K, const void* a, long long lda, co
 int mmn_selftest_gemm_bf16_mn(int M, int N, int K, const void* a, long long lda, const void* b, long long ldb,
                               float* out_f32, void* stream);
 
+/* Diagnostic (bench.py): FP32-FMA micro-benchmark — every SM runs 2048 threads of 8 independent FFMA chains, `iters` rounds
+ * each.  out: device float[4] (keeps the chains alive); *flops (host) receives the floating-point operations of the launch.
+ * Timed by the caller with CUDA events on `stream`: the measured FP32-FMA peak the fp32 step kernels are held against
+ * (SURVEY.md section 8d). */
+int mmn_selftest_fma_peak(int iters, float* out, double* flops, void* stream);
+
 /* Kernels launched so far by bf16 (wide-regime) plans in this process: launch accounting for benchmarks. */
 int64_t mmn_wide_launch_count(void);
 

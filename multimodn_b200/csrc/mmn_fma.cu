@@ -63,3 +63,37 @@ extern "C" int mmn_adam_step(const mmn_plan* plan, float* params, const float* g
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// FP32-FMA micro-benchmark (mmn_selftest_fma_peak): 8 independent FFMA chains per thread, 2048 threads per SM
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) mmn_fma_peak_kernel(int iters, float* out) {
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = 1.0f + 1e-3f * (float)(threadIdx.x + i);
+  const float m = 1.0f - 1e-7f * (float)(blockIdx.x & 3), c = 1e-6f * (float)(threadIdx.x & 7);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fmaf(a[i], m, c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i];
+  if (s == 123.456f) out[threadIdx.x & 3] = s;      // never true: keeps the chains observable
+}
+}  // namespace
+
+extern "C" int mmn_selftest_fma_peak(int iters, float* out, double* flops, void* stream) {
+  if (iters <= 0 || !out || !flops) return fail("mmn_selftest_fma_peak: bad argument");
+  int dev = 0, n_sms = 0;
+  MMN_CUDA(cudaGetDevice(&dev));
+  MMN_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = n_sms * 8;
+  MMN_LAUNCH(mmn_fma_peak_kernel, dim3(grid), dim3(256), 0, stream, iters, out);
+  MMN_CUDA(cudaGetLastError());
+  *flops = 2.0 * 32.0 * (double)iters * 256.0 * (double)grid;
+  return 0;
+}

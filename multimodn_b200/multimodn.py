@@ -87,6 +87,11 @@ class _Runtime:
         self.layerwise = int(self.lib.dll.mmn_plan_engine(self.plan)) == 3      # bf16 plans: many launches per step
         self.grad_events = None
         self.comm_stream = None
+        # CrossEntropyLoss raises on a target outside [0, C) (and ignores -100): the kernels index with the target, so it is
+        # validated on the device every batch (no host sync) and the verdict is read where the epoch's metrics are read
+        self._n_classes = torch.tensor([m.n_classes for m in self.packed.decoders], dtype=torch.int64, device=self.device)
+        self._target_err = torch.zeros((), dtype=torch.int64, device=self.device)
+        self._dp_err = torch.zeros((), dtype=torch.int64, device=self.device)
 
     def __del__(self):
         try:
@@ -199,14 +204,19 @@ class _Runtime:
             if tgt.dim() != 2 or tgt.shape[1] != self.D or tgt.shape[0] != n_rows:
                 raise ValueError(f"target must be ({n_rows}, {self.D}), got {tuple(tgt.shape)}")
             tgt = tgt.contiguous()
+            bad = ((tgt < 0) | (tgt >= self._n_classes)).any().to(torch.int64)
+            self._target_err = torch.maximum(self._target_err, bad)
         npos = max(len(xs), 1)
         seq_pos = (C.c_int32 * max(len(seq), 1))(*[p for p, _ in seq])
         seq_enc = (C.c_int32 * max(len(seq), 1))(*enc_ids)
         xptr = (C.c_void_p * npos)(*[t.data_ptr() for t in xs])
         xld = (C.c_int64 * npos)(*[t.stride(0) for t in xs])
-        world, rank, group = dp if dp else (1, 0, None)
+        world, rank, group = (dp[0], dp[1], dp[2]) if dp else (1, 0, None)
+        n_global, row_offset = n_rows * world, rank * n_rows
+        if dp and len(dp) > 3 and dp[3] is not None:        # (n_rows_global, row_offset) agreed across the ranks
+            n_global, row_offset = dp[3]
         b = _lib.Batch()
-        b.n_rows, b.n_rows_global, b.row_offset = n_rows, n_rows * world, rank * n_rows
+        b.n_rows, b.n_rows_global, b.row_offset = n_rows, n_global, row_offset
         b.seq_len = len(seq)
         b.seq_pos = C.cast(seq_pos, C.POINTER(C.c_int32))
         b.seq_enc = C.cast(seq_enc, C.POINTER(C.c_int32))
@@ -251,6 +261,14 @@ class _Runtime:
                                                    C.byref(o), self.gflat.data_ptr(), ws.data_ptr(), ws_bytes,
                                                    self.stream()))
         return seed
+
+    def check_targets(self):
+        """raise like nn.CrossEntropyLoss does for a target outside [0, n_classes) (one small D2H; called where the
+        epoch's metrics are read back anyway)"""
+        if int(self._target_err.item()) != 0:
+            self._target_err.zero_()
+            raise IndexError("Target out of bounds: a target lies outside [0, n_classes) of its decoder "
+                             "(ignore_index = -100 is not supported by the fused step)")
 
     def assign_grads(self):
         """loss.backward() epilogue (multimodn.py:203): hand each parameter a view of the packed
@@ -306,12 +324,14 @@ class MultiModN(nn.Module):
         self.to(self.device)
         self._rt: Optional[_Runtime] = None
         self._dp = None                 # (world, rank, group) once data parallelism is enabled
+        self._dp_hash = 0
 
     # -- plumbing ------------------------------------------------------------------------------
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_rt"] = None             # plan handles and packed buffers are rebuilt on demand
         state["_dp"] = None
+        state["_dp_hash"] = 0
         return state
 
     def runtime(self) -> _Runtime:
@@ -340,8 +360,11 @@ class MultiModN(nn.Module):
 
     def _allreduce_grads(self, rt, seq):
         """Gradient all-reduce of one train step.  Fused single-launch plans: one collective over the packed buffer.
-        Layer-wise (bf16) plans: one collective per encoder block, in the order the backward pass finishes them, on a side
-        stream behind the block's gradient-ready event, so that it overlaps the remaining backward GEMMs."""
+        Layer-wise (bf16) plans: one collective per encoder block on a side stream behind the block's gradient-ready
+        event, so that it overlaps the remaining backward GEMMs.  The collectives are issued in an order
+        that does not depend on the rank-local sequence (descending encoder id = the order the default sequence finishes
+        them; an encoder outside the sequence waits for the end-of-step event), so ranks that disagree on the sequence
+        still pair their collectives — the disagreement itself is reported by ``_dp_note`` / ``check_data_parallel``."""
         if not (self._dp and self._dp[0] > 1):
             return
         if not rt.grad_events:
@@ -349,16 +372,46 @@ class MultiModN(nn.Module):
             return
         main = torch.cuda.current_stream(self.device)
         comm = rt.comm_stream
-        in_seq = [e for _, e in reversed(seq)]
+        in_seq = {e for _, e in seq}
+        all_ids = list(range(rt.E - 1, -1, -1))
         with torch.cuda.stream(comm):
-            for e in in_seq:
-                comm.wait_event(rt.grad_events[e])
+            for e in all_ids:
+                comm.wait_event(rt.grad_events[e if e in in_seq else rt.E])
                 lo, hi = rt.packed.encoder_range(e)
                 torch.distributed.all_reduce(rt.gflat[lo:hi], group=self._dp[2])
             comm.wait_event(rt.grad_events[rt.E])
-            for lo, hi in rt.packed.complement_ranges(in_seq, rt.n_grads):
+            for lo, hi in rt.packed.complement_ranges(all_ids, rt.n_grads):
                 torch.distributed.all_reduce(rt.gflat[lo:hi], group=self._dp[2])
         main.wait_stream(comm)
+
+    # Data-parallel contract: every rank feeds the same number of rows per batch (use drop_last / equal shards: the kernel
+    # divides by n_rows * world and keys the dropout stream by rank * n_rows) and the same encoding sequence.  Both are
+    # folded into a running hash per epoch; one tiny MAX all-reduce per epoch compares the ranks without a host sync and
+    # the verdict is read with the epoch's metrics (``_finalize``) or by ``check_data_parallel()``.
+    def _dp_note(self, n_rows, seq):
+        if self._dp and self._dp[0] > 1:
+            h = self._dp_hash
+            for v in (n_rows, len(seq), *[p * 131 + e for p, e in seq]):
+                h = (h * 1000003 + int(v) + 1) % 2147483629
+            self._dp_hash = h
+
+    def _dp_close_epoch(self, rt):
+        if not (self._dp and self._dp[0] > 1):
+            return
+        h = float(self._dp_hash)
+        self._dp_hash = 0
+        t = torch.tensor([h, -h], dtype=torch.float64, device=rt.device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX, group=self._dp[2])
+        rt._dp_err = torch.maximum(rt._dp_err, (t[0] + t[1] != 0).to(torch.int64))
+
+    def check_data_parallel(self):
+        """raise if the ranks of the data-parallel group disagreed on a batch size or an encoding sequence (one D2H)"""
+        rt = self.runtime()
+        if self._dp and self._dp[0] > 1 and int(rt._dp_err.item()) != 0:
+            rt._dp_err.zero_()
+            raise RuntimeError("data-parallel ranks disagreed on the rows per batch or on the encoding sequence: every rank "
+                               "must feed equally sized batches (drop_last / equal shards) and the same sequence; "
+                               "gradients of this epoch are not the global-batch gradients")
 
     # -- the encoding sequence (multimodn.py:509-531) --------------------------------------------
     def get_encoder_iterable(self, encoder_sequence, shuffle_mode: bool, train: bool) -> List[Tuple[int, int]]:
@@ -377,11 +430,18 @@ class MultiModN(nn.Module):
             pairs = [(i, int(e)) for i, e in enumerate(seq)]
         if shuffle_mode and train:
             random.shuffle(pairs)                                   # multimodn.py:527-529
+            if self._dp and self._dp[0] > 1:                        # one order for the whole global batch: rank 0's
+                box = [pairs]
+                src = torch.distributed.get_global_rank(self._dp[2], 0) if self._dp[2] is not None else 0
+                torch.distributed.broadcast_object_list(box, src=src, group=self._dp[2])
+                pairs = [tuple(p) for p in box[0]]
         return pairs
 
     # -- epoch bookkeeping (multimodn.py:222-250, 367-409) ---------------------------------------
     def _finalize(self, rt: _Runtime, metrics: Tensor, n_batches: int):
         self._allreduce(metrics)
+        rt.check_targets()
+        self.check_data_parallel()
         mats, n_present, sc = rt.split_metrics(metrics.cpu().numpy())
         ce, n_correct, tp, tn, fp, fn = mats
         n_samples = np.ones((rt.E + 1, 1)) + n_present.reshape(-1, 1)      # starts at ONE (:105,:270)
@@ -423,6 +483,7 @@ class MultiModN(nn.Module):
             seq = self.get_encoder_iterable(encoder_sequence, shuffle_mode=self.shuffle_mode, train=True)
             optimizer.zero_grad()
             mb, keep, n_rows = rt.prepare_batch(list(data), target, seq, self.missing_mode, self._dp)
+            self._dp_note(n_rows, seq)
             if batch_metrics is not None:
                 batch_metrics.zero_()
             rt.train_step(mb, n_rows, float(self.err_penalty), float(self.state_change_penalty), True,
@@ -448,6 +509,7 @@ class MultiModN(nn.Module):
                            f"\tErr loss: {err:.4f}\n"
                            f"\tState change: {chg:.4f}")
 
+        self._dp_close_epoch(rt)
         if history is not None:
             fin = self._finalize(rt, epoch_metrics, n_batches)
             history.state_change_loss.append(fin["state_change"])
@@ -476,11 +538,13 @@ class MultiModN(nn.Module):
         for data, target, encoder_sequence in rt.staged(test_loader):
             seq = self.get_encoder_iterable(encoder_sequence, shuffle_mode=self.shuffle_mode, train=False)
             mb, keep, n_rows = rt.prepare_batch(list(data), target, seq, self.missing_mode, self._dp)
+            self._dp_note(n_rows, seq)
             last = torch.zeros((n_rows, rt.sumC), dtype=torch.float32, device=rt.device)
             rt.forward(mb, n_rows, metrics=metrics, last_outputs=last)
             outs.append(last)
             tgts.append(keep[1])
             del keep
+        self._dp_close_epoch(rt)
         fin = self._finalize(rt, metrics, n_batches)
         if log_results:
             logger(f"{tag.capitalize()} results\n"

@@ -84,3 +84,48 @@ def test_two_ranks_equal_one_rank(tmp_path, missing_mode, optimizer):
     assert_close(got["acc"], np.stack(hist.accuracy["train"]), rtol=1e-6, what="train accuracy history")
     assert_close(got["sc"], np.stack(hist.state_change_loss), rtol=1e-5, what="state-change history")
     assert_close(got["val"], hist.loss["val"][0], rtol=1e-5, what="val loss")
+
+
+def _contract_worker(rank, world, port, case, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import random
+        from multimodn_b200 import MultiModNHistory
+        model, opt, data, y = _make("row", "torch")
+        model.enable_data_parallel()
+        n = len(y) // world
+        lo, hi = rank * n, (rank + 1) * n
+        msg = "ok"
+        if case == "ragged":                      # rank 1 feeds fewer rows than rank 0: must be reported, not averaged away
+            hi -= 5 * rank
+        if case == "shuffle":
+            model.shuffle_mode = True
+            random.seed(100 + rank)               # different local draws: rank 0's order must win everywhere
+        loader = [([torch.from_numpy(x[lo:hi]) for x in data], torch.from_numpy(y[lo:hi]))]
+        try:
+            model.train_epoch(loader, opt, CrossEntropyLoss(), MultiModNHistory(["a", "b"]))
+        except RuntimeError as exc:
+            msg = str(exc)
+        params = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).numpy().copy()
+        np.savez(out + f".{rank}.npz", params=params, msg=np.array(msg))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ranks_with_different_batch_sizes_are_reported(tmp_path):
+    out = str(tmp_path / "dp")
+    mp.spawn(_contract_worker, args=(2, _free_port(), "ragged", out), nprocs=2, join=True)
+    for r in range(2):
+        assert "disagreed on the rows per batch" in str(np.load(out + f".{r}.npz")["msg"])
+
+
+def test_shuffle_mode_under_data_parallel_uses_one_order(tmp_path):
+    """shuffle_mode draws from the per-process `random`; under DP rank 0's order is broadcast, so both ranks apply the same
+    sequence and end the step with identical parameters"""
+    out = str(tmp_path / "dp")
+    mp.spawn(_contract_worker, args=(2, _free_port(), "shuffle", out), nprocs=2, join=True)
+    a, b = np.load(out + ".0.npz"), np.load(out + ".1.npz")
+    assert str(a["msg"]) == "ok" and str(b["msg"]) == "ok"
+    assert (a["params"] == b["params"]).all()
