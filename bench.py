@@ -404,8 +404,11 @@ class Bench:
         l0 = int(lib.mmn_wide_launch_count())
         kms = self.timed(kernel_only, K) / K
         wide_launches = (int(lib.mmn_wide_launch_count()) - l0) // K
-        if clock is not None:                                # keep the load on for a rank-uniform number of extra rounds
-            for _ in range(2):
+        if clock is not None:
+            # keep the load on until nvidia-smi (100 ms period) has a dozen samples: the number of extra rounds is computed
+            # from the max-over-ranks kernel time, i.e. it is the same on every rank (no rank-local loop conditions)
+            extra = int(min(200, max(2, 1500.0 / max(kms * K, 1e-3))))
+            for _ in range(extra):
                 self.timed(kernel_only, K)
             clock.__exit__()
         macs, macs_strict = macs_per_row(w), macs_per_row(w, strict=True)
@@ -589,8 +592,11 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the secondary configurations")
+    ap.add_argument("--precision", default=None, choices=["fp32", "bf16"], help="override the workload's precision")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
+    if args.precision:
+        w = dict(w, precision=args.precision)
     if args.impl == "reference":
         return run_reference(args, w)
 

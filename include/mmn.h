@@ -39,9 +39,11 @@ extern "C" {
 #define MMN_MAX_DECODERS 16
 #define MMN_MAX_CLASSES 32
 
-/* Arithmetic of a plan.  FP32: the fused per-tile step kernels, 1e-5 relative to the reference.  BF16: the wide regime
- * (BASELINE config 4) — every layer is a tensor-core GEMM over the whole batch with bf16 weights / activations / layer
- * gradients, fp32 accumulation, fp32 master weights and gradients; 1e-2 relative to the reference. */
+/* Arithmetic of a plan.  FP32: the fused per-tile step kernels, 1e-5 relative to the reference.  BF16: bf16 weights /
+ * activations / layer gradients, fp32 accumulation, fp32 master weights and gradients; 1e-2 relative to the reference.
+ * Narrow models (state <= 64, layers <= 64 wide, <= 3 Linear layers per module, <= 8 classes) run the fused per-tile
+ * mma kernel (MMN_ENGINE_NB, one launch per step); everything else the wide regime (BASELINE config 4): every layer a
+ * tcgen05 GEMM over the whole batch (MMN_ENGINE_WIDE). */
 enum { MMN_PRECISION_FP32 = 0, MMN_PRECISION_BF16 = 1 };
 
 /* activation applied after a Linear layer (mlp_encoder.py:46,76; decoders.py:20,44-45) */
@@ -149,7 +151,8 @@ void mmn_plan_destroy(mmn_plan* plan);
  *                   resident in tensor memory; needs state <= 64, layers <= 64 wide, <= 16 classes.  Default of
  *                   mmn_forward when the model qualifies; mmn_train_step uses it under MMN_ENGINE=tc2
  * The environment variable MMN_ENGINE=fma|tc|tc2, read by mmn_plan_create, forces one. */
-enum { MMN_ENGINE_FMA = 0, MMN_ENGINE_TC = 1, MMN_ENGINE_TC2 = 2, MMN_ENGINE_WIDE = 3 /* precision = bf16 */ };
+enum { MMN_ENGINE_FMA = 0, MMN_ENGINE_TC = 1, MMN_ENGINE_TC2 = 2, MMN_ENGINE_WIDE = 3 /* precision = bf16, layer-wise */,
+       MMN_ENGINE_NB = 4 /* precision = bf16, fused per-tile mma.sync kernel for narrow models; MMN_ENGINE=wide opts out */ };
 int32_t mmn_plan_engine(const mmn_plan* plan);           /* engine of mmn_train_step */
 
 /* Data-parallel overlap (the gradient all-reduce "issued per encoder block in reverse order to overlap with

@@ -134,10 +134,26 @@ extern "C" int mmn_plan_create(const mmn_model_desc* desc, mmn_plan** out) {
   }
   if (desc->precision != MMN_PRECISION_FP32 && desc->precision != MMN_PRECISION_BF16) { delete p; return fail("precision must be MMN_PRECISION_FP32 or MMN_PRECISION_BF16"); }
   if (desc->precision == MMN_PRECISION_BF16) {
+    // narrow models: the fused per-tile mma kernel (one launch per step); MMN_ENGINE=wide forces the layer-wise regime
+    const char* want_bf16 = getenv("MMN_ENGINE");
+    const bool force_wide = want_bf16 && !strcmp(want_bf16, "wide");
+    if (!force_wide && mmn_nb_plan_init(p) == 0) {
+      p->engine = p->fwd_engine = MMN_ENGINE_NB;
+      if (cudaMalloc((void**)&p->dev, sizeof(DevPlan)) != cudaSuccess ||
+          cudaMemcpy(p->dev, &P, sizeof(DevPlan), cudaMemcpyHostToDevice) != cudaSuccess) {
+        mmn_nb_plan_free(p);
+        delete p;
+        return fail("mmn_plan_create: device allocation failed");
+      }
+      *out = p;
+      return 0;
+    }
+    mmn_nb_plan_free(p);
 #ifdef MMN_EMU
     delete p;
-    return fail("precision = bf16 (the wide regime) is not part of the host emulator");
+    return fail("precision = bf16: only the per-tile kernel (narrow models) is part of the host emulator: %s", g_err.c_str());
 #else
+    g_err.clear();
     p->engine = p->fwd_engine = MMN_ENGINE_WIDE;
     if (mmn_wide_plan_init(p) || cudaMalloc((void**)&p->dev, sizeof(DevPlan)) != cudaSuccess ||
         cudaMemcpy(p->dev, &P, sizeof(DevPlan), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -192,6 +208,7 @@ extern "C" void mmn_plan_destroy(mmn_plan* plan) {
   if (!plan) return;
   if (plan->dev) cudaFree(plan->dev);
   if (plan->wide_w) cudaFree(plan->wide_w);
+  mmn_nb_plan_free(plan);
 #ifndef MMN_EMU
   if (plan->side_stream) cudaStreamDestroy((cudaStream_t)plan->side_stream);
   if (plan->side_fork) cudaEventDestroy((cudaEvent_t)plan->side_fork);
@@ -225,6 +242,7 @@ extern "C" int32_t mmn_plan_forward_engine(const mmn_plan* plan) { return plan ?
 
 extern "C" int64_t mmn_workspace_bytes(const mmn_plan* plan, int64_t n_rows, int32_t with_backward) {
   if (!plan || n_rows < 0) return -1;
+  if (plan->engine == MMN_ENGINE_NB) return mmn_nb_workspace_bytes(plan, n_rows, with_backward != 0);
 #ifndef MMN_EMU
   if (plan->engine == MMN_ENGINE_WIDE) return mmn_wide_workspace_bytes(plan, n_rows, with_backward != 0);
 #endif
@@ -289,6 +307,7 @@ extern "C" int mmn_forward(const mmn_plan* plan, const mmn_batch* batch, const f
     return mmn_wide_step(plan, a, workspace, workspace_bytes, stream, false);
   }
 #endif
+  if (plan->engine == MMN_ENGINE_NB) return mmn_nb_step(plan, a, workspace, workspace_bytes, stream, false);
   (void)workspace; (void)workspace_bytes;
   return launch_step(plan, a, stream, false);
 }
@@ -315,7 +334,9 @@ extern "C" int mmn_train_step(const mmn_plan* plan, const mmn_batch* batch, cons
 #ifndef MMN_EMU
   if (plan->engine == MMN_ENGINE_WIDE) return mmn_wide_step(plan, a, workspace, workspace_bytes, stream, true);
 #endif
-  if (launch_step(plan, a, stream, true)) return 1;
+  if (plan->engine == MMN_ENGINE_NB) {
+    if (mmn_nb_step(plan, a, workspace, workspace_bytes, stream, true)) return 1;
+  } else if (launch_step(plan, a, stream, true)) return 1;
 #ifndef MMN_EMU
   for (int i = 0; i < plan->n_grad_events; ++i)          // one launch: every gradient block is final at its end
     MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->grad_events[i], (cudaStream_t)stream));

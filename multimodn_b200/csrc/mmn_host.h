@@ -36,6 +36,11 @@ struct mmn_plan {
   void* dec_stream = nullptr;    // second side stream: the decoders' backward chains, next to the encoders' backward GEMMs
   void* dec_fork = nullptr;
   void* dec_done[MMN_MAX_ENCODERS + 1] = {};   // cudaEvent_t per step: that step's decoder chains are done
+  // bf16 tile kernel (mmn_nb.cuh; narrow models under precision = bf16): lowered plan (host / device copies) and the device
+  // arena the per-step imaging kernel fills with bf16 weight images
+  void* nb_host = nullptr;
+  void* nb_dev = nullptr;
+  void* nb_arena = nullptr;
   // optional cudaEvent_t handles recorded by mmn_train_step as gradient blocks become final (mmn_plan_set_grad_events)
   void* grad_events[MMN_MAX_ENCODERS + 1] = {};
   int n_grad_events = 0;
@@ -66,6 +71,10 @@ size_t mmn_v2_smem(const mmn::DevPlan& P);
 int mmn_launch_fma(const mmn_plan* plan, const mmn::StepArgs& a, void* stream, bool train);
 int mmn_launch_tc(const mmn_plan* plan, const mmn::StepArgs& a, void* stream, bool train);
 int mmn_launch_v2(const mmn_plan* plan, const mmn::StepArgs& a, void* stream, bool train);
+int mmn_nb_plan_init(mmn_plan* p);
+void mmn_nb_plan_free(mmn_plan* p);
+int64_t mmn_nb_workspace_bytes(const mmn_plan* plan, int64_t n_rows, bool train);
+int mmn_nb_step(const mmn_plan* plan, const mmn::StepArgs& a, void* ws, size_t ws_bytes, void* stream, bool train);
 #ifndef MMN_EMU
 int mmn_wide_plan_init(mmn_plan* p);
 int64_t mmn_wide_workspace_bytes(const mmn_plan* plan, int64_t n_rows, bool train);

@@ -7,4 +7,4 @@ ROOT=$(cd "$HERE/../.." && pwd)
 g++ -x c++ -std=c++17 -O2 -g -DMMN_EMU -fPIC -shared -Wall -Wno-unknown-pragmas -Wno-unused-function \
     -I"$HERE" -I"$ROOT/include" -I"$ROOT/multimodn_b200/csrc" \
     -o "$HERE/libmmn_emu.so" "$ROOT/multimodn_b200/csrc/mmn_api.cu" "$ROOT/multimodn_b200/csrc/mmn_fma.cu" \
-    "$ROOT/multimodn_b200/csrc/mmn_tc.cu" "$ROOT/multimodn_b200/csrc/mmn_tc2.cu"
+    "$ROOT/multimodn_b200/csrc/mmn_tc.cu" "$ROOT/multimodn_b200/csrc/mmn_tc2.cu" "$ROOT/multimodn_b200/csrc/mmn_nb.cu"

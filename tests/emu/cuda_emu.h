@@ -154,6 +154,26 @@ inline void warp_barrier() {
 }
 // a .sync.aligned instruction: every lane of the warp must execute it together
 inline void warp_collective() { warp_barrier(); }
+// barrier `id` over `count` threads (bar.sync id, count); any number of ids, each with its own arrival counter
+inline void named_barrier_id(unsigned id, unsigned count) {
+  static unsigned n_arrived[16] = {0}, gen_[16] = {0};
+  const unsigned gen = gen_[id];
+  if (++n_arrived[id] == count) { n_arrived[id] = 0; ++gen_[id]; }
+  else while (gen_[id] == gen) yield();
+}
+// warp-wide exchange: every lane publishes N 64-bit words, then reads any lane's words (mma.sync / ldmatrix / movmatrix
+// models).  Usage: publish(...); ...read peer()...; done();
+struct WarpExchange {
+  static constexpr int kWords = 8;
+  static uint64_t (&buf())[64][32][kWords] { static uint64_t b[64][32][kWords]; return b; }
+  static void publish(const uint64_t* words, int n) {
+    const unsigned w = tIdx().x / 32, lane = tIdx().x % 32;
+    for (int i = 0; i < n; ++i) buf()[w][lane][i] = words[i];
+    warp_barrier();
+  }
+  static uint64_t peer(unsigned lane, int i) { return buf()[tIdx().x / 32][lane & 31][i]; }
+  static void done() { warp_barrier(); }
+};
 template <class T>
 inline T shfl(T v, unsigned src_lane) {
   static_assert(sizeof(T) <= 8, "shfl payload");
@@ -184,6 +204,15 @@ template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) {
   unsigned l = threadIdx.x % 32; return emu::shfl(v, l + d < 32 ? l + d : l);
 }
 template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return emu::shfl(v, src); }
+static inline unsigned __ballot_sync(unsigned, int pred) {
+  uint64_t w = pred ? 1 : 0;
+  emu::WarpExchange::publish(&w, 1);
+  unsigned m = 0;
+  for (unsigned l = 0; l < 32; ++l) m |= (unsigned)(emu::WarpExchange::peer(l, 0) & 1) << l;
+  emu::WarpExchange::done();
+  return m;
+}
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline void __threadfence() {}
 static inline void __trap() { abort(); }
 
