@@ -102,16 +102,25 @@ bool mmn_nb_build(const DevPlan& P, int max_smem, NbPlan& N, const char** why) {
   arena += 4 * N.Spad;
   N.arena_bytes = (arena + 15) & ~15;
   // kernel instantiation and the stash / staging geometry that depends on it
-  const int kss = N.Spad / 16, ksh = std::max(1, max_hidden / 16);
+  bool one_layer_encoder = false;
+  int xs = 0;
+  for (int e = 0; e < P.E; ++e) {
+    one_layer_encoder |= N.enc[e].n_layers == 1;
+    N.enc[e].xs_off = xs;
+    xs += N.enc[e].L[0].ka_pad / 16;
+  }
+  N.xs_steps = xs;
+  // the x-fed layer keeps 16 KSH output columns in registers: a 1-layer encoder's output is the state itself
+  const int kss = N.Spad / 16, ksh = std::max(std::max(1, max_hidden / 16), one_layer_encoder ? N.Spad / 16 : 0);
   const Inst* inst = nullptr;
   for (const Inst& c : kInsts)
     if (kss <= c.kss && ksh <= c.ksh) { inst = &c; break; }
   if (!inst) { *why = reasons[2]; return false; }
   N.kss = kss;
   N.ksh = ksh;
-  N.stash_step_regs = 8 * inst->kss + 2 * 8 * inst->ksh;
+  N.stash_step_regs = 4 * MI * (inst->kss + 2 * inst->ksh);     // Frag<KS>: MI x KS x 4 registers
   for (int e = 0; e < P.E; ++e)
-    for (int j = 0; j < kMaxL; ++j) N.enc[e].stash_off[j] = 8 * inst->kss + 8 * inst->ksh * std::min(j, 1);
+    for (int j = 0; j < kMaxL; ++j) N.enc[e].stash_off[j] = 4 * MI * (inst->kss + inst->ksh * std::min(j, 1));
   const int max_a = std::max(N.Spad, std::max(16, max_hidden)), max_dz = std::max(N.Spad, max_out);
   N.stage_dz_off = max_a * 2;
   N.stage_pitch = (max_a + max_dz) * 2 + 16;
@@ -155,7 +164,10 @@ static int nb_grid(const mmn_plan* plan, int64_t n_rows) {
 int64_t mmn_nb_workspace_bytes(const mmn_plan* plan, int64_t n_rows, bool train) {
   if (!train) return 0;
   const NbPlan& N = *static_cast<const NbPlan*>(plan->nb_host);
-  return (int64_t)nb_grid(plan, n_rows) * (kNbGroups * kWarpsPerGroup) * (int64_t)N.E * N.stash_step_regs * 32 * 4;
+  const int64_t grid = nb_grid(plan, n_rows);
+  const int64_t reg_stash = grid * (kNbGroups * kWarpsPerGroup) * (int64_t)N.E * N.stash_step_regs * 32 * 4;
+  const int64_t x_stash = grid * kNbGroups * (int64_t)N.xs_steps * kWarpsPerGroup * MI * 32 * 16;
+  return ((reg_stash + 255) & ~(int64_t)255) + x_stash;
 }
 
 int mmn_nb_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes, void* stream, bool train) {
@@ -174,6 +186,11 @@ int mmn_nb_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_byt
   args.stash = static_cast<unsigned*>(ws);
   args.stash_words_per_warp = (long long)N.E * N.stash_step_regs * 32;
   const int grid = nb_grid(plan, a.n_rows);
+  {
+    const int64_t reg_stash = (int64_t)grid * (kNbGroups * kWarpsPerGroup) * (int64_t)N.E * N.stash_step_regs * 32 * 4;
+    args.xstash = reinterpret_cast<float4*>(static_cast<char*>(ws) + ((reg_stash + 255) & ~(int64_t)255));
+    args.xstash_vec_per_group = (long long)N.xs_steps * kWarpsPerGroup * MI * 32;
+  }
   const size_t smem = nb_smem_bytes(N);
   const Inst& c = inst_of(N);
   if (c.kss == 1) return launch_inst<1, 1>(plan, args, grid, smem, stream, train);

@@ -34,7 +34,13 @@
 namespace mmn {
 namespace nb {
 
-constexpr int kNbGroups = 2, kWarpsPerGroup = 4, kThreadsNb = kNbGroups * kWarpsPerGroup * 32, kTileRows = 128;
+// MI = m16 tiles per warp: a warp owns 16 MI rows of its group's 128-row tile.  MI = 1: 8 warps per group, 16 warps per CTA at
+// <= 128 registers (fragments of a 64-wide state: 16 registers, the fp32 state gradient: 32); MI = 2 halves the shared-memory
+// reads per MMA but needs ~2x the registers per thread (8 warps per CTA, spills in the reverse sweep).
+constexpr int MI = 1;
+constexpr int kWarpRows = 16 * MI, kTileRows = 128;
+constexpr int kNbGroups = 2, kWarpsPerGroup = kTileRows / kWarpRows, kGroupThreads = kWarpsPerGroup * 32;
+constexpr int kThreadsNb = kNbGroups * kGroupThreads;
 constexpr int kMaxL = 3;          // Linear layers per encoder / decoder in this engine
 constexpr int kMaxW = 64;         // widest state / hidden layer
 constexpr int kMaxC = 8;          // classes per decoder (one n8 tile)
@@ -52,6 +58,7 @@ struct NbEnc {
   int F, n_layers;
   float p_drop;
   int stash_off[kMaxL];           // register offset of layer j's OUTPUT inside a step's stash block (hidden layers)
+  int xs_off;                     // first k16-step of this encoder's x fragments inside the group's x stash
   NbLayer L[kMaxL];
 };
 struct NbDec {
@@ -65,6 +72,7 @@ struct NbPlan {
   int stash_step_regs;            // registers per thread per step: state + hidden outputs
   int stage_pitch, stage_dz_off;  // staging buffer: row pitch (bytes), byte offset of the dz part inside a row
   int kss, ksh;                   // k16-steps of the state / of the widest hidden layer (template instantiation)
+  int xs_steps;                   // k16-steps of x over all encoders (x stash size per group)
   long long init_param_off, n_params;
   NbEnc enc[MMN_MAX_ENCODERS];
   NbDec dec[MMN_MAX_DECODERS];
@@ -76,6 +84,8 @@ struct NbArgs {
   const unsigned char* arena;     // device: images prepared by mmn_nb_prep_kernel for this step's parameters
   unsigned* stash;                // device: per-warp register stash
   long long stash_words_per_warp;
+  float4* xstash;                 // device: per-group stash of the bf16 x fragments (16 bytes per thread per k16-step)
+  long long xstash_vec_per_group;
 };
 
 // shared-memory footprint of the step kernel
@@ -145,10 +155,14 @@ struct Lane {
   int lane, g, t, warp, wg, gi;
 };
 
+// sigmoid / tanh through one exp2 + one reciprocal (tanh z = 2 sigmoid(2 z) - 1): MUFU-bound, a dozen instructions
+__device__ __forceinline__ float nb_squash(float z, float cin, float cm, float ca) {
+  return fmaf(__fdividef(1.f, 1.f + __expf(-cin * z)), cm, ca);
+}
 __device__ __forceinline__ float nb_act(int act, float z) {
   if (act == MMN_ACT_RELU) return fmaxf(z, 0.f);
-  if (act == MMN_ACT_SIGMOID) return __fdividef(1.f, 1.f + expf(-z));
-  if (act == MMN_ACT_TANH) return tanhf(z);
+  if (act == MMN_ACT_SIGMOID) return nb_squash(z, 1.f, 1.f, 0.f);
+  if (act == MMN_ACT_TANH) return nb_squash(z, 2.f, 2.f, -1.f);
   return z;
 }
 
@@ -167,7 +181,7 @@ __device__ __forceinline__ void nb_keep2(const Drop& d, unsigned row, unsigned c
 // A fragments of a [32 x 16 KS] activation: F[mi][ks][i]
 template <int KS>
 struct Frag {
-  unsigned v[2][KS][4];
+  unsigned v[MI][KS][4];
 };
 
 // element (mi, ks, i, half) of a fragment array <-> (row, col) of the warp's 32 x 16 KS tile
@@ -176,7 +190,7 @@ __device__ __forceinline__ int frag_col(const Lane& L, int ks, int i, int half) 
 
 // ---- one k-range of a forward GEMM: acc[mi][j] += A[mi][ks] . W[8 (j0 + j) .., kcol0 + 16 ks ..]^T for ks < ks_n, j < nj ----
 template <int KS, int NT>
-__device__ __forceinline__ void mma_fwd(float (&acc)[2][NT][4], const Frag<KS>& A, int ks_n, unsigned img, int pitch, int kcol0,
+__device__ __forceinline__ void mma_fwd(float (&acc)[MI][NT][4], const Frag<KS>& A, int ks_n, unsigned img, int pitch, int kcol0,
                                         int j0, int nj, const Lane& L) {
   const unsigned lane_off = (unsigned)((8 * (L.lane >> 4) + (L.lane & 7)) * pitch + 16 * ((L.lane >> 3) & 1));
 #pragma unroll
@@ -188,7 +202,7 @@ __device__ __forceinline__ void mma_fwd(float (&acc)[2][NT][4], const Frag<KS>& 
           unsigned b[4];
           ldsm_x4(b, img + lane_off + (unsigned)(8 * (j0 + 2 * jp) * pitch + (kcol0 + 16 * ks) * 2));
 #pragma unroll
-          for (int mi = 0; mi < 2; ++mi) {
+          for (int mi = 0; mi < MI; ++mi) {
             mma_bf16(acc[mi][2 * jp], A.v[mi][ks], b[0], b[1]);
             if (2 * jp + 1 < nj) mma_bf16(acc[mi][2 * jp + 1], A.v[mi][ks], b[2], b[3]);
           }
@@ -200,7 +214,7 @@ __device__ __forceinline__ void mma_fwd(float (&acc)[2][NT][4], const Frag<KS>& 
 
 // ---- data gradient: acc[mi][j] += DZ[mi][ks] . W[16 ks .., col0 + 8 (j0 + j) ..]  (contraction over the layer's outputs) ----
 template <int KS, int NT>
-__device__ __forceinline__ void mma_dgrad(float (&acc)[2][NT][4], const Frag<KS>& DZ, int ks_n, unsigned img, int pitch, int col0,
+__device__ __forceinline__ void mma_dgrad(float (&acc)[MI][NT][4], const Frag<KS>& DZ, int ks_n, unsigned img, int pitch, int col0,
                                           int j0, int nj, const Lane& L) {
   // ldmatrix.trans: matrix q = lane / 8: rows 16 ks + 8 (q & 1) + (lane & 7), cols col0 + 8 (j + (q >> 1))
   const unsigned lane_off = (unsigned)((8 * ((L.lane >> 3) & 1) + (L.lane & 7)) * pitch + 16 * (L.lane >> 4));
@@ -213,7 +227,7 @@ __device__ __forceinline__ void mma_dgrad(float (&acc)[2][NT][4], const Frag<KS>
           unsigned b[4];
           ldsm_x4_t(b, img + lane_off + (unsigned)(16 * ks * pitch + (col0 + 8 * (j0 + 2 * jp)) * 2));
 #pragma unroll
-          for (int mi = 0; mi < 2; ++mi) {
+          for (int mi = 0; mi < MI; ++mi) {
             mma_bf16(acc[mi][2 * jp], DZ.v[mi][ks], b[0], b[1]);
             if (2 * jp + 1 < nj) mma_bf16(acc[mi][2 * jp + 1], DZ.v[mi][ks], b[2], b[3]);
           }
@@ -224,7 +238,7 @@ __device__ __forceinline__ void mma_dgrad(float (&acc)[2][NT][4], const Frag<KS>
 }
 
 template <int NT>
-__device__ __forceinline__ void acc_bias(float (&acc)[2][NT][4], const float* bias, int j0, int nj, const Lane& L) {
+__device__ __forceinline__ void acc_bias(float (&acc)[MI][NT][4], const float* bias, int j0, int nj, const Lane& L) {
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
     float b0 = 0.f, b1 = 0.f;
@@ -233,31 +247,59 @@ __device__ __forceinline__ void acc_bias(float (&acc)[2][NT][4], const float* bi
       b0 = bb.x; b1 = bb.y;
     }
 #pragma unroll
-    for (int mi = 0; mi < 2; ++mi) { acc[mi][j][0] = b0; acc[mi][j][1] = b1; acc[mi][j][2] = b0; acc[mi][j][3] = b1; }
+    for (int mi = 0; mi < MI; ++mi) { acc[mi][j][0] = b0; acc[mi][j][1] = b1; acc[mi][j][2] = b0; acc[mi][j][3] = b1; }
   }
 }
 template <int NT>
-__device__ __forceinline__ void acc_zero(float (&acc)[2][NT][4]) {
+__device__ __forceinline__ void acc_zero(float (&acc)[MI][NT][4]) {
 #pragma unroll
-  for (int mi = 0; mi < 2; ++mi)
+  for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
     for (int j = 0; j < NT; ++j)
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[mi][j][c] = 0.f;
 }
 
+// activation over accumulator tiles with the kind test hoisted out of the element loops (a per-element switch unrolls into
+// a branch ladder per value: most of the kernel's code size before this)
+template <int NT>
+__device__ __forceinline__ void acc_act(float (&acc)[MI][NT][4], int act) {
+  if (act == MMN_ACT_RELU) {
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[mi][j][c] = fmaxf(acc[mi][j][c], 0.f);
+  } else if (act == MMN_ACT_SIGMOID || act == MMN_ACT_TANH) {
+    const float cin = act == MMN_ACT_TANH ? 2.f : 1.f, ca = act == MMN_ACT_TANH ? -1.f : 0.f;
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[mi][j][c] = nb_squash(acc[mi][j][c], cin, cin, ca);
+  }
+}
+// derivative through the activation OUTPUT a, applied to two packed values
+__device__ __forceinline__ void nb_dact2(int act, float a0, float a1, float& g0, float& g1) {
+  if (act == MMN_ACT_RELU) { g0 = a0 > 0.f ? g0 : 0.f; g1 = a1 > 0.f ? g1 : 0.f; }
+  else if (act == MMN_ACT_SIGMOID) { g0 *= a0 * (1.f - a0); g1 *= a1 * (1.f - a1); }
+  else if (act == MMN_ACT_TANH) { g0 *= 1.f - a0 * a0; g1 *= 1.f - a1 * a1; }
+}
+
 // activation + bf16 pack of accumulator tiles [j0, j0 + nj) into the A fragments of the next layer (columns >= N -> 0)
 template <int KS, int NT>
-__device__ __forceinline__ void acc_to_frag(Frag<KS>& O, const float (&acc)[2][NT][4], int act, int N, int j0, int nj, const Lane& L) {
+__device__ __forceinline__ void acc_to_frag(Frag<KS>& O, float (&acc)[MI][NT][4], int act, int N, int j0, int nj, const Lane& L) {
+  acc_act<NT>(acc, act);
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
     if (j < nj && (j0 + j) < 2 * KS) {
       const int jj = j0 + j;
       const int c0 = 8 * jj + 2 * L.t;
 #pragma unroll
-      for (int mi = 0; mi < 2; ++mi) {
-        float v0 = nb_act(act, acc[mi][j][0]), v1 = nb_act(act, acc[mi][j][1]);
-        float v2 = nb_act(act, acc[mi][j][2]), v3 = nb_act(act, acc[mi][j][3]);
+      for (int mi = 0; mi < MI; ++mi) {
+        float v0 = acc[mi][j][0], v1 = acc[mi][j][1], v2 = acc[mi][j][2], v3 = acc[mi][j][3];
         if (c0 >= N) { v0 = 0.f; v2 = 0.f; }
         if (c0 + 1 >= N) { v1 = 0.f; v3 = 0.f; }
         // tile jj -> k-step jj / 2, half jj % 2: registers (half * 2) [row g] and (half * 2 + 1) [row g + 8]
@@ -270,7 +312,7 @@ __device__ __forceinline__ void acc_to_frag(Frag<KS>& O, const float (&acc)[2][N
 template <int KS>
 __device__ __forceinline__ void frag_zero(Frag<KS>& F) {
 #pragma unroll
-  for (int mi = 0; mi < 2; ++mi)
+  for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
@@ -281,7 +323,7 @@ __device__ __forceinline__ void frag_zero(Frag<KS>& F) {
 template <int KS>
 __device__ __forceinline__ void stash_put(unsigned* base, const Frag<KS>& F, int ks_n, int lane) {
 #pragma unroll
-  for (int mi = 0; mi < 2; ++mi)
+  for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks)
       if (ks < ks_n)
@@ -291,7 +333,7 @@ __device__ __forceinline__ void stash_put(unsigned* base, const Frag<KS>& F, int
 template <int KS>
 __device__ __forceinline__ void stash_get(const unsigned* base, Frag<KS>& F, int ks_n, int lane) {
 #pragma unroll
-  for (int mi = 0; mi < 2; ++mi)
+  for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
@@ -302,13 +344,13 @@ __device__ __forceinline__ void stash_get(const unsigned* base, Frag<KS>& F, int
 template <int KS>
 __device__ __forceinline__ void stage_put(unsigned char* buf, int pitch, int col_off, const Frag<KS>& F, int ks_n, const Lane& L) {
 #pragma unroll
-  for (int mi = 0; mi < 2; ++mi)
+  for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks)
       if (ks < ks_n)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int r = 32 * L.wg + frag_row(L, mi, i), c = frag_col(L, ks, i, 0);
+          const int r = kWarpRows * L.wg + frag_row(L, mi, i), c = frag_col(L, ks, i, 0);
           *reinterpret_cast<unsigned*>(buf + r * pitch + col_off + c * 2) = F.v[mi][ks][i];
         }
 }
@@ -393,16 +435,17 @@ __device__ __forceinline__ void wgrad_items(const unsigned char* buf, int pitch,
 
 // ------------------------------------------------------------------------------------------------
 // x part of a first-layer weight gradient: gW[n][c] += sum_r dz0[r][n] x~[r][c], x~ = bf16(dropout(nan_to_0(x))).
-// Each warp takes 16-column blocks of x over ALL 128 rows of the group: LDG in the forward fragment layout (row g, 4
-// consecutive columns), movmatrix.trans turns the packed pairs into B fragments whose contraction index is the row.
+// The forward sweep left x~ in the group's x stash exactly as its A fragments (16 bytes per thread per k16-step: rows g / g + 8
+// of the warp's 16-row slab, columns 4t .. 4t + 3 of the step).  Each warp takes 16-column blocks (= forward k-steps) over ALL
+// 128 rows of the group: one LDG.128 per forward warp, movmatrix.trans turns the packed column pairs into B fragments whose
+// contraction index is the row.  No conversion work is repeated and x itself is read from HBM once.
 // ------------------------------------------------------------------------------------------------
 template <int MTX>
-__device__ __forceinline__ void wgrad_x(const unsigned char* buf, int pitch, int dz_off, int N, const float* __restrict__ x,
-                                        long long ld, int F, long long row0, long long n_rows, const Drop& drop,
-                                        float* __restrict__ gW, int ldw, const Lane& L) {
+__device__ __forceinline__ void wgrad_x(const unsigned char* buf, int pitch, int dz_off, int N, const float4* __restrict__ xs,
+                                        int F, float* __restrict__ gW, int ldw, const Lane& L) {
+  static_assert(MI == 1, "the x stash layout assumes one m16 tile per warp");
   const unsigned sbuf = smem_addr(buf);
   const int MT = (N + 15) >> 4;
-  const bool vec = ((ld & 3) == 0) && ((F & 3) == 0) && ((reinterpret_cast<size_t>(x) & 15) == 0);
   const bool v2 = (ldw & 1) == 0;
   const int q = L.lane >> 3, lr = L.lane & 7;
   const unsigned a_lane = (unsigned)((8 * (q >> 1) + lr) * pitch + dz_off + 16 * (q & 1));
@@ -416,53 +459,23 @@ __device__ __forceinline__ void wgrad_x(const unsigned char* buf, int pitch, int
       for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[m][j][e] = 0.f;
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      unsigned p0[8], p1[8];
-      float4 v[8];
+    // forward warp w holds rows 16 w + g (registers x, z) and 16 w + g + 8 (registers y, w) of this 16-column block
+    float4 v[kWarpsPerGroup];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        long long r = row0 + 64 * half + 8 * i + L.g;
-        r = r < n_rows ? r : n_rows - 1;                     // rows past the batch: any valid address, their dz is zero
-        const float* src = x + r * ld + c;
-        if (vec) {
-          v[i] = c < F ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-          v[i].x = c + 0 < F ? __ldg(src + 0) : 0.f;
-          v[i].y = c + 1 < F ? __ldg(src + 1) : 0.f;
-          v[i].z = c + 2 < F ? __ldg(src + 2) : 0.f;
-          v[i].w = c + 3 < F ? __ldg(src + 3) : 0.f;
-        }
-      }
+    for (int w = 0; w < kWarpsPerGroup; ++w) v[w] = __ldcg(xs + ((long long)blk * kWarpsPerGroup + w) * 32 + L.lane);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 w = v[i];
-        w.x = w.x != w.x ? 0.f : w.x; w.y = w.y != w.y ? 0.f : w.y;          // 0 * NaN = NaN: never let it reach the MMA
-        w.z = w.z != w.z ? 0.f : w.z; w.w = w.w != w.w ? 0.f : w.w;
-        if (drop.enabled) {
-          const unsigned row = drop.row_base + (unsigned)(64 * half + 8 * i + L.g);
-          bool k0, k1, k2, k3;
-          nb_keep2(drop, row, (unsigned)c, k0, k1);
-          nb_keep2(drop, row, (unsigned)c + 2, k2, k3);
-          w.x = k0 ? w.x * drop.scale : 0.f; w.y = k1 ? w.y * drop.scale : 0.f;
-          w.z = k2 ? w.z * drop.scale : 0.f; w.w = k3 ? w.w * drop.scale : 0.f;
-        }
-        p0[i] = pack_bf16(w.x, w.y);
-        p1[i] = pack_bf16(w.z, w.w);
-      }
+    for (int w = 0; w < kWarpsPerGroup; ++w) {
+      // k16-step = the 16 rows of forward warp w: b0 from rows g (.x = cols 4t, 4t+1 -> tile 0; .z = cols 4t+2, +3 -> tile 1),
+      // b1 from rows g + 8 (.y / .w)
+      const unsigned b00 = movm_t(__float_as_uint(v[w].x)), b01 = movm_t(__float_as_uint(v[w].y));
+      const unsigned b10 = movm_t(__float_as_uint(v[w].z)), b11 = movm_t(__float_as_uint(v[w].w));
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        // k16-step = rows 16 ks .. 16 ks + 15 of this half: b0 from the 8-row group 2 ks, b1 from 2 ks + 1
-        const unsigned b00 = movm_t(p0[2 * ks]), b01 = movm_t(p0[2 * ks + 1]);
-        const unsigned b10 = movm_t(p1[2 * ks]), b11 = movm_t(p1[2 * ks + 1]);
-#pragma unroll
-        for (int m = 0; m < MTX; ++m) {
-          if (m < MT) {
-            unsigned a[4];
-            ldsm_x4_t(a, sbuf + a_lane + (unsigned)((64 * half + 16 * ks) * pitch + 32 * m));
-            mma_bf16(acc[m][0], a, b00, b01);
-            mma_bf16(acc[m][1], a, b10, b11);
-          }
+      for (int m = 0; m < MTX; ++m) {
+        if (m < MT) {
+          unsigned a[4];
+          ldsm_x4_t(a, sbuf + a_lane + (unsigned)(16 * w * pitch + 32 * m));
+          mma_bf16(acc[m][0], a, b00, b01);
+          mma_bf16(acc[m][1], a, b10, b11);
         }
       }
     }
@@ -499,13 +512,14 @@ template <int KSS, int KSH, bool TRAIN>
 __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs args) {
   constexpr int NTS = 2 * KSS;            // n8 tiles of a state-wide output
   constexpr int KSM = KSS > KSH ? KSS : KSH;
-  constexpr int NTX = 2 * KSM;            // n8 tiles of an x-fed layer's output (hidden, or the state for 1-layer encoders)
+  constexpr int NTX = 2 * KSH;            // n8 tiles of an x-fed layer's output (a hidden layer; the host picks an instantiation
+                                          // with 16 KSH >= state for 1-layer encoders)
   const StepArgs& A = args.a;
   MMN_DYN_SMEM(smem_raw);
 
   Lane L;
   L.lane = threadIdx.x & 31; L.g = L.lane >> 2; L.t = L.lane & 3;
-  L.warp = threadIdx.x >> 5; L.wg = L.warp & 3; L.gi = L.warp >> 2;
+  L.warp = threadIdx.x >> 5; L.wg = L.warp % kWarpsPerGroup; L.gi = L.warp / kWarpsPerGroup;
   const int tid = threadIdx.x;
 
   // ---- carve shared memory ----
@@ -547,16 +561,17 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
   const long long n_tiles = (A.n_rows + kTileRows - 1) / kTileRows;
   unsigned* my_stash = TRAIN ? args.stash + ((long long)blockIdx.x * (kNbGroups * kWarpsPerGroup) + L.warp) * args.stash_words_per_warp
                              : nullptr;
+  float4* xstash_group = TRAIN ? args.xstash + ((long long)blockIdx.x * kNbGroups + L.gi) * args.xstash_vec_per_group : nullptr;
   Drop nodrop;
   nodrop.enabled = 0; nodrop.seed_mix = 0; nodrop.thr = 0; nodrop.row_base = 0; nodrop.scale = 1.f;
 
   for (long long tile = (long long)blockIdx.x * kNbGroups + L.gi; tile < n_tiles; tile += (long long)gridDim.x * kNbGroups) {
     const long long row0 = tile * kTileRows;                    // first row of the group's tile
-    const long long wrow0 = row0 + 32 * L.wg;                   // first row of this warp
-    group_bar(L.gi);                                            // previous tile's readers of ys / tile_any / staging are done
+    const long long wrow0 = row0 + kWarpRows * L.wg;                   // first row of this warp
+    group_bar(L.gi, kGroupThreads);                                            // previous tile's readers of ys / tile_any / staging are done
     // ---- tile prologue: targets as bytes, flags ----
     if (A.targets) {
-      for (int idx = L.wg * 32 + L.lane; idx < kTileRows * D; idx += 128) {
+      for (int idx = L.wg * 32 + L.lane; idx < kTileRows * D; idx += kGroupThreads) {
         const int r = idx / D, d = idx - r * D;
         long long y = 0;
         if (row0 + r < A.n_rows) y = A.targets[(row0 + r) * D + d];
@@ -569,7 +584,7 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
     // valid-row bits of this thread's 4 rows: bit (2 mi + h)
     unsigned valid = 0;
 #pragma unroll
-    for (int mi = 0; mi < 2; ++mi)
+    for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
       for (int h = 0; h < 2; ++h)
         if (wrow0 + 16 * mi + L.g + 8 * h < A.n_rows) valid |= 1u << (2 * mi + h);
@@ -578,7 +593,7 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
       const int nv = __popc(valid);
       if (nv) atomicAdd(&cnt[0], nv);
     }
-    group_bar(L.gi);
+    group_bar(L.gi, kGroupThreads);
 
     // ---- initial state (state.py:29-32), rounded to bf16 like every state ----
     Frag<KSS> sA;
@@ -591,18 +606,18 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
         lo = pack_bf16(a.x, a.y); hi = pack_bf16(b.x, b.y);
       }
 #pragma unroll
-      for (int mi = 0; mi < 2; ++mi) { sA.v[mi][ks][0] = lo; sA.v[mi][ks][1] = lo; sA.v[mi][ks][2] = hi; sA.v[mi][ks][3] = hi; }
+      for (int mi = 0; mi < MI; ++mi) { sA.v[mi][ks][0] = lo; sA.v[mi][ks][1] = lo; sA.v[mi][ks][2] = hi; sA.v[mi][ks][3] = hi; }
     }
 
     // =============================================================================================
     // decoders on the state in sA (multimodn.py:141-157, 176-191); TRAIN: followed by their backward pass, G += dLoss/ds
     // =============================================================================================
-    auto decoders = [&](int hist_row, unsigned mask4, bool is_last_enc, float (&G)[2][NTS][4]) {
+    auto decoders = [&](int hist_row, unsigned mask4, bool is_last_enc, float (&G)[MI][NTS][4]) {
       for (int d = 0; d < D; ++d) {
         const NbDec& dec = P.dec[d];
         const int nl = dec.n_layers, C = dec.C;
         Frag<KSH> h1, h2;
-        float head[2][2][4];
+        float head[MI][2][4];
         // ---- forward chain ----
         {
           const NbLayer& l0 = dec.L[0];
@@ -614,7 +629,7 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
             for (int pass = 0; pass < (KSH + 1) / 2; ++pass) {
               const int j0 = 4 * pass, nj = min(4, l0.n_tiles - j0);
               if (nj > 0) {
-                float acc[2][4][4];
+                float acc[MI][4][4];
                 acc_bias<4>(acc, reinterpret_cast<const float*>(arena + l0.bias_off), j0, nj, L);
                 mma_fwd<KSS, 4>(acc, sA, kss, s_arena + l0.img_off, l0.pitch, 0, j0, nj, L);
                 acc_to_frag<KSH, 4>(h1, acc, l0.act, l0.N, j0, min(4, l0.n16 / 8 - j0), L);
@@ -626,7 +641,7 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
               for (int pass = 0; pass < (KSH + 1) / 2; ++pass) {
                 const int j0 = 4 * pass, nj = min(4, l1.n_tiles - j0);
                 if (nj > 0) {
-                  float acc[2][4][4];
+                  float acc[MI][4][4];
                   acc_bias<4>(acc, reinterpret_cast<const float*>(arena + l1.bias_off), j0, nj, L);
                   mma_fwd<KSH, 4>(acc, h1, l1.ka_pad / 16, s_arena + l1.img_off, l1.pitch, 0, j0, nj, L);
                   acc_to_frag<KSH, 4>(h2, acc, l1.act, l1.N, j0, min(4, l1.n16 / 8 - j0), L);
@@ -645,12 +660,12 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
         float ce_sum = 0.f;
         unsigned pk1 = 0, pk2 = 0;
 #pragma unroll
-        for (int mi = 0; mi < 2; ++mi) {
+        for (int mi = 0; mi < MI; ++mi) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int bit = 2 * mi + h;
             const bool rv = (valid >> bit) & 1u, m = (mask4 >> bit) & 1u;
-            const int r = 32 * L.wg + 16 * mi + L.g + 8 * h;               // row inside the group's tile
+            const int r = kWarpRows * L.wg + 16 * mi + L.g + 8 * h;               // row inside the group's tile
             const int c0 = 2 * L.t, c1 = 2 * L.t + 1;
             const float p0 = nb_act(hact, head[mi][0][2 * h]), p1 = nb_act(hact, head[mi][0][2 * h + 1]);
             const bool ok0 = c0 < C, ok1 = c1 < C;
@@ -677,11 +692,11 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
             if (A.targets) {
               const int y = ys[r * MMN_MAX_DECODERS + d];
               const float mx = bv;
-              const float e0 = ok0 ? expf(p0 - mx) : 0.f, e1 = ok1 ? expf(p1 - mx) : 0.f;
+              const float e0 = ok0 ? __expf(p0 - mx) : 0.f, e1 = ok1 ? __expf(p1 - mx) : 0.f;
               const float se = quad_sum(e0 + e1);
               const float py = quad_sum((c0 == y ? p0 : 0.f) + (c1 == y && ok1 ? p1 : 0.f));
               if (m && L.t == 0) {
-                ce_sum += mx + logf(se) - py;
+                ce_sum += mx + __logf(se) - py;
                 pk1 += (pred == y ? 1u : 0u);
                 if (C == 2) {
                   pk1 += (pred == 1 && y == 1 ? 1u << 8 : 0u) + (pred == 0 && y == 0 ? 1u << 16 : 0u) + (pred == 1 && y == 0 ? 1u << 24 : 0u);
@@ -693,9 +708,7 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
                 const float coef = m ? A.c_err : 0.f, inv = __fdividef(1.f, se);
                 float d0 = ok0 ? coef * (e0 * inv - (c0 == y ? 1.f : 0.f)) : 0.f;
                 float d1 = ok1 ? coef * (e1 * inv - (c1 == y ? 1.f : 0.f)) : 0.f;
-                if (hact == MMN_ACT_SIGMOID) { d0 *= p0 * (1.f - p0); d1 *= p1 * (1.f - p1); }
-                else if (hact == MMN_ACT_TANH) { d0 *= 1.f - p0 * p0; d1 *= 1.f - p1 * p1; }
-                else if (hact == MMN_ACT_RELU) { d0 = p0 > 0.f ? d0 : 0.f; d1 = p1 > 0.f ? d1 : 0.f; }
+                nb_dact2(hact, p0, p1, d0, d1);
                 dzh.v[mi][0][h] = pack_bf16(d0, d1);          // register h: row g + 8 h, k = classes 2t, 2t + 1
               }
             }
@@ -722,7 +735,7 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
         // head layer
         {
           const NbLayer& lh = dec.L[nl - 1];
-          group_bar(L.gi);                                    // staging buffer free
+          group_bar(L.gi, kGroupThreads);                                    // staging buffer free
           if (nl == 1) stage_put<KSS>(stage, stage_pitch, 0, sA, kss, L);
           else stage_put<KSH>(stage, stage_pitch, 0, nl == 3 ? h2 : h1, lh.ka_pad / 16, L);
           stage_put<1>(stage, stage_pitch, P.stage_dz_off, dzh, 1, L);
@@ -737,7 +750,7 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
             for (int pass = 0; pass < (KSH + 1) / 2; ++pass) {
               const int j0 = 4 * pass, nj = min(4, lh.ka_pad / 8 - j0);
               if (nj > 0) {
-                float acc[2][4][4];
+                float acc[MI][4][4];
                 acc_zero<4>(acc);
                 mma_dgrad<1, 4>(acc, dzh, 1, s_arena + lh.img_off, lh.pitch, 0, j0, nj, L);
                 // dz = da * act'(h): through the activation OUTPUT held in the forward fragments
@@ -746,15 +759,13 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
                   if (j < nj) {
                     const int jj = j0 + j;
 #pragma unroll
-                    for (int mi = 0; mi < 2; ++mi) {
+                    for (int mi = 0; mi < MI; ++mi) {
 #pragma unroll
                       for (int hh = 0; hh < 2; ++hh) {
                         const unsigned hv = hin.v[mi][jj >> 1][(jj & 1) * 2 + hh];
                         const float a0 = bf16_lo(hv), a1 = bf16_hi(hv);
                         float g0 = acc[mi][j][2 * hh], g1 = acc[mi][j][2 * hh + 1];
-                        if (pact == MMN_ACT_RELU) { g0 = a0 > 0.f ? g0 : 0.f; g1 = a1 > 0.f ? g1 : 0.f; }
-                        else if (pact == MMN_ACT_SIGMOID) { g0 *= a0 * (1.f - a0); g1 *= a1 * (1.f - a1); }
-                        else if (pact == MMN_ACT_TANH) { g0 *= 1.f - a0 * a0; g1 *= 1.f - a1 * a1; }
+                        nb_dact2(pact, a0, a1, g0, g1);
                         dz.v[mi][jj >> 1][(jj & 1) * 2 + hh] = pack_bf16(g0, g1);
                       }
                     }
@@ -763,12 +774,12 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
               }
             }
           }
-          group_bar(L.gi);                                    // staged rows of every warp are visible
+          group_bar(L.gi, kGroupThreads);                                    // staged rows of every warp are visible
           wgrad_items(stage, stage_pitch, P.stage_dz_off, lh.N, lh.ka, grads + lh.w_off, lh.ktot, 0, grads + lh.b_off, L);
           // middle layer (nl == 3): dz is the gradient at layer 1's output
           if (nl == 3) {
             const NbLayer& l1 = dec.L[1];
-            group_bar(L.gi);
+            group_bar(L.gi, kGroupThreads);
             stage_put<KSH>(stage, stage_pitch, 0, h1, l1.ka_pad / 16, L);
             stage_put<KSH>(stage, stage_pitch, P.stage_dz_off, dz, l1.n16 / 16, L);
             Frag<KSH> dz1;
@@ -777,7 +788,7 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
             for (int pass = 0; pass < (KSH + 1) / 2; ++pass) {
               const int j0 = 4 * pass, nj = min(4, l1.ka_pad / 8 - j0);
               if (nj > 0) {
-                float acc[2][4][4];
+                float acc[MI][4][4];
                 acc_zero<4>(acc);
                 mma_dgrad<KSH, 4>(acc, dz, l1.n16 / 16, s_arena + l1.img_off, l1.pitch, 0, j0, nj, L);
 #pragma unroll
@@ -785,15 +796,13 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
                   if (j < nj) {
                     const int jj = j0 + j;
 #pragma unroll
-                    for (int mi = 0; mi < 2; ++mi) {
+                    for (int mi = 0; mi < MI; ++mi) {
 #pragma unroll
                       for (int hh = 0; hh < 2; ++hh) {
                         const unsigned hv = h1.v[mi][jj >> 1][(jj & 1) * 2 + hh];
                         const float a0 = bf16_lo(hv), a1 = bf16_hi(hv);
                         float g0 = acc[mi][j][2 * hh], g1 = acc[mi][j][2 * hh + 1];
-                        if (pact == MMN_ACT_RELU) { g0 = a0 > 0.f ? g0 : 0.f; g1 = a1 > 0.f ? g1 : 0.f; }
-                        else if (pact == MMN_ACT_SIGMOID) { g0 *= a0 * (1.f - a0); g1 *= a1 * (1.f - a1); }
-                        else if (pact == MMN_ACT_TANH) { g0 *= 1.f - a0 * a0; g1 *= 1.f - a1 * a1; }
+                        nb_dact2(pact, a0, a1, g0, g1);
                         dz1.v[mi][jj >> 1][(jj & 1) * 2 + hh] = pack_bf16(g0, g1);
                       }
                     }
@@ -801,18 +810,18 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
                 }
               }
             }
-            group_bar(L.gi);
+            group_bar(L.gi, kGroupThreads);
             wgrad_items(stage, stage_pitch, P.stage_dz_off, l1.N, l1.ka, grads + l1.w_off, l1.ktot, 0, grads + l1.b_off, L);
             dz = dz1;
           }
           // first layer (nl >= 2): input = the state; its data gradient accumulates straight into G
           if (nl > 1) {
             const NbLayer& l0 = dec.L[0];
-            group_bar(L.gi);
+            group_bar(L.gi, kGroupThreads);
             stage_put<KSS>(stage, stage_pitch, 0, sA, kss, L);
             stage_put<KSH>(stage, stage_pitch, P.stage_dz_off, dz, l0.n16 / 16, L);
             mma_dgrad<KSH, NTS>(G, dz, l0.n16 / 16, s_arena + l0.img_off, l0.pitch, 0, 0, 2 * kss, L);
-            group_bar(L.gi);
+            group_bar(L.gi, kGroupThreads);
             wgrad_items(stage, stage_pitch, P.stage_dz_off, l0.N, l0.ka, grads + l0.w_off, l0.ktot, 0, grads + l0.b_off, L);
           }
         }
@@ -827,25 +836,25 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
       const NbLayer& ly = enc.L[0];
       const float* bias = reinterpret_cast<const float*>(arena + ly.bias_off);
       const unsigned img = s_arena + ly.img_off;
-      float acc[2][NTX][4];
+      float acc[MI][NTX][4];
       acc_bias<NTX>(acc, bias, 0, ly.n_tiles, L);
       const float* x = A.x[pos];
       const long long ld = A.x_ld[pos];
       const int F = enc.F, ksx = ly.ka_pad / 16;
       const bool vec = ((ld & 3) == 0) && ((F & 3) == 0) && ((reinterpret_cast<size_t>(x) & 15) == 0);
-      const float* rp[2][2];
+      const float* rp[MI][2];
 #pragma unroll
-      for (int mi = 0; mi < 2; ++mi)
+      for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           long long r = wrow0 + 16 * mi + L.g + 8 * hh;
           r = r < A.n_rows ? r : A.n_rows - 1;
           rp[mi][hh] = x + r * ld + 4 * L.t;
         }
-      auto load4 = [&](int ks, float4 (&v)[2][2]) {
+      auto load4 = [&](int ks, float4 (&v)[MI][2]) {
         const int c = 16 * ks + 4 * L.t;
 #pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
+        for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             const float* src = rp[mi][hh] + 16 * ks;
@@ -858,54 +867,68 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
             }
           }
       };
-      float4 nx0[2][2], nx1[2][2];
-      load4(0, nx0);
-      if (ksx > 1) load4(1, nx1);
-      for (int ks = 0; ks < ksx; ++ks) {
-        float4 cur[2][2];
+      // ring of XC k16-steps in registers: the loads of step ks + XC are issued as soon as step ks has been converted, so
+      // 2 MI XC LDG.128 per thread stay in flight behind the conversion + MMAs (HBM latency), in 8 MI XC registers
+      constexpr int XC = 4;
+      float4 ring[XC][MI][2];
 #pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
+      for (int u = 0; u < XC; ++u)
+        if (u < ksx) load4(u, ring[u]);
+      float4* xs = TRAIN ? xstash_group + ((long long)enc.xs_off * kWarpsPerGroup + L.wg) * 32 + L.lane : nullptr;
+      for (int ks0 = 0; ks0 < ksx; ks0 += XC) {
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) { cur[mi][hh] = nx0[mi][hh]; nx0[mi][hh] = nx1[mi][hh]; }
-        if (ks + 2 < ksx) load4(ks + 2, nx1);
-        Frag<1> xa;
-        const int c = 16 * ks + 4 * L.t;
+        for (int u = 0; u < XC; ++u) {
+          const int ks = ks0 + u;
+          if (ks < ksx) {
+            Frag<1> xa;
+            const int c = 16 * ks + 4 * L.t;
 #pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
+            for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            float4 w = cur[mi][hh];
-            const bool bad = (w.x != w.x) | (w.y != w.y) | (w.z != w.z) | (w.w != w.w);
-            if (bad) {
-              nanbits |= 1u << (2 * mi + hh);              // NaN marks the modality missing for this row
-              w.x = w.x != w.x ? 0.f : w.x; w.y = w.y != w.y ? 0.f : w.y;
-              w.z = w.z != w.z ? 0.f : w.z; w.w = w.w != w.w ? 0.f : w.w;
+              for (int hh = 0; hh < 2; ++hh) {
+                float4 w = ring[u][mi][hh];
+                const bool bad = (w.x != w.x) | (w.y != w.y) | (w.z != w.z) | (w.w != w.w);
+                if (bad) {
+                  nanbits |= 1u << (2 * mi + hh);              // NaN marks the modality missing for this row
+                  w.x = w.x != w.x ? 0.f : w.x; w.y = w.y != w.y ? 0.f : w.y;
+                  w.z = w.z != w.z ? 0.f : w.z; w.w = w.w != w.w ? 0.f : w.w;
+                }
+                if (drop.enabled) {
+                  const unsigned row = drop.row_base + (unsigned)(kWarpRows * L.wg + 16 * mi + L.g + 8 * hh);
+                  bool k0, k1, k2, k3;
+                  nb_keep2(drop, row, (unsigned)c, k0, k1);
+                  nb_keep2(drop, row, (unsigned)c + 2, k2, k3);
+                  w.x = k0 ? w.x * drop.scale : 0.f; w.y = k1 ? w.y * drop.scale : 0.f;
+                  w.z = k2 ? w.z * drop.scale : 0.f; w.w = k3 ? w.w * drop.scale : 0.f;
+                }
+                // fragment registers hh (row g + 8 hh, "k 2t, 2t+1") and 2 + hh ("k 2t+8, 2t+9"): the image's x columns are
+                // permuted to match (nb_image_layer)
+                xa.v[mi][0][hh] = pack_bf16(w.x, w.y);
+                xa.v[mi][0][2 + hh] = pack_bf16(w.z, w.w);
+              }
+            if (ks + XC < ksx) load4(ks + XC, ring[u]);
+            if (TRAIN) {
+              // the converted fragments are the B operand of the first-layer weight gradient (wgrad_x): 16 bytes per thread
+#pragma unroll
+              for (int mi = 0; mi < MI; ++mi)
+                __stcg(xs + ((long long)ks * kWarpsPerGroup * MI + mi) * 32,
+                       make_float4(__uint_as_float(xa.v[mi][0][0]), __uint_as_float(xa.v[mi][0][1]),
+                                   __uint_as_float(xa.v[mi][0][2]), __uint_as_float(xa.v[mi][0][3])));
             }
-            if (drop.enabled) {
-              const unsigned row = drop.row_base + (unsigned)(32 * L.wg + 16 * mi + L.g + 8 * hh);
-              bool k0, k1, k2, k3;
-              nb_keep2(drop, row, (unsigned)c, k0, k1);
-              nb_keep2(drop, row, (unsigned)c + 2, k2, k3);
-              w.x = k0 ? w.x * drop.scale : 0.f; w.y = k1 ? w.y * drop.scale : 0.f;
-              w.z = k2 ? w.z * drop.scale : 0.f; w.w = k3 ? w.w * drop.scale : 0.f;
-            }
-            // fragment registers hh (row g + 8 hh, "k 2t, 2t+1") and 2 + hh ("k 2t+8, 2t+9"): the image's x columns are
-            // permuted to match (nb_image_layer)
-            xa.v[mi][0][hh] = pack_bf16(w.x, w.y);
-            xa.v[mi][0][2 + hh] = pack_bf16(w.z, w.w);
+            mma_fwd<1, NTX>(acc, xa, 1, img, ly.pitch, 16 * ks, 0, ly.n_tiles, L);
           }
-        mma_fwd<1, NTX>(acc, xa, 1, img, ly.pitch, 16 * ks, 0, ly.n_tiles, L);
+        }
       }
       if (ly.has_state) {
         if (drop.enabled) {
           Frag<KSS> sd;
 #pragma unroll
-          for (int mi = 0; mi < 2; ++mi)
+          for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
             for (int ks = 0; ks < KSS; ++ks)
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const unsigned row = drop.row_base + (unsigned)(32 * L.wg + frag_row(L, mi, i));
+                const unsigned row = drop.row_base + (unsigned)(kWarpRows * L.wg + frag_row(L, mi, i));
                 const unsigned col = (unsigned)(F + frag_col(L, ks, i, 0));
                 bool k0, k1;
                 nb_keep2(drop, row, col, k0, k1);
@@ -929,7 +952,7 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
       for (int pass = 0; pass < (KSM + 1) / 2; ++pass) {
         const int j0 = 4 * pass, nj = min(4, ly.n_tiles - j0), nzero = min(4, n_out_tiles - j0);
         if (nzero > 0) {
-          float acc[2][4][4];
+          float acc[MI][4][4];
           acc_bias<4>(acc, bias, j0, max(nj, 0), L);
           if (nj > 0) {
             mma_fwd<KSH, 4>(acc, in, ly.ka_pad / 16, img, ly.pitch, 0, j0, nj, L);
@@ -966,7 +989,7 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
     auto select_state = [&](int e, const Frag<KSS>& cand, unsigned present4) {
       float sc = 0.f;
 #pragma unroll
-      for (int mi = 0; mi < 2; ++mi)
+      for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
         for (int ks = 0; ks < KSS; ++ks)
 #pragma unroll
@@ -999,7 +1022,7 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
       return drop;
     };
 
-    float Gdummy[2][NTS][4];
+    float Gdummy[MI][NTS][4];
     if (!TRAIN) decoders(0, valid, false, Gdummy);
 
     // ---- forward sweep over the encoding sequence (multimodn.py:159-191) ----
@@ -1023,7 +1046,7 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
     }
     if (!TRAIN && A.final_state) {
 #pragma unroll
-      for (int mi = 0; mi < 2; ++mi)
+      for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
         for (int ks = 0; ks < KSS; ++ks)
 #pragma unroll
@@ -1041,9 +1064,9 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
     // reverse sweep: G = dLoss/ds_k for the warp's rows, fp32, accumulator layout
     // =============================================================================================
     if (TRAIN) {
-      float G[2][NTS][4];
+      float G[MI][NTS][4];
       acc_zero<NTS>(G);
-      group_bar(L.gi);                                       // tile_any of every warp is visible
+      group_bar(L.gi, kGroupThreads);                                       // tile_any of every warp is visible
       float* grads = A.grads;
       for (int k = Ls; k >= 0; --k) {
         const unsigned mask4 = (unsigned)(pm >> (4 * k)) & 0xFu;
@@ -1069,7 +1092,7 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
                 lo = pack_bf16(a.x, a.y); hi = pack_bf16(b.x, b.y);
               }
 #pragma unroll
-              for (int mi = 0; mi < 2; ++mi) { sP.v[mi][ks][0] = lo; sP.v[mi][ks][1] = lo; sP.v[mi][ks][2] = hi; sP.v[mi][ks][3] = hi; }
+              for (int mi = 0; mi < MI; ++mi) { sP.v[mi][ks][0] = lo; sP.v[mi][ks][1] = lo; sP.v[mi][ks][2] = hi; sP.v[mi][ks][3] = hi; }
             }
           }
         }
@@ -1077,7 +1100,7 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
         const NbLayer& ll = enc.L[nl - 1];
         Frag<KSS> dzS;
 #pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
+        for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
           for (int ks = 0; ks < KSS; ++ks)
 #pragma unroll
@@ -1092,9 +1115,7 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
                 G[mi][jj][cc] = g0; G[mi][jj][cc + 1] = g1;
                 if ((mask4 >> (2 * mi + (i & 1))) & 1u) {
                   float z0 = g0, z1 = g1;
-                  if (ll.act == MMN_ACT_RELU) { z0 = a0 > 0.f ? z0 : 0.f; z1 = a1 > 0.f ? z1 : 0.f; }
-                  else if (ll.act == MMN_ACT_SIGMOID) { z0 *= a0 * (1.f - a0); z1 *= a1 * (1.f - a1); }
-                  else if (ll.act == MMN_ACT_TANH) { z0 *= 1.f - a0 * a0; z1 *= 1.f - a1 * a1; }
+                  nb_dact2(ll.act, a0, a1, z0, z1);
                   outv = pack_bf16(z0, z1);
                 }
               }
@@ -1103,20 +1124,20 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
         const Drop drop = make_drop(e);
         // the carry select: present rows take the data gradient w.r.t. the state columns (through the dropout mask), absent
         // rows keep G; then u_k leaves with the opposite sign (it belongs to s_{k-1}: multimodn.py:165,174)
-        auto carry_into_G = [&](const float (&cacc)[2][4][4], int j0, int nj, int Fcat) {
+        auto carry_into_G = [&](const float (&cacc)[MI][4][4], int j0, int nj, int Fcat) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             if (j < nj) {
               const int jj = j0 + j;
 #pragma unroll
-              for (int mi = 0; mi < 2; ++mi)
+              for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                   const unsigned a = sA.v[mi][jj >> 1][(jj & 1) * 2 + hh], b = sP.v[mi][jj >> 1][(jj & 1) * 2 + hh];
                   const float u0 = A.c_sc * (bf16_lo(a) - bf16_lo(b)), u1 = A.c_sc * (bf16_hi(a) - bf16_hi(b));
                   float c0 = cacc[mi][j][2 * hh], c1 = cacc[mi][j][2 * hh + 1];
                   if (drop.enabled) {
-                    const unsigned row = drop.row_base + (unsigned)(32 * L.wg + 16 * mi + L.g + 8 * hh);
+                    const unsigned row = drop.row_base + (unsigned)(kWarpRows * L.wg + 16 * mi + L.g + 8 * hh);
                     bool k0, k1;
                     nb_keep2(drop, row, (unsigned)(Fcat + 8 * jj + 2 * L.t), k0, k1);
                     c0 = k0 ? c0 * drop.scale : 0.f;
@@ -1139,7 +1160,7 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
           // input of this layer: x (j == 0) or the stashed output of layer j - 1
           Frag<KSH> hin;
           if (j > 0) stash_get<KSH>(stash_step + enc.stash_off[j - 1] * 32, hin, ly.ka_pad / 16, L.lane);
-          group_bar(L.gi);                                  // staging buffer free
+          group_bar(L.gi, kGroupThreads);                                  // staging buffer free
           if (last) stage_put<KSS>(stage, stage_pitch, P.stage_dz_off, dzS, ks_dz, L);
           else stage_put<KSH>(stage, stage_pitch, P.stage_dz_off, dzH, ks_dz, L);
           if (j > 0) stage_put<KSH>(stage, stage_pitch, 0, hin, ly.ka_pad / 16, L);
@@ -1151,7 +1172,7 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
             for (int pass = 0; pass < (KSH + 1) / 2; ++pass) {
               const int j0 = 4 * pass, nj = min(4, ly.ka_pad / 8 - j0);
               if (nj > 0) {
-                float acc[2][4][4];
+                float acc[MI][4][4];
                 acc_zero<4>(acc);
                 if (last) mma_dgrad<KSS, 4>(acc, dzS, ks_dz, img, ly.pitch, 0, j0, nj, L);
                 else mma_dgrad<KSH, 4>(acc, dzH, ks_dz, img, ly.pitch, 0, j0, nj, L);
@@ -1160,15 +1181,13 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
                   if (jq < nj) {
                     const int jj = j0 + jq;
 #pragma unroll
-                    for (int mi = 0; mi < 2; ++mi)
+                    for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
                       for (int hh = 0; hh < 2; ++hh) {
                         const unsigned hv = hin.v[mi][jj >> 1][(jj & 1) * 2 + hh];
                         const float a0 = bf16_lo(hv), a1 = bf16_hi(hv);
                         float g0 = acc[mi][jq][2 * hh], g1 = acc[mi][jq][2 * hh + 1];
-                        if (pact == MMN_ACT_RELU) { g0 = a0 > 0.f ? g0 : 0.f; g1 = a1 > 0.f ? g1 : 0.f; }
-                        else if (pact == MMN_ACT_SIGMOID) { g0 *= a0 * (1.f - a0); g1 *= a1 * (1.f - a1); }
-                        else if (pact == MMN_ACT_TANH) { g0 *= 1.f - a0 * a0; g1 *= 1.f - a1 * a1; }
+                        nb_dact2(pact, a0, a1, g0, g1);
                         dzPrev.v[mi][jj >> 1][(jj & 1) * 2 + hh] = pack_bf16(g0, g1);
                       }
                   }
@@ -1176,28 +1195,28 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
               }
             }
           }
-          group_bar(L.gi);                                  // staged rows visible
+          group_bar(L.gi, kGroupThreads);                                  // staged rows visible
           if (j > 0) {
             wgrad_items(stage, stage_pitch, P.stage_dz_off, ly.N, ly.ka, grads + ly.w_off, ly.ktot, 0, grads + ly.b_off, L);
           } else {
             // x columns straight from global memory (the bias gradient rides with the state job, or alone)
-            wgrad_x<KSM>(stage, stage_pitch, P.stage_dz_off, ly.N, A.x[pos], A.x_ld[pos], enc.F, row0, A.n_rows,
-                         drop, grads + ly.w_off, ly.ktot, L);
+            wgrad_x<KSH>(stage, stage_pitch, P.stage_dz_off, ly.N, xstash_group + (long long)enc.xs_off * kWarpsPerGroup * 32,
+                         enc.F, grads + ly.w_off, ly.ktot, L);
             if (!ly.has_state)
               wgrad_items(stage, stage_pitch, P.stage_dz_off, ly.N, 0, grads + ly.w_off, ly.ktot, 0, grads + ly.b_off, L);
           }
           if (ly.has_state) {
             // second job on the same dz: a = the state columns [s_{k-1} with the dropout mask]; and the carry
-            group_bar(L.gi);                                // readers of the a part are done (dz part stays)
+            group_bar(L.gi, kGroupThreads);                                // readers of the a part are done (dz part stays)
             if (drop.enabled) {
               Frag<KSS> sd;
 #pragma unroll
-              for (int mi = 0; mi < 2; ++mi)
+              for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
                 for (int ks = 0; ks < KSS; ++ks)
 #pragma unroll
                   for (int i = 0; i < 4; ++i) {
-                    const unsigned row = drop.row_base + (unsigned)(32 * L.wg + frag_row(L, mi, i));
+                    const unsigned row = drop.row_base + (unsigned)(kWarpRows * L.wg + frag_row(L, mi, i));
                     bool k0, k1;
                     nb_keep2(drop, row, (unsigned)(enc.F + frag_col(L, ks, i, 0)), k0, k1);
                     const unsigned sv = sP.v[mi][ks][i];
@@ -1211,14 +1230,14 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
             for (int pass = 0; pass < (KSS + 1) / 2; ++pass) {
               const int j0 = 4 * pass, nj = min(4, 2 * kss - j0);
               if (nj > 0) {
-                float acc[2][4][4];
+                float acc[MI][4][4];
                 acc_zero<4>(acc);
                 if (last) mma_dgrad<KSS, 4>(acc, dzS, ks_dz, img, ly.pitch, ly.ka_pad, j0, nj, L);
                 else mma_dgrad<KSH, 4>(acc, dzH, ks_dz, img, ly.pitch, ly.ka_pad, j0, nj, L);
                 carry_into_G(acc, j0, nj, j == 0 ? enc.F : 0);
               }
             }
-            group_bar(L.gi);
+            group_bar(L.gi, kGroupThreads);
             wgrad_items(stage, stage_pitch, P.stage_dz_off, ly.N, S, grads + ly.w_off, ly.ktot, ly.ka,
                         (j > 0) ? nullptr : grads + ly.b_off, L);
           }
@@ -1232,7 +1251,7 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
         if (jj < 2 * kss) {
           float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-          for (int mi = 0; mi < 2; ++mi)
+          for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh)
               if ((valid >> (2 * mi + hh)) & 1u) { s0 += G[mi][jj][2 * hh]; s1 += G[mi][jj][2 * hh + 1]; }

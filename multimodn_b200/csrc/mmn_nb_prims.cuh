@@ -62,8 +62,8 @@ __device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
 __device__ __forceinline__ void red_add(float* p, float a) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory"); }
-// barrier over the 128 threads of one group (ids 1, 2: id 0 is __syncthreads)
-__device__ __forceinline__ void group_bar(int gi) { asm volatile("bar.sync %0, 128;" ::"r"(gi + 1) : "memory"); }
+// barrier over the threads of one group (ids 1, 2: id 0 is __syncthreads)
+__device__ __forceinline__ void group_bar(int gi, int n_threads) { asm volatile("bar.sync %0, %1;" ::"r"(gi + 1), "r"(n_threads) : "memory"); }
 #else
 static inline unsigned pack_bf16(float lo, float hi) { return bf16_bits(lo) | (bf16_bits(hi) << 16); }
 static inline float bf16_lo(unsigned p) { return __uint_as_float(p << 16); }
@@ -133,7 +133,7 @@ static inline void mma_bf16(float (&c)[4], const unsigned (&a)[4], unsigned b0, 
 }
 static inline void red_add_v2(float* p, float a, float b) { p[0] += a; p[1] += b; }
 static inline void red_add(float* p, float a) { *p += a; }
-static inline void group_bar(int gi) { emu::named_barrier_id(gi + 1, 128); }
+static inline void group_bar(int gi, int n_threads) { emu::named_barrier_id(gi + 1, n_threads); }
 #endif
 
 }  // namespace nb

@@ -400,7 +400,8 @@ class MultiModN(nn.Module):
             return
         h = float(self._dp_hash)
         self._dp_hash = 0
-        t = torch.tensor([h, -h], dtype=torch.float64, device=rt.device)
+        t = torch.full((2,), h, dtype=torch.float64, device=rt.device)     # fill kernels: no host-to-device copy, no sync
+        t[1].neg_()
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX, group=self._dp[2])
         rt._dp_err = torch.maximum(rt._dp_err, (t[0] + t[1] != 0).to(torch.int64))
 

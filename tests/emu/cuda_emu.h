@@ -227,6 +227,8 @@ template <class T> static inline T __ldcs(const T* p) { return *p; }
 template <class T> static inline void __stcg(T* p, T v) { *p = v; }
 template <class T> static inline void __stcs(T* p, T v) { *p = v; }
 static inline float __fdividef(float a, float b) { return a / b; }
+#define __expf(a) expf(a)      /* glibc declares __expf / __logf itself */
+#define __logf(a) logf(a)
 static inline float __saturatef(float a) { return a < 0 ? 0 : (a > 1 ? 1 : a); }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }

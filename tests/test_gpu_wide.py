@@ -20,6 +20,13 @@ from model_utils import model_from_spec, GradTap, tapped_flat
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def force_layerwise_regime(monkeypatch):
+    """narrow models under precision="bf16" default to the per-tile kernel (tests/test_gpu_nb.py); this file is about the
+    layer-wise tcgen05 regime, which MMN_ENGINE=wide selects for any model"""
+    monkeypatch.setenv("MMN_ENGINE", "wide")
 HIST = ("loss", "accuracy", "sensitivity", "specificity", "balanced_accuracy")
 RTOL = 1e-2
 
