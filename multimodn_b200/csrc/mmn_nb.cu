@@ -13,21 +13,22 @@ int round16(int v) { return (v + 15) & ~15; }
 struct Inst { int kss, ksh; };
 const Inst kInsts[] = {{1, 1}, {4, 2}, {4, 4}};
 
-void fill_layer(NbLayer& o, const DevLayer& l, int Spad, bool x_type, int& arena) {
+// One Linear layer of the plan.  in_pad / out_pad: padded widths (multiples of 16) of the chained input / of the output inside
+// the instantiation; spad: padded state width.
+void fill_layer(NbLayer& o, const DevLayer& l, int in_pad, int out_pad, int spad, bool x_type, int& arena) {
   o.N = l.out_dim;
-  o.n_tiles = (l.out_dim + 7) / 8;
-  o.n16 = round16(l.out_dim);
   o.ka = l.in_dim;
-  o.ka_pad = round16(l.in_dim);
+  o.ka_pad = in_pad;
+  o.n_pad = out_pad;
   o.has_state = l.has_state;
   o.x_type = x_type ? 1 : 0;
   o.act = l.act;
   o.ktot = l.ktot;
   o.w_off = l.w_off;
   o.b_off = l.b_off;
-  o.pitch = (o.ka_pad + (l.has_state ? Spad : 0)) * 2 + 16;
+  o.pitch = (o.ka_pad + (l.has_state ? spad : 0)) * 2 + 16;      // odd multiple of 16 bytes: conflict-free ldmatrix
   o.img_off = arena;
-  arena += o.n16 * o.pitch;
+  arena += o.n_pad * o.pitch;
 }
 
 template <int KSS, int KSH>
@@ -60,70 +61,80 @@ bool mmn_nb_build(const DevPlan& P, int max_smem, NbPlan& N, const char** why) {
                                   "weights + staging exceed the shared memory of one SM"};
   memset(&N, 0, sizeof N);
   if (P.S > kMaxW) { *why = reasons[0]; return false; }
-  N.S = P.S; N.Spad = round16(P.S); N.E = P.E; N.D = P.D; N.sumC = P.sumC; N.n_metrics = P.n_metrics;
+  N.S = P.S; N.E = P.E; N.D = P.D; N.sumC = P.sumC; N.n_metrics = P.n_metrics;
   N.init_param_off = P.init_off; N.n_params = P.n_params;
-  int arena = 0, max_hidden = 0, max_out = 16;
+  // the instantiation: k16-steps of the state and of the widest hidden layer.  The x-fed first layer keeps 16 KSH output
+  // columns in registers, so a 1-layer encoder (whose output is the state itself) needs KSH >= the state's k-steps.
+  int max_hidden = 16;
+  bool one_layer_encoder = false;
   for (int e = 0; e < P.E; ++e) {
     const DevEncoder& s = P.enc[e];
     if (s.n_layers > kMaxL) { *why = reasons[1]; return false; }
+    one_layer_encoder |= s.n_layers == 1;
+    for (int j = 0; j + 1 < s.n_layers; ++j) {
+      if (s.L[j].out_dim > kMaxW) { *why = reasons[2]; return false; }
+      max_hidden = std::max(max_hidden, round16(s.L[j].out_dim));
+    }
+  }
+  for (int d = 0; d < P.D; ++d) {
+    const DevDecoder& s = P.dec[d];
+    if (s.n_layers > kMaxL) { *why = reasons[1]; return false; }
+    if (s.C > kMaxC) { *why = reasons[3]; return false; }
+    for (int j = 0; j + 1 < s.n_layers; ++j) {
+      if (s.L[j].out_dim > kMaxW) { *why = reasons[2]; return false; }
+      max_hidden = std::max(max_hidden, round16(s.L[j].out_dim));
+    }
+  }
+  const int need_kss = round16(P.S) / 16, need_ksh = std::max(max_hidden / 16, one_layer_encoder ? need_kss : 0);
+  const Inst* inst = nullptr;
+  for (const Inst& c : kInsts)
+    if (need_kss <= c.kss && need_ksh <= c.ksh) { inst = &c; break; }
+  if (!inst) { *why = reasons[2]; return false; }
+  N.kss = inst->kss;
+  N.ksh = inst->ksh;
+  const int spad = 16 * inst->kss, hpad = 16 * inst->ksh;
+
+  int arena = 0, xs = 0;
+  for (int e = 0; e < P.E; ++e) {
+    const DevEncoder& s = P.enc[e];
     NbEnc& d = N.enc[e];
     d.F = s.F; d.n_layers = s.n_layers; d.p_drop = s.p_drop;
     for (int j = 0; j < s.n_layers; ++j) {
-      if (j < s.n_layers - 1) {
-        if (s.L[j].out_dim > kMaxW) { *why = reasons[2]; return false; }
-        max_hidden = std::max(max_hidden, round16(s.L[j].out_dim));
-      }
-      fill_layer(d.L[j], s.L[j], N.Spad, j == 0, arena);
-      max_out = std::max(max_out, d.L[j].n16);
+      const bool last = j == s.n_layers - 1;
+      const int in_pad = j == 0 ? round16(s.F) : hpad;
+      // a 1-layer encoder's image serves the forward (16 KSH output tiles) and the carry (contraction over 16 KSS rows)
+      const int out_pad = !last ? hpad : (j == 0 ? std::max(spad, hpad) : spad);
+      fill_layer(d.L[j], s.L[j], in_pad, out_pad, spad, j == 0, arena);
     }
+    d.xs_off = xs;
+    xs += round16(s.F) / 16;
   }
+  N.xs_steps = xs;
   for (int dd = 0; dd < P.D; ++dd) {
     const DevDecoder& s = P.dec[dd];
-    if (s.n_layers > kMaxL) { *why = reasons[1]; return false; }
-    if (s.C > kMaxC) { *why = reasons[3]; return false; }
     NbDec& d = N.dec[dd];
     d.C = s.C; d.n_layers = s.n_layers; d.out_off = s.out_off;
     for (int j = 0; j < s.n_layers; ++j) {
-      if (j < s.n_layers - 1) {
-        if (s.L[j].out_dim > kMaxW) { *why = reasons[2]; return false; }
-        max_hidden = std::max(max_hidden, round16(s.L[j].out_dim));
-      }
-      fill_layer(d.L[j], s.L[j], N.Spad, false, arena);
-      max_out = std::max(max_out, d.L[j].n16);
+      const bool last = j == s.n_layers - 1;
+      fill_layer(d.L[j], s.L[j], j == 0 ? spad : hpad, last ? 16 : hpad, spad, false, arena);
     }
   }
-  // biases (fp32, 8 per n-tile) and the initial state behind the images
+  // biases (fp32, one per image row) and the initial state behind the images
   arena = (arena + 15) & ~15;
   for (int e = 0; e < P.E; ++e)
-    for (int j = 0; j < N.enc[e].n_layers; ++j) { N.enc[e].L[j].bias_off = arena; arena += 32 * N.enc[e].L[j].n_tiles; }
+    for (int j = 0; j < N.enc[e].n_layers; ++j) { N.enc[e].L[j].bias_off = arena; arena += 4 * N.enc[e].L[j].n_pad; }
   for (int dd = 0; dd < P.D; ++dd)
-    for (int j = 0; j < N.dec[dd].n_layers; ++j) { N.dec[dd].L[j].bias_off = arena; arena += 32 * N.dec[dd].L[j].n_tiles; }
+    for (int j = 0; j < N.dec[dd].n_layers; ++j) { N.dec[dd].L[j].bias_off = arena; arena += 4 * N.dec[dd].L[j].n_pad; }
   N.init_off = arena;
-  arena += 4 * N.Spad;
+  arena += 4 * spad;
   N.arena_bytes = (arena + 15) & ~15;
-  // kernel instantiation and the stash / staging geometry that depends on it
-  bool one_layer_encoder = false;
-  int xs = 0;
-  for (int e = 0; e < P.E; ++e) {
-    one_layer_encoder |= N.enc[e].n_layers == 1;
-    N.enc[e].xs_off = xs;
-    xs += N.enc[e].L[0].ka_pad / 16;
-  }
-  N.xs_steps = xs;
-  // the x-fed layer keeps 16 KSH output columns in registers: a 1-layer encoder's output is the state itself
-  const int kss = N.Spad / 16, ksh = std::max(std::max(1, max_hidden / 16), one_layer_encoder ? N.Spad / 16 : 0);
-  const Inst* inst = nullptr;
-  for (const Inst& c : kInsts)
-    if (kss <= c.kss && ksh <= c.ksh) { inst = &c; break; }
-  if (!inst) { *why = reasons[2]; return false; }
-  N.kss = kss;
-  N.ksh = ksh;
-  N.stash_step_regs = 4 * MI * (inst->kss + 2 * inst->ksh);     // Frag<KS>: MI x KS x 4 registers
+  // register stash per step: the state (4 KSS registers) and up to two hidden outputs (4 KSH each)
+  N.stash_step_regs = 4 * (inst->kss + 2 * inst->ksh);
   for (int e = 0; e < P.E; ++e)
-    for (int j = 0; j < kMaxL; ++j) N.enc[e].stash_off[j] = 4 * MI * (inst->kss + inst->ksh * std::min(j, 1));
-  const int max_a = std::max(N.Spad, std::max(16, max_hidden)), max_dz = std::max(N.Spad, max_out);
-  N.stage_dz_off = max_a * 2;
-  N.stage_pitch = (max_a + max_dz) * 2 + 16;
+    for (int j = 0; j < kMaxL; ++j) N.enc[e].stash_off[j] = 4 * (inst->kss + inst->ksh * std::min(j, 1));
+  const int max_w = std::max(spad, hpad);
+  N.stage_dz_off = max_w * 2;
+  N.stage_pitch = 2 * max_w * 2 + 16;
   if (nb_smem_bytes(N) > (size_t)max_smem) { *why = reasons[4]; return false; }
   return true;
 }
@@ -166,7 +177,7 @@ int64_t mmn_nb_workspace_bytes(const mmn_plan* plan, int64_t n_rows, bool train)
   const NbPlan& N = *static_cast<const NbPlan*>(plan->nb_host);
   const int64_t grid = nb_grid(plan, n_rows);
   const int64_t reg_stash = grid * (kNbGroups * kWarpsPerGroup) * (int64_t)N.E * N.stash_step_regs * 32 * 4;
-  const int64_t x_stash = grid * kNbGroups * (int64_t)N.xs_steps * kWarpsPerGroup * MI * 32 * 16;
+  const int64_t x_stash = grid * kNbGroups * (int64_t)N.xs_steps * kWarpsPerGroup * 32 * 16;
   return ((reg_stash + 255) & ~(int64_t)255) + x_stash;
 }
 
@@ -189,7 +200,7 @@ int mmn_nb_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_byt
   {
     const int64_t reg_stash = (int64_t)grid * (kNbGroups * kWarpsPerGroup) * (int64_t)N.E * N.stash_step_regs * 32 * 4;
     args.xstash = reinterpret_cast<float4*>(static_cast<char*>(ws) + ((reg_stash + 255) & ~(int64_t)255));
-    args.xstash_vec_per_group = (long long)N.xs_steps * kWarpsPerGroup * MI * 32;
+    args.xstash_vec_per_group = (long long)N.xs_steps * kWarpsPerGroup * 32;
   }
   const size_t smem = nb_smem_bytes(N);
   const Inst& c = inst_of(N);
