@@ -187,7 +187,7 @@ int mmn_nb_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_byt
   int n_layers = 0;
   for (int e = 0; e < N.E; ++e) n_layers += N.enc[e].n_layers;
   for (int d = 0; d < N.D; ++d) n_layers += N.dec[d].n_layers;
-  MMN_LAUNCH(mmn_nb_prep_kernel<0>, dim3(n_layers + 1), dim3(256), 0, stream, static_cast<const NbPlan*>(plan->nb_dev), a.params,
+  MMN_LAUNCH(mmn_nb_prep_kernel<0>, dim3(std::min(plan->n_sms, 64)), dim3(256), 0, stream, static_cast<const NbPlan*>(plan->nb_dev), a.params,
              static_cast<unsigned char*>(plan->nb_arena));
   MMN_CUDA(cudaGetLastError());
   NbArgs args;

@@ -137,16 +137,15 @@ template <int = 0>
 __global__ void __launch_bounds__(256) mmn_nb_prep_kernel(const NbPlan* plan, const float* __restrict__ params,
                                                          unsigned char* __restrict__ arena) {
   const NbPlan& P = *plan;
-  // one block per layer; the last block writes the initial state
-  int b = blockIdx.x;
+  // every block takes a grid-stride slice of every layer's image (the 1088-column first layer of an image encoder is
+  // most of the work: one block per layer would serialise it)
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
   for (int e = 0; e < P.E; ++e)
-    for (int j = 0; j < P.enc[e].n_layers; ++j, --b)
-      if (b == 0) { nb_image_layer(P.enc[e].L[j], 16 * P.kss, P.S, params, arena, threadIdx.x, blockDim.x); return; }
+    for (int j = 0; j < P.enc[e].n_layers; ++j) nb_image_layer(P.enc[e].L[j], 16 * P.kss, P.S, params, arena, tid, nthreads);
   for (int d = 0; d < P.D; ++d)
-    for (int j = 0; j < P.dec[d].n_layers; ++j, --b)
-      if (b == 0) { nb_image_layer(P.dec[d].L[j], 16 * P.kss, P.S, params, arena, threadIdx.x, blockDim.x); return; }
+    for (int j = 0; j < P.dec[d].n_layers; ++j) nb_image_layer(P.dec[d].L[j], 16 * P.kss, P.S, params, arena, tid, nthreads);
   float* init = reinterpret_cast<float*>(arena + P.init_off);
-  for (int c = threadIdx.x; c < 16 * P.kss; c += blockDim.x) init[c] = c < P.S ? __ldg(params + P.init_param_off + c) : 0.f;
+  for (int c = tid; c < 16 * P.kss; c += nthreads) init[c] = c < P.S ? __ldg(params + P.init_param_off + c) : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -449,15 +448,25 @@ __device__ __forceinline__ void wgrad_x(const unsigned char* buf, int pitch, int
   const int q = L.lane >> 3, lr = L.lane & 7;
   const unsigned a_lane = sbuf + (unsigned)((8 * (q >> 1) + lr) * pitch + dz_off + 16 * (q & 1));
   const int n_blk = (F + 15) >> 4;
+  // forward warp w holds rows 16 w + g (registers x, z) and 16 w + g + 8 (registers y, w) of a 16-column block; the 8 loads
+  // of the warp's NEXT block are in flight while the current one is multiplied
+  float4 v[kWarpsPerGroup], vn[kWarpsPerGroup];
+  if (L.wg < n_blk) {
+#pragma unroll
+    for (int w = 0; w < kWarpsPerGroup; ++w) vn[w] = __ldcg(xs + ((long long)L.wg * kWarpsPerGroup + w) * 32 + L.lane);
+  }
   for (int blk = L.wg; blk < n_blk; blk += kWarpsPerGroup) {
     const int c = 16 * blk + 4 * L.t;
     float acc[MTX][2][4];
 #pragma unroll
     for (int m = 0; m < MTX; ++m) acc_zero<2>(acc[m]);
-    // forward warp w holds rows 16 w + g (registers x, z) and 16 w + g + 8 (registers y, w) of this 16-column block
-    float4 v[kWarpsPerGroup];
 #pragma unroll
-    for (int w = 0; w < kWarpsPerGroup; ++w) v[w] = __ldcg(xs + ((long long)blk * kWarpsPerGroup + w) * 32 + L.lane);
+    for (int w = 0; w < kWarpsPerGroup; ++w) v[w] = vn[w];
+    if (blk + kWarpsPerGroup < n_blk) {
+#pragma unroll
+      for (int w = 0; w < kWarpsPerGroup; ++w)
+        vn[w] = __ldcg(xs + ((long long)(blk + kWarpsPerGroup) * kWarpsPerGroup + w) * 32 + L.lane);
+    }
 #pragma unroll
     for (int w = 0; w < kWarpsPerGroup; ++w) {
       // k16-step = the 16 rows of forward warp w: b0 from rows g (.x = cols 4t, 4t+1 -> tile 0; .z = cols 4t+2, +3 -> tile 1),
@@ -1074,9 +1083,10 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
           group_bar(L.gi, kGroupThreads);
           stage_put<KSS>(stage, stage_pitch, dz_off, dzS, L);
           group_bar(L.gi, kGroupThreads);
-          wgrad_x<KSH>(stage, stage_pitch, dz_off, ly.N, xs, enc.F, grads + ly.w_off, ly.ktot, L);
           if (ly.has_state) state_job(dzS, ly, true, enc.F);
           else wgrad_items(stage, stage_pitch, dz_off, ly.N, 0, grads + ly.w_off, ly.ktot, 0, grads + ly.b_off, L);
+          sA = sP;
+          wgrad_x<KSH>(stage, stage_pitch, dz_off, ly.N, xs, enc.F, grads + ly.w_off, ly.ktot, L);
         } else {
           // last layer: input = the stashed output of layer nl - 2 (+ the state for MLPEncoder)
           Frag<KSH> hin, dzH;
@@ -1122,11 +1132,13 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
           group_bar(L.gi, kGroupThreads);
           stage_put<KSH>(stage, stage_pitch, dz_off, dzH, L);
           group_bar(L.gi, kGroupThreads);
-          wgrad_x<KSH>(stage, stage_pitch, dz_off, ly.N, xs, enc.F, grads + ly.w_off, ly.ktot, L);
+          // (the state job first: it finalises G and ends the live ranges of s_k and dz, which leaves the x columns the
+          //  registers to keep the next block's loads in flight)
           if (ly.has_state) state_job(dzH, ly, true, enc.F);
           else wgrad_items(stage, stage_pitch, dz_off, ly.N, 0, grads + ly.w_off, ly.ktot, 0, grads + ly.b_off, L);
+          sA = sP;                                           // the state the next (earlier) step's decoders and u_{k-1} see
+          wgrad_x<KSH>(stage, stage_pitch, dz_off, ly.N, xs, enc.F, grads + ly.w_off, ly.ktot, L);
         }
-        sA = sP;                                             // the state the next (earlier) step's decoders and u_{k-1} see
       }
       // ---- gradient of the initial state: column sums of G over the valid rows (tile backward of state.py:30) ----
 #pragma unroll
