@@ -485,8 +485,8 @@ class Bench:
         g = torch.Generator().manual_seed(4)
         perms = [[(i + s) % E for i in range(E)] for s in range(n_perm // 2)]
         perms += [torch.randperm(E, generator=g).tolist() for _ in range(n_perm - len(perms))]
-        model.predict(xs, np.array(perms[0]))                       # warm-up (plan, workspace)
-        model.predict(xs, np.array(perms[1]))
+        for p in perms[:2]:                                         # warm-up (plan, workspace)
+            model.predict([xs[e] for e in p], np.array(p))
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for p in perms:
@@ -632,6 +632,7 @@ def main():
                 c2 = WORKLOADS["c2_mimic"]
                 configs["c2_mimic"] = bench.train(c2, c2["batch"], K, W, e2e=False)
                 configs["c2_mimic"]["dp_parity"] = bench.dp_parity(c2, rows_per_rank=4096)
+                configs["c2_mimic_bf16"] = bench.train(c2, c2["batch"], K, W, precision="bf16", e2e=False)
             except Exception as exc:  # noqa: BLE001
                 configs["c2_mimic"] = dict(error=f"{type(exc).__name__}: {exc}")
     elif not args.no_configs:
@@ -650,6 +651,8 @@ def main():
                                                     e2e_steps=6))
         c2 = WORKLOADS["c2_mimic"]
         guarded("c2_mimic_bf16", lambda: bench.train(c2, c2["batch"], Ks, 3, precision="bf16", e2e=True, e2e_steps=6))
+        c1 = WORKLOADS["c1_titanic"]
+        guarded("c1_titanic_bf16", lambda: bench.train(c1, c1["batch"], Ks, 3, precision="bf16", e2e=False))
         guarded("c5_sweep", lambda: bench.predict_sweep(WORKLOADS["c3_mnar"], 1 << 20))
 
     cpu = None

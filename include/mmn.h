@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MMN_ABI_VERSION 2   /* 2: mmn_model_desc.precision, bf16 plans, gradient-ready events */
+#define MMN_ABI_VERSION 3   /* 2: mmn_model_desc.precision, bf16 plans, gradient-ready events; 3: mmn_outputs.target_error */
 #define MMN_MAX_LAYERS 6      /* Linear layers per encoder / decoder */
 #define MMN_MAX_ENCODERS 16
 #define MMN_MAX_DECODERS 16
@@ -125,6 +125,9 @@ typedef struct mmn_outputs {
   float* last_outputs;   /* (n_rows, sum_d C_d): decoder outputs at the step of encoder id E-1
                             (multimodn.py:354-357) */
   float* final_state;    /* (n_rows, S) (multimodn.py:488-492) */
+  int32_t* target_error; /* device int32[1] or NULL: set to 1 when a target lies outside [0, n_classes) of its decoder —
+                            nn.CrossEntropyLoss raises there (multimodn.py:146); the kernels clamp the index for memory
+                            safety and report, the caller raises */
 } mmn_outputs;
 
 typedef struct mmn_train_args {

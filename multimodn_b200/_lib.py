@@ -14,7 +14,7 @@ MAX_ENCODERS = 16
 MAX_DECODERS = 16
 MAX_CLASSES = 32
 ACT_CODES = {"identity": 0, "relu": 1, "sigmoid": 2, "tanh": 3}
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libmmn.so")
 
@@ -49,7 +49,7 @@ class Batch(C.Structure):
 
 class Outputs(C.Structure):
     _fields_ = [("metrics", C.c_void_p), ("predictions", C.c_void_p), ("pred_ld", C.c_int64),
-                ("last_outputs", C.c_void_p), ("final_state", C.c_void_p)]
+                ("last_outputs", C.c_void_p), ("final_state", C.c_void_p), ("target_error", C.c_void_p)]
 
 
 class TrainArgs(C.Structure):

@@ -288,6 +288,7 @@ int fill_args(const mmn_plan* plan, const mmn_batch* b, const float* params, con
     a.pred_ld = out->pred_ld;
     a.last_outputs = out->last_outputs;
     a.final_state = out->final_state;
+    a.target_error = out->target_error;
     if (out->predictions && out->pred_ld < b->n_rows) return fail("pred_ld < n_rows");
   }
   return 0;

@@ -91,6 +91,7 @@ struct StepArgs {
   long long pred_ld;
   float* last_outputs;
   float* final_state;
+  int* target_error;           // device flag: a target outside [0, C) was seen (the index is clamped for memory safety)
   float c_err;   // err_penalty / (D (E+1) B_global)
   float c_sc;    // 2 * state_change_penalty_scaled / (E B_global S)
   unsigned dropout_seed;

@@ -727,6 +727,7 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, ENG::kMinBlocks) mmn_step_
         const int r = idx / D;
         long long y = 0;
         if (r < rows_valid) y = args.targets[(row0 + r) * D + (idx - r * D)];
+        if ((y < 0 || y >= P.dec[idx - r * D].C) && args.target_error) *args.target_error = 1;   // CrossEntropyLoss would raise
         sm.ys[idx] = (int)y;
       }
     }

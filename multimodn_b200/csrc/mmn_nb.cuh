@@ -365,13 +365,14 @@ __device__ __forceinline__ void drop_state(Frag<KSS>& o, const Frag<KSS>& s, con
 // ------------------------------------------------------------------------------------------------
 // weight-gradient job: gW[n][col_base + k] += sum over the group's 128 rows dz[r][n] a[r][k]   (n < N, k < K),
 // gb[n] += sum_r dz[r][n].  a and dz are in the group's staging buffer (row-major bf16); work items (k-tile pair, m-tile)
-// are dealt round-robin to the 8 warps; the bias column rides along as one more item per m-tile (B = ones).
+// are dealt round-robin to the 8 warps; the bias column rides along with the first k-tile pair as one more MMA per k-step
+// against a synthesised ones-column.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void wgrad_items(const unsigned char* buf, int pitch, int dz_off, int N, int K, float* __restrict__ gW,
                                             int ld, int col_base, float* __restrict__ gb, const Lane& L) {
   const unsigned sbuf = smem_addr(buf);
   const int MT = (N + 15) >> 4, KP = (K + 15) >> 4;
-  const int n_items = MT * KP + (gb ? MT : 0);
+  const int n_items = MT * (KP > 0 ? KP : 1);               // K == 0: a bias-only job
   const bool v2 = ((ld & 1) == 0) && ((col_base & 1) == 0);
   // ldmatrix.trans lane offsets: A (dz^T): matrix q: rows r0 + 8 (q >> 1) + (lane & 7), cols n0 + 8 (q & 1)
   //                              B (a):    matrix q: rows r0 + 8 (q & 1) + (lane & 7), cols c0 + 8 (q >> 1)
@@ -380,21 +381,13 @@ __device__ __forceinline__ void wgrad_items(const unsigned char* buf, int pitch,
   const unsigned b_lane = sbuf + (unsigned)((8 * (q & 1) + lr) * pitch + 16 * (q >> 1));
   const unsigned ones = L.g == 0 ? 0x3F803F80u : 0u;        // B = [1 0 0 ...]: column 0 of the extra tile sums the rows
   for (int item = L.wg; item < n_items; item += kWarpsPerGroup) {
-    const bool is_bias = item >= MT * KP;
-    int m, p;
-    if (is_bias) { m = item - MT * KP; p = 0; }
-    else { p = item / MT; m = item - p * MT; }
-    float acc[2][4];
+    const int p = item / MT, m = item - p * MT;
+    const bool with_bias = gb != nullptr && p == 0;         // the item of the first k-tile pair also sums dz over the rows
+    float acc[2][4], accb[4];
     acc_zero<2>(acc);
+    accb[0] = accb[1] = accb[2] = accb[3] = 0.f;
     const unsigned a_at = a_lane + 32 * m, b_at = b_lane + 32 * p;
-    if (is_bias) {
-#pragma unroll
-      for (int ks = 0; ks < kTileRows / 16; ++ks) {
-        unsigned a[4];
-        ldsm_x4_t(a, a_at + (unsigned)(16 * ks * pitch));
-        mma_bf16(acc[0], a, ones, ones);
-      }
-    } else {
+    if (KP > 0) {
 #pragma unroll
       for (int ks = 0; ks < kTileRows / 16; ++ks) {
         unsigned a[4], b[4];
@@ -403,15 +396,22 @@ __device__ __forceinline__ void wgrad_items(const unsigned char* buf, int pitch,
         ldsm_x4_t(b, b_at + (unsigned)(16 * ks * pitch));
         mma_bf16(acc[0], a, b[0], b[1]);
         mma_bf16(acc[1], a, b[2], b[3]);
+        if (with_bias) mma_bf16(accb, a, ones, ones);
+      }
+    } else {
+#pragma unroll
+      for (int ks = 0; ks < kTileRows / 16; ++ks) {
+        unsigned a[4];
+        ldsm_x4_t(a, a_at + (unsigned)(16 * ks * pitch));
+        mma_bf16(accb, a, ones, ones);
       }
     }
     const int n0 = 16 * m + L.g;
-    if (is_bias) {
-      if (L.t == 0) {
-        if (n0 < N) red_add(gb + n0, acc[0][0]);
-        if (n0 + 8 < N) red_add(gb + n0 + 8, acc[0][2]);
-      }
-    } else {
+    if (with_bias && L.t == 0) {
+      if (n0 < N) red_add(gb + n0, accb[0]);
+      if (n0 + 8 < N) red_add(gb + n0 + 8, accb[2]);
+    }
+    if (KP > 0) {
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int k = 16 * p + 8 * j + 2 * L.t;
@@ -665,7 +665,8 @@ __global__ void __launch_bounds__(kThreadsNb, 1) mmn_nb_step_kernel(const NbArgs
         long long y = 0;
         if (row0 + r < A.n_rows) y = A.targets[(row0 + r) * D + d];
         const int C = P.dec[d].C;
-        y = y < 0 ? 0 : (y >= C ? C - 1 : y);                   // memory safety only: the host validates targets and raises
+        if ((y < 0 || y >= C) && A.target_error) *A.target_error = 1;   // CrossEntropyLoss would raise: reported, the caller raises
+        y = y < 0 ? 0 : (y >= C ? C - 1 : y);                   // memory safety
         ys[r * MMN_MAX_DECODERS + d] = (unsigned char)y;
       }
     }

@@ -296,6 +296,7 @@ __global__ void __launch_bounds__(V2Engine::kBlockThreads, 1) mmn_step_kernel_v2
         const int rr = idx / D;
         long long y = 0;
         if (rr < rows_valid) y = args.targets[(row0 + rr) * D + (idx - rr * D)];
+        if ((y < 0 || y >= P.dec[idx - rr * D].C) && args.target_error) *args.target_error = 1;
         sm.ys[idx] = (int)y;
       }
     }

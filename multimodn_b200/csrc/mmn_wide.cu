@@ -388,7 +388,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
       LossArgs la;
       memset(&la, 0, sizeof la);
       la.p = Pout; la.ldp = dec.C; la.C = dec.C; la.act = dec.L[dec.n_layers - 1].act; la.D = D; la.d = d;
-      la.hist_row = hist_row; la.n_mat_rows = E + 1; la.rows = B; la.targets = a.targets;
+      la.hist_row = hist_row; la.n_mat_rows = E + 1; la.rows = B; la.targets = a.targets; la.target_error = a.target_error;
       la.present = k == 0 ? nullptr : present + (size_t)k * B;
       la.skip = skip;
       la.metrics = a.metrics; la.inv_rows_global = a.inv_rows_global;

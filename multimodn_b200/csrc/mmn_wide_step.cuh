@@ -334,6 +334,7 @@ struct LossArgs {
   int C, act, D, d, hist_row, n_mat_rows; // n_mat_rows = E + 1
   long long rows;
   const long long* targets;               // [rows x D] or null
+  int* target_error;                      // device flag: a target outside [0, C) was seen
   const unsigned char* present;           // [rows] or null (initial state: every row counts)
   const int* skip;
   double* metrics; double inv_rows_global;
@@ -366,6 +367,7 @@ __global__ void wide_decoder_loss_kernel(const LossArgs a) {
       for (int c = 0; c < a.C; ++c) a.last_outputs[r * a.ld_last + a.out_off + c] = p[c];
     if (a.targets) {
       y = (int)a.targets[r * a.D + a.d];
+      if ((y < 0 || y >= a.C) && a.target_error) *a.target_error = 1;
       y = y < 0 ? 0 : (y >= a.C ? a.C - 1 : y);
       float se = 0.f;
       for (int c = 0; c < a.C; ++c) se += expf(p[c] - mx);

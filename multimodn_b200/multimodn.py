@@ -87,10 +87,9 @@ class _Runtime:
         self.layerwise = int(self.lib.dll.mmn_plan_engine(self.plan)) == 3      # bf16 plans: many launches per step
         self.grad_events = None
         self.comm_stream = None
-        # CrossEntropyLoss raises on a target outside [0, C) (and ignores -100): the kernels index with the target, so it is
-        # validated on the device every batch (no host sync) and the verdict is read where the epoch's metrics are read
-        self._n_classes = torch.tensor([m.n_classes for m in self.packed.decoders], dtype=torch.int64, device=self.device)
-        self._target_err = torch.zeros((), dtype=torch.int64, device=self.device)
+        # CrossEntropyLoss raises on a target outside [0, C) (and ignores -100): the kernels clamp the index for memory
+        # safety and set mmn_outputs.target_error; the verdict is read where the epoch's metrics are read (no sync per batch)
+        self._target_err = torch.zeros(1, dtype=torch.int32, device=self.device)      # written by the kernels
         self._dp_err = torch.zeros((), dtype=torch.int64, device=self.device)
 
     def __del__(self):
@@ -204,8 +203,6 @@ class _Runtime:
             if tgt.dim() != 2 or tgt.shape[1] != self.D or tgt.shape[0] != n_rows:
                 raise ValueError(f"target must be ({n_rows}, {self.D}), got {tuple(tgt.shape)}")
             tgt = tgt.contiguous()
-            bad = ((tgt < 0) | (tgt >= self._n_classes)).any().to(torch.int64)
-            self._target_err = torch.maximum(self._target_err, bad)
         npos = max(len(xs), 1)
         seq_pos = (C.c_int32 * max(len(seq), 1))(*[p for p, _ in seq])
         seq_enc = (C.c_int32 * max(len(seq), 1))(*enc_ids)
@@ -241,6 +238,7 @@ class _Runtime:
         o.pred_ld = predictions.shape[-1] if predictions is not None else 0
         o.last_outputs = last_outputs.data_ptr() if last_outputs is not None else None
         o.final_state = final_state.data_ptr() if final_state is not None else None
+        o.target_error = self._target_err.data_ptr()
         return o
 
     def forward(self, batch, n_rows, **outs):
