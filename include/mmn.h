@@ -147,15 +147,16 @@ int mmn_abi_version(void);
 int mmn_plan_create(const mmn_model_desc* desc, mmn_plan** out);
 void mmn_plan_destroy(mmn_plan* plan);
 
-/* Which kernel family a plan uses (results agree to fp32 round-off):
- *   MMN_ENGINE_FMA  FP32-FMA register-tile GEMMs — default of mmn_train_step
- *   MMN_ENGINE_TC   tcgen05 3xTF32, operands staged through shared memory (MMN_ENGINE=tc)
- *   MMN_ENGINE_TC2  tcgen05 3xTF32 with the activations (forward) and the state / layer gradients (backward)
- *                   resident in tensor memory; needs state <= 64, layers <= 64 wide, <= 16 classes.  Default of
- *                   mmn_forward when the model qualifies; mmn_train_step uses it under MMN_ENGINE=tc2
- * The environment variable MMN_ENGINE=fma|tc|tc2, read by mmn_plan_create, forces one. */
-enum { MMN_ENGINE_FMA = 0, MMN_ENGINE_TC = 1, MMN_ENGINE_TC2 = 2, MMN_ENGINE_WIDE = 3 /* precision = bf16, layer-wise */,
-       MMN_ENGINE_NB = 4 /* precision = bf16, fused per-tile mma.sync kernel for narrow models; MMN_ENGINE=wide opts out */ };
+/* Which kernel family a plan uses:
+ *   MMN_ENGINE_FMA   fp32 plans, mmn_train_step (and mmn_forward when the model does not qualify for TC2): FP32-FMA
+ *                    register-tile GEMMs, one launch per step
+ *   MMN_ENGINE_TC2   fp32 plans, mmn_forward: tcgen05 3xTF32 with the activations resident in tensor memory; needs
+ *                    state <= 64, layers <= 64 wide, <= 16 classes (MMN_ENGINE=fma opts out)
+ *   MMN_ENGINE_NB    bf16 plans, narrow models (state <= 64, layers <= 64 wide, <= 3 Linear layers per module, <= 8 classes):
+ *                    fused per-tile mma.sync kernel, one launch per step, forward and train
+ *   MMN_ENGINE_WIDE  bf16 plans, everything else (and MMN_ENGINE=wide): every layer a tcgen05 GEMM over the whole batch
+ * (MMN_ENGINE_TC, round 1's shared-memory-staged tcgen05 step engine, no longer exists; the value is kept reserved.) */
+enum { MMN_ENGINE_FMA = 0, MMN_ENGINE_TC = 1 /* reserved */, MMN_ENGINE_TC2 = 2, MMN_ENGINE_WIDE = 3, MMN_ENGINE_NB = 4 };
 int32_t mmn_plan_engine(const mmn_plan* plan);           /* engine of mmn_train_step */
 
 /* Data-parallel overlap (the gradient all-reduce "issued per encoder block in reverse order to overlap with

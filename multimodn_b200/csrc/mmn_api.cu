@@ -23,7 +23,6 @@ int mmn_fail(const char* fmt, ...) {
 namespace {
 int round32(int v) { return (v + 31) & ~31; }
 size_t fma_smem(const DevPlan& P, int rm, int occ = 1) { return mmn_fma_smem(P, rm, occ); }
-size_t tc_smem(const DevPlan& P) { return mmn_tc_smem(P); }
 // largest FMA row tile (32*RM rows) whose shared-memory footprint fits
 int pick_rm(const mmn_plan* p) {
   for (int rm : {4, 2, 1})
@@ -170,25 +169,16 @@ extern "C" int mmn_plan_create(const mmn_model_desc* desc, mmn_plan** out) {
   const char* occ_env = getenv("MMN_FMA_OCC");        // "1" | "2" | unset = auto
   const bool occ2_fits = fma_smem(P, 2, 2) + 1024 <= (size_t)(233472 / 2);
   if (occ2_fits && !(occ_env && !strcmp(occ_env, "1"))) { p->rm = 2; p->occ = 2; }
-  const bool tc_fits = tc_smem(P) <= (size_t)p->max_smem;
-  const char* want = getenv("MMN_ENGINE");            // "tc" | "fma" | unset = auto
-  if (want && !strcmp(want, "tc") && !tc_fits) {
-    const size_t need = tc_smem(P);
-    const int limit = p->max_smem;
-    delete p;
-    return fail("MMN_ENGINE=tc: the tensor-core engine needs %zu B of shared memory for this model (limit %d)", need, limit);
-  }
-  // default: the FP32-FMA engine (faster at the current stage of tuning, profiles/r1_engine_timers.txt);
-  // MMN_ENGINE=tc opts into the tcgen05 3xTF32 engine
-  p->engine = (tc_fits && want && !strcmp(want, "tc")) ? MMN_ENGINE_TC : MMN_ENGINE_FMA;
-  // forward-only launches (test / predict / get_states): the TMEM-resident kernel where the model qualifies
+  // fp32 plans: the FP32-FMA kernel trains; forward-only launches (test / predict / get_states) use the TMEM-resident
+  // tcgen05 3xTF32 kernel where the model qualifies (MMN_ENGINE=fma keeps them on the FMA kernel)
+  const char* want = getenv("MMN_ENGINE");            // "fma" | "tc2" | unset = auto
+  p->engine = MMN_ENGINE_FMA;
   const bool v2_ok = mmn_v2_supports(P) && mmn_v2_smem(P) <= (size_t)p->max_smem;
   if (want && !strcmp(want, "tc2") && !v2_ok) {
     delete p;
     return fail("MMN_ENGINE=tc2: the TMEM-resident kernel needs state <= 64, layers <= 64 wide, <= 16 classes");
   }
-  p->fwd_engine = (v2_ok && !want) || (want && !strcmp(want, "tc2")) ? MMN_ENGINE_TC2 : p->engine;
-  if (want && !strcmp(want, "tc2")) p->engine = MMN_ENGINE_TC2;
+  p->fwd_engine = (v2_ok && !(want && !strcmp(want, "fma"))) ? MMN_ENGINE_TC2 : MMN_ENGINE_FMA;
   if (p->engine == MMN_ENGINE_FMA && p->rm == 0) {
     const size_t need = fma_smem(P, 1);
     delete p;
@@ -350,7 +340,6 @@ namespace {
 int launch_step_impl(const mmn_plan* plan, const StepArgs& a, void* stream, bool train) {
   const int engine = train ? plan->engine : plan->fwd_engine;
   if (engine == MMN_ENGINE_TC2) return mmn_launch_v2(plan, a, stream, train);
-  if (engine == MMN_ENGINE_TC) return mmn_launch_tc(plan, a, stream, train);
   return mmn_launch_fma(plan, a, stream, train);
 }
 }  // namespace

@@ -65,11 +65,9 @@ inline int grid_for(const mmn_plan* p, int engine, int64_t n_rows) {
 
 // per-family entry points (defined next to the kernels they launch)
 size_t mmn_fma_smem(const mmn::DevPlan& P, int rm, int occ);
-size_t mmn_tc_smem(const mmn::DevPlan& P);
 bool mmn_v2_supports(const mmn::DevPlan& P);
 size_t mmn_v2_smem(const mmn::DevPlan& P);
 int mmn_launch_fma(const mmn_plan* plan, const mmn::StepArgs& a, void* stream, bool train);
-int mmn_launch_tc(const mmn_plan* plan, const mmn::StepArgs& a, void* stream, bool train);
 int mmn_launch_v2(const mmn_plan* plan, const mmn::StepArgs& a, void* stream, bool train);
 int mmn_nb_plan_init(mmn_plan* p);
 void mmn_nb_plan_free(mmn_plan* p);

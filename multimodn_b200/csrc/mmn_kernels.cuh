@@ -706,10 +706,6 @@ __global__ void __launch_bounds__(ENG::kBlockThreads, ENG::kMinBlocks) mmn_step_
   for (int i = tid; i < E + 1; i += NT) sm.cnt[i] = 0;
   ENG::init(sm, es);
   const long long t_kernel = MMN_CLOCK();
-  if (ENG::kTensor && threadIdx.x >= NT) {      // 9th warp: issues the tensor-core MMAs
-    ENG::issuer_loop(sm, es, args.debug_timers ? args.debug_timers + 16 * (gridDim.x + blockIdx.x) : nullptr);
-    return;
-  }
 
   const long long n_tiles = (args.n_rows + TM - 1) / TM;
   float* slot = TRAIN ? args.stash + (long long)blockIdx.x * args.slot_floats : nullptr;

@@ -10,12 +10,18 @@ template <class ENG, bool TRAIN>
 int launch_engine(const mmn_plan* plan, const StepArgs& a_in, void* stream) {
   StepArgs a = a_in;
   const size_t smem = step_smem_bytes(plan->host, ENG::TM, ENG::stage_bytes());
-  const int grid = grid_for(plan, ENG::kTensor ? MMN_ENGINE_TC : MMN_ENGINE_FMA, a.n_rows);
+  const int grid = grid_for(plan, MMN_ENGINE_FMA, a.n_rows);
   auto kfn = mmn_step_kernel<ENG, TRAIN>;
-  MMN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static bool configured = false;          // per instantiation: the attributes are set once, not on every launch
+  if (!configured) {
+    MMN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->max_smem));
 #ifndef MMN_EMU
-  // two CTAs per SM need (almost) the whole 228 KB as shared memory: ask for the largest carve-out explicitly
-  MMN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    // two CTAs per SM need (almost) the whole 228 KB as shared memory: ask for the largest carve-out explicitly
+    MMN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+#endif
+    configured = true;
+  }
+#ifndef MMN_EMU
   if (getenv("MMN_DEBUG_OCC")) {
     int nb = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, ENG::kBlockThreads, smem);

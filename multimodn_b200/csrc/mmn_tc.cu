@@ -1,14 +1,8 @@
-// mmn_tc.cu — translation unit of the tcgen05 3xTF32 engine with shared-memory-staged operands (mmn_tc.cuh).
+// mmn_tc.cu — translation unit of the tcgen05 3xTF32 self-test (mmn_tc.cuh).
 #include "mmn_tc.cuh"
-#include "mmn_launch.cuh"
+#include "mmn_host.h"
 
 using namespace mmn;
-
-size_t mmn_tc_smem(const DevPlan& P) { return step_smem_bytes(P, TcEngine::TM, TcEngine::stage_bytes()); }
-
-int mmn_launch_tc(const mmn_plan* plan, const StepArgs& a, void* stream, bool train) {
-  return train ? launch_engine<TcEngine, true>(plan, a, stream) : launch_engine<TcEngine, false>(plan, a, stream);
-}
 
 // Diagnostic: one tcgen05 3xTF32 GEMM in each operand configuration of the tensor-core engine
 // (mmn_tc.cuh).  a, b, out: device pointers, see mmn_tc_selftest_kernel.

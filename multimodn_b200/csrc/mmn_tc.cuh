@@ -1,23 +1,13 @@
-// mmn_tc.cuh — tcgen05 (5th-gen tensor core) GEMM engine of the fused step, fp32-accurate via 3xTF32.
+// mmn_tc.cuh — tcgen05 (5th-gen tensor core) building blocks for fp32-accurate GEMMs via 3xTF32: PTX wrappers (mbarrier,
+// tcgen05.alloc / mma / ld / st / commit), UMMA shared-memory and instruction descriptors, the SWIZZLE_128B (K-major) and
+// SWIZZLE_128B_BASE32B (MN-major) image writers with the hi / lo split
+//         a*b ~= hi_a*hi_b + lo_a*hi_b + hi_a*lo_b          (error ~2^-21 relative),
+// and a one-tile self-test kernel for every operand configuration.  Users: the TMEM-resident forward kernel (mmn_tc2.cuh)
+// and, for the PTX wrappers, the wide regime (mmn_wide.cuh).
 //
-// Same three GEMM shapes as the FMA engine (mmn_kernels.cuh), same staging/epilogue structure, but the
-// multiply runs on the tensor cores with the accumulator in TMEM:
-//
-//   * every operand chunk is staged into shared memory in the UMMA canonical SWIZZLE_128B layout
-//     ([rows][32 fp32] = 128-byte rows, 8-row / 1024-byte atoms, 16-byte chunk index XOR (row & 7)),
-//     split into hi = tf32-representable part and lo = v - hi, so that
-//         a*b ~= hi_a*hi_b + lo_a*hi_b + hi_a*lo_b          (error ~2^-21 relative)
-//     and every tcgen05.mma.kind::tf32 consumes operands it represents exactly (hi) or to 2^-11 (lo);
-//   * ONE [rows x 32] image serves as a K-major operand (rows = M or N, contraction along the 32
-//     columns: forward activations, weights W[n][k]) or as an MN-major operand (contraction along
-//     the rows: weights for the data gradient, both operands of the weight gradient) — no transposes;
-//   * one elected thread issues the MMAs (M = 128 batch rows, N = 32/64, K = 8 per instruction) and
-//     commits them to an mbarrier; all 8 warps then read their 32-lane quarter of the accumulator
-//     with tcgen05.ld and run the epilogue (bias, activation, masks, gradient reds).
-//
-// Under -DMMN_EMU (tests/emu, CPU only) the tcgen05 / mbarrier instructions are replaced by a
-// functional model with the same descriptor arithmetic, so the control flow and the layout code are
-// exercised on the CPU; the real instruction semantics are validated by the -m gpu tests.
+// Under -DMMN_EMU (tests/emu, CPU only) the tcgen05 / mbarrier instructions are replaced by a functional model with the
+// same descriptor arithmetic, so the control flow and the layout code are exercised on the CPU; the real instruction
+// semantics are validated by the -m gpu tests (tests/test_gpu_tc_selftest.py checks the model against the hardware).
 #pragma once
 
 #include "mmn_kernels.cuh"
@@ -287,72 +277,16 @@ __device__ __forceinline__ void tc_store_elem(float* hi_img, float* lo_img, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Tensor-core engine: same three GEMM entry points as FmaEngine, 128-row tiles only.
-// Shared-memory staging (1024-byte aligned, first in the dynamic allocation):
-//   XB 64 KB = 2 buffers x {hi, lo} x [128 x 32] activation chunk images (16 KB each)
-//   WB 32 KB = 2 buffers x {hi, lo} x [64 x 32] weight block images (8 KB each)
-// The weight-gradient GEMM re-purposes them: XB = dz images {hi g0, hi g1, lo g0, lo g1}, WB = one
-// input-chunk image pair {hi, lo}.
+// Shared helpers of the tcgen05 3xTF32 kernels: the MMA issue sequence of one staged chunk and the staging of a weight
+// block as a (hi, lo) K-major image pair.  (Round 1 also had a complete step engine on shared-memory-staged operands here;
+// it lost to the FP32-FMA kernel on every configuration and was removed in round 2 — DESIGN.md section 4.)
 // ------------------------------------------------------------------------------------------------
 struct TcEngine {
-  static constexpr int RM = 4;
-  static constexpr int TM = 128;
-  static constexpr bool kTensor = true;
-  static constexpr int kWorkers = 256;                    // worker warps: kWorkers / 128 per TMEM lane quarter
+  static constexpr int kWorkers = 256;                    // worker threads of the TMEM-resident kernel (mmn_tc2.cuh)
   static constexpr int NW = kWorkers;
-  static constexpr int QA = 1024 / NW;                    // float4 per thread of a [128 x 32] chunk
   static constexpr int QW = 512 / NW;                     // float4 per thread of a weight block
-  static constexpr int CS = NW / 128;                     // column slices of the accumulator (one per warp of a quarter)
-  static constexpr int kBlockThreads = kWorkers + 32;     // + the MMA-issuing warp
-  static constexpr int kMinBlocks = 1;
   using State = TcState;
-  static size_t stage_bytes() { return 1024 + (size_t)(kTcStageXB + kTcStageWB + 512) * 4 + 64 + 2 * sizeof(TcCmd); }
 
-  // mbarriers: full[2] (one arrival per worker: chunk staged) then done[2] (1 arrival: tcgen05.commit)
-  __device__ static __forceinline__ unsigned long long* full_bar(const Smem& sm, int slot) { return sm.bar + slot; }
-  __device__ static __forceinline__ unsigned long long* done_bar(const Smem& sm, int slot) { return sm.bar + 2 + slot; }
-  __device__ static __forceinline__ TcCmd* cmd_slot(const Smem& sm, int slot) {
-    return reinterpret_cast<TcCmd*>(sm.bar + 4) + slot;
-  }
-
-  __device__ static __forceinline__ char* carve(Smem& sm, char* p) {
-    p += (1024 - (smem_u32(p) & 1023)) & 1023;
-    float* f = reinterpret_cast<float*>(p);
-    sm.XB = f; f += kTcStageXB;
-    sm.WB = f; f += kTcStageWB;
-    sm.RED = f; f += 512;
-    sm.bar = reinterpret_cast<unsigned long long*>(f);
-    char* q = reinterpret_cast<char*>(sm.bar + 4) + 2 * sizeof(TcCmd);
-    sm.tslot = reinterpret_cast<unsigned*>(q);
-    return q + 16;
-  }
-  __device__ static __forceinline__ void init(const Smem& sm, State& es) {      // every thread of the CTA
-    const int tid = threadIdx.x;
-    for (int i = tid; i < kTcStageXB + kTcStageWB; i += kBlockThreads) sm.XB[i] = 0.f;   // XB and WB are contiguous
-    if (tid == 0) {
-      mbar_init(full_bar(sm, 0), kWorkers); mbar_init(full_bar(sm, 1), kWorkers);
-      mbar_init(done_bar(sm, 0), 1); mbar_init(done_bar(sm, 1), 1);
-      mbar_fence_init();
-    }
-    if (tid < 32) tmem_alloc(sm.tslot, kTcTmemCols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    es.tmem = *sm.tslot;
-    es.seq = 0;
-    es.pending[0] = es.pending[1] = 0;
-    es.parity[0] = es.parity[1] = 0;
-    for (int i = 0; i < 16; ++i) es.t[i] = 0;
-  }
-  __device__ static __forceinline__ void fini(const Smem& sm, State& es) {      // workers only
-    drain(sm, es);
-    const int slot = es.seq & 1;
-    if (threadIdx.x == 0) cmd_slot(sm, slot)->op = TC_OP_QUIT;
-    mbar_arrive(full_bar(sm, slot));
-    tc_fence_before();
-    MMN_WSYNC_N(kWorkers);
-    if (threadIdx.x < 32) tmem_dealloc(es.tmem, kTcTmemCols);
-  }
   // one chunk: NJ k-slices x (lo*hi, hi*lo, hi*hi); every operand is a function of uniform values
   template <bool AMN, bool BMN, int NJ>
   __device__ static __forceinline__ void issue(unsigned a_hi, unsigned a_lo, unsigned a_grp, unsigned b_hi, unsigned b_lo,
@@ -371,68 +305,6 @@ struct TcEngine {
       }
     }
   }
-  // the extra warp: wait for a staged chunk, issue its MMAs, commit them to the slot's done barrier
-  __device__ static __forceinline__ void issuer_loop(const Smem& sm, State& es, long long* dbg = nullptr) {
-    const unsigned xb = smem_u32(sm.XB), wb = smem_u32(sm.WB);     // warp-uniform
-    const unsigned tmem0 = 0;                                      // the CTA's only TMEM allocation starts at column 0
-    if (es.tmem != 0) __trap();
-    const bool leader = elect_one() != 0;
-    unsigned par[2] = {0u, 0u};
-    long long t_idle = 0, t_issue = 0;
-    for (unsigned seq = 0;; ++seq) {
-      const unsigned slot = seq & 1u;
-      const long long t0 = MMN_CLOCK();
-      mbar_wait(full_bar(sm, slot), par[slot]);
-      par[slot] ^= 1u;
-      tc_fence_after();
-      const unsigned op = cmd_slot(sm, slot)->op;    // mbar_wait above is an acquire + compiler barrier
-      const unsigned kind = op & 3u, nj = (op >> 4) & 31u;
-      const bool n64 = (op >> 2) & 1u, first = (op >> 3) & 1u;
-      if (kind == TC_OP_QUIT) break;
-      const long long t1 = MMN_CLOCK();
-      const unsigned a_hi = xb + slot * 32768u, b_hi = wb + slot * 16384u;
-      if (kind == TC_OP_NT) {
-        if (n64) issue<false, false, 4>(a_hi, a_hi + 16384u, 0, b_hi, b_hi + 8192u, 0, umma_idesc_tf32(128, 64, 0, 0), tmem0, nj, first, leader);
-        else issue<false, false, 4>(a_hi, a_hi + 16384u, 0, b_hi, b_hi + 8192u, 0, umma_idesc_tf32(128, 32, 0, 0), tmem0, nj, first, leader);
-      } else if (kind == TC_OP_NN) {
-        if (n64) issue<false, true, 4>(a_hi, a_hi + 16384u, 0, b_hi, b_hi + 8192u, 4096, umma_idesc_tf32(128, 64, 0, 1), tmem0, nj, first, leader);
-        else issue<false, true, 4>(a_hi, a_hi + 16384u, 0, b_hi, b_hi + 8192u, 4096, umma_idesc_tf32(128, 32, 0, 1), tmem0, nj, first, leader);
-      } else {           // TN: A = dz images at XB, B = input chunk at WB (slot 0) or the upper half of XB (slot 1)
-        const unsigned in_hi = slot ? xb + 32768u : wb;
-        issue<true, true, 16>(xb, xb + 16384u, 0, in_hi, in_hi + 16384u, 0, umma_idesc_tf32(128, 32, 1, 1), tmem0 + 32u * slot, 16, true, leader);
-      }
-      if (leader) umma_commit(done_bar(sm, slot));
-      __syncwarp();
-      const long long t2 = MMN_CLOCK();
-      t_idle += t1 - t0;
-      t_issue += t2 - t1;
-    }
-    if (dbg && leader) { dbg[0] = t_idle; dbg[1] = t_issue; }
-  }
-  __device__ static __forceinline__ void wait(const Smem& sm, State& es, int slot) {
-    if (es.pending[slot]) {
-      const long long t0 = MMN_CLOCK();
-      mbar_wait(done_bar(sm, slot), es.parity[slot]);
-      es.t[0] += MMN_CLOCK() - t0;
-      es.parity[slot] ^= 1;
-      es.pending[slot] = 0;
-    }
-  }
-  __device__ static __forceinline__ void drain(const Smem& sm, State& es) {
-    wait(sm, es, es.seq & 1);          // older commit first (in-order completion)
-    wait(sm, es, (es.seq & 1) ^ 1);
-  }
-  // hand the chunk staged in `slot` to the issuer (the operand images sit at fixed places of the slot)
-  __device__ static __forceinline__ void post(const Smem& sm, State& es, int slot, unsigned kind, int N, int nj,
-                                              unsigned first) {
-    if (threadIdx.x == 0) cmd_slot(sm, slot)->op = kind | (N == 64 ? 4u : 0u) | (first ? 8u : 0u) | ((unsigned)nj << 4);
-    fence_proxy_async();               // this thread's image stores -> visible to the tensor-core (async) proxy
-    tc_fence_before();                 // this thread's earlier tcgen05.ld of the accumulator are ordered before
-    mbar_arrive(full_bar(sm, slot));
-    es.pending[slot] = 1;
-    es.seq += 1;
-  }
-
   // ---- weight block: [nrows <= 64][ncols <= 32] of row-major W -> K-major image pair (rows = n) ----
   __device__ static __forceinline__ void w_load_k(float (&w)[4 * QW], const float* __restrict__ W, int ldw, int row0, int nrows,
                                                   int col0, int ncols, bool vec) {
@@ -470,357 +342,8 @@ struct TcEngine {
       for (int i = 0; i < 4 * QW; ++i) tc_store_elem<false>(hi, lo, (t >> 5) + (NW / 32) * i, t & 31, w[i]);
     }
   }
-  // ---- weight block for the data gradient: rows n (contraction) x up to 64 output columns j ->
-  //      MN-major image pairs, one 4 KB image per group of 32 columns ----
-  __device__ static __forceinline__ void w_load_mn(float (&w)[4 * QW], const float* __restrict__ W, int ldw, int row0, int nrows,
-                                                   int col0, int ncols, bool vec) {
-    const int t = threadIdx.x;
-    if (vec) {
-      const int c4 = (t & 15) * 4;
-#pragma unroll
-      for (int i = 0; i < QW; ++i) {
-        const int r = (t >> 4) + (NW / 16) * i;
-        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < nrows && c4 < ncols) {
-          const float* p = W + (long long)(row0 + r) * ldw + col0 + c4;
-          if (c4 + 3 < ncols) q = __ldg(reinterpret_cast<const float4*>(p));
-          else { q.x = __ldg(p); if (c4 + 1 < ncols) q.y = __ldg(p + 1); if (c4 + 2 < ncols) q.z = __ldg(p + 2); }
-        }
-        w[4 * i] = q.x; w[4 * i + 1] = q.y; w[4 * i + 2] = q.z; w[4 * i + 3] = q.w;
-      }
-    } else {
-      const int c = t & 63;
-#pragma unroll
-      for (int i = 0; i < 4 * QW; ++i) {
-        const int r = (t >> 6) + (NW / 64) * i;
-        w[i] = (r < nrows && c < ncols) ? __ldg(W + (long long)(row0 + r) * ldw + col0 + c) : 0.f;
-      }
-    }
-  }
-  __device__ static __forceinline__ void w_store_mn(float* hi, float* lo, const float (&w)[4 * QW], bool vec) {
-    const int t = threadIdx.x;
-    if (vec) {
-      const int c4 = t & 15, g = c4 >> 3;
-#pragma unroll
-      for (int i = 0; i < QW; ++i)
-        tc_store_quad<true>(hi + g * 1024, lo + g * 1024, (t >> 4) + (NW / 16) * i, c4 & 7,
-                            make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]));
-    } else {
-      const int c = t & 63, g = c >> 5;
-#pragma unroll
-      for (int i = 0; i < 4 * QW; ++i) tc_store_elem<true>(hi + g * 1024, lo + g * 1024, (t >> 6) + (NW / 64) * i, c & 31, w[i]);
-    }
-  }
-
-  // ---- activation chunk [128 x 32]: global sources are fetched into 8 registers per thread early ...
-  __device__ static __forceinline__ void a_load(float (&v)[4 * QA], const ASeg& sg, int k0, int kw, int rows_valid, bool vec) {
-    if (sg.kind != SEG_X && sg.kind != SEG_STASH) return;
-    const int t = threadIdx.x;
-    if (vec) {
-      const int c4 = (t & 7) * 4;
-#pragma unroll
-      for (int i = 0; i < QA; ++i) {
-        const int r = (t >> 3) + (NW / 8) * i;
-        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < rows_valid && c4 < kw) {
-          const float4* p = reinterpret_cast<const float4*>(sg.ptr + (long long)r * sg.ld + k0 + c4);
-          q = sg.kind == SEG_X ? __ldg(p) : __ldcg(p);
-        }
-        v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
-      }
-    } else {
-      const int c = t & 31;
-#pragma unroll
-      for (int i = 0; i < 4 * QA; ++i) {
-        const int r = (t >> 5) + (NW / 32) * i;
-        float x = 0.f;
-        if (r < rows_valid && c < kw) {
-          const float* p = sg.ptr + (long long)r * sg.ld + k0 + c;
-          x = sg.kind == SEG_X ? __ldg(p) : __ldcg(p);   // stash: written earlier by this CTA, L2-coherent load
-        }
-        v[i] = x;
-      }
-    }
-  }
-  // ---- ... and written as an image pair here; shared-memory tiles are read here.  NaN scan / sanitise
-  //      for x, dropout when enabled. ----
-  template <bool MN>
-  __device__ static __forceinline__ void a_store(float* hi, float* lo, float (&v)[4 * QA], const Smem& sm, const ASeg& sg,
-                                                 int k0, int kw, const Drop& drop, bool scan_nan, bool vec) {
-    const int t = threadIdx.x;
-    const bool from_smem = sg.kind == SEG_SMEM || sg.kind == SEG_SMEM_STAGED;
-    if (vec || from_smem) {
-      const int c4 = t & 7;
-#pragma unroll
-      for (int i = 0; i < QA; ++i) {
-        const int r = (t >> 3) + (NW / 8) * i;
-        float4 q;
-        if (from_smem) q = *reinterpret_cast<const float4*>(sg.ptr + (long long)r * sg.ld + k0 + 4 * c4);   // zero-padded tile
-        else q = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        if (sg.kind == SEG_X) {
-          bool bad = false;
-          if (q.x != q.x) { bad = true; q.x = 0.f; }
-          if (q.y != q.y) { bad = true; q.y = 0.f; }
-          if (q.z != q.z) { bad = true; q.z = 0.f; }
-          if (q.w != q.w) { bad = true; q.w = 0.f; }
-          if (bad && scan_nan) sm.rownan[r] = 1;
-        }
-        if (drop.enabled) {
-          const unsigned col = (unsigned)(sg.wcol + k0 + 4 * c4), row = drop.row_base + (unsigned)r;
-          if ((col & 1u) == 0) {
-            const unsigned h0 = mmn_dropout_hash(drop.seed_mix, row, col >> 1);
-            const unsigned h1 = mmn_dropout_hash(drop.seed_mix, row, (col >> 1) + 1);
-            q.x = (h0 & 0xffffu) >= drop.thr ? q.x * drop.scale : 0.f;
-            q.y = (h0 >> 16) >= drop.thr ? q.y * drop.scale : 0.f;
-            q.z = (h1 & 0xffffu) >= drop.thr ? q.z * drop.scale : 0.f;
-            q.w = (h1 >> 16) >= drop.thr ? q.w * drop.scale : 0.f;
-          } else {
-            q.x = mmn_dropout_keep(drop.seed_mix, row, col + 0, drop.thr) ? q.x * drop.scale : 0.f;
-            q.y = mmn_dropout_keep(drop.seed_mix, row, col + 1, drop.thr) ? q.y * drop.scale : 0.f;
-            q.z = mmn_dropout_keep(drop.seed_mix, row, col + 2, drop.thr) ? q.z * drop.scale : 0.f;
-            q.w = mmn_dropout_keep(drop.seed_mix, row, col + 3, drop.thr) ? q.w * drop.scale : 0.f;
-          }
-          if (4 * c4 + 0 >= kw) q.x = 0.f;
-          if (4 * c4 + 1 >= kw) q.y = 0.f;
-          if (4 * c4 + 2 >= kw) q.z = 0.f;
-          if (4 * c4 + 3 >= kw) q.w = 0.f;
-        }
-        tc_store_quad<MN>(hi, lo, r, c4, q);
-      }
-    } else {
-      const int c = t & 31;
-#pragma unroll
-      for (int i = 0; i < 4 * QA; ++i) {
-        const int r = (t >> 5) + (NW / 32) * i;
-        float x = v[i];
-        if (sg.kind == SEG_X && x != x) {
-          if (scan_nan) sm.rownan[r] = 1;
-          x = 0.f;
-        }
-        if (drop.enabled && c < kw)
-          x = mmn_dropout_keep(drop.seed_mix, drop.row_base + (unsigned)r, (unsigned)(sg.wcol + k0 + c), drop.thr)
-                  ? x * drop.scale : 0.f;
-        tc_store_elem<MN>(hi, lo, r, c, x);
-      }
-    }
-  }
-  // this thread's accumulator slice: lane quarter q = warp & 3 (row 32 q + lane), column slice warp >> 2
-  static_assert(CS == 2, "the epilogues below give each thread 16-column slices (2 warps per lane quarter)");
-  // this thread's 16-column slice h of an N = 32 (h = 0) or N = 64 (h = 0, 1) accumulator: columns 32 h + 16 cs ..
-  __device__ static __forceinline__ void acc_load(const State& es, int q, int col, float (&v)[16]) {
-    tmem_ld16(es.tmem + ((unsigned)(32 * q) << 16) + col, v);
-  }
-
-  // ------------------------------------------------------------------------------------------------
-  // out[r][n] = bias[n] + sum_seg sum_k a[r][k] W[n][wcol + k]      (A, W K-major; N pass of 32 / 64)
-  // ------------------------------------------------------------------------------------------------
-  template <class Epi>
-  __device__ static __forceinline__ void gemm_nt(const Smem& sm, State& es, const float* __restrict__ W, int ldw, int N,
-                                                 const float* __restrict__ bias, int act, const ASeg* segs, int nseg,
-                                                 const Drop& drop, int rows_valid, bool scan_nan, Epi epi) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, cs = warp >> 2;
-    const long long t_begin = MMN_CLOCK();
-    bool avec[2];
-    avec[0] = seg_vec_ok(segs[0]);
-    avec[1] = nseg > 1 ? seg_vec_ok(segs[1]) : false;
-    for (int n0 = 0; n0 < N; n0 += 64) {
-      const int nrows = min(64, N - n0);
-      const int Np = nrows <= 32 ? 32 : 64;
-      float wr[4 * QW], ar[4 * QA];
-      ChunkIt it{0, 0};
-      bool wv = w_vec_ok(W, ldw, segs[0].wcol);
-      w_load_k(wr, W, ldw, n0, nrows, segs[0].wcol, min(KC, segs[0].width), wv);
-      a_load(ar, segs[0], 0, min(KC, segs[0].width), rows_valid, avec[0]);
-      unsigned first = 1;
-      int slot = 0;
-      while (it.valid(nseg)) {
-        const ASeg sg = segs[it.s];
-        const int kw = min(KC, sg.width - it.k0);
-        slot = es.seq & 1;
-        float* xh = sm.XB + slot * 8192;
-        float* wh = sm.WB + slot * 4096;
-        wait(sm, es, slot);                       // MMAs that read this slot two chunks ago are done
-        w_store_k(wh, wh + 2048, wr, wv);
-        a_store<false>(xh, xh + 4096, ar, sm, sg, it.k0, kw, drop, scan_nan && n0 == 0, avec[it.s]);
-        ChunkIt nx = it;
-        nx.next(segs);
-        if (nx.valid(nseg)) {
-          const ASeg& ns = segs[nx.s];
-          const int nkw = min(KC, ns.width - nx.k0);
-          wv = w_vec_ok(W, ldw, ns.wcol + nx.k0);
-          w_load_k(wr, W, ldw, n0, nrows, ns.wcol + nx.k0, nkw, wv);
-          a_load(ar, ns, nx.k0, nkw, rows_valid, avec[nx.s]);
-        }
-        post(sm, es, slot, TC_OP_NT, Np, (kw + 7) >> 3, first);
-        first = 0;
-        it = nx;
-      }
-      auto load_bias = [&](int n, float (&bj)[16]) {
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (n + i + 3 < N) b4 = __ldg(reinterpret_cast<const float4*>(bias + n + i));     // bias offsets are 16-byte aligned
-          else {
-            if (n + i < N) b4.x = __ldg(bias + n + i);
-            if (n + i + 1 < N) b4.y = __ldg(bias + n + i + 1);
-            if (n + i + 2 < N) b4.z = __ldg(bias + n + i + 2);
-          }
-          bj[i] = b4.x; bj[i + 1] = b4.y; bj[i + 2] = b4.z; bj[i + 3] = b4.w;
-        }
-      };
-      float bj[16];
-      load_bias(n0 + 16 * cs, bj);
-      wait(sm, es, slot ^ 1);     // older commit first (in-order completion), then the last one
-      wait(sm, es, slot);
-      tc_fence_after();
-      const long long t_epi = MMN_CLOCK();
-      const int r = 32 * q + lane;
-      for (int h = 0; h < (Np >> 5); ++h) {
-        const int cb = 32 * h + 16 * cs;
-        if (h) load_bias(n0 + cb, bj);
-        float v[16];
-        acc_load(es, q, cb, v);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += bj[i];
-        act_fwd_n(act, v);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) epi(r, n0 + cb + i, v[i]);
-      }
-      es.t[4] += MMN_CLOCK() - t_epi;
-    }
-    MMN_WSYNC_N(kWorkers);        // outputs (and the row NaN flags) visible to every worker
-    es.t[1] += MMN_CLOCK() - t_begin;
-  }
-
-  // ------------------------------------------------------------------------------------------------
-  // out[r][j] = sum_n dz[r][n] W[n][col0 + j]      (dz K-major from its shared tile, W MN-major)
-  // ------------------------------------------------------------------------------------------------
-  template <class Pre, class Epi>
-  __device__ static __forceinline__ void gemm_nn(const Smem& sm, State& es, const float* dz, int ldd, int N,
-                                                 const float* __restrict__ W, int ldw, int col0, int J, Pre pre, Epi epi) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, cs = warp >> 2;
-    const int r = 32 * q + lane;
-    const long long t_begin = MMN_CLOCK();
-    Drop nodrop;
-    nodrop.enabled = 0; nodrop.seed_mix = 0; nodrop.thr = 0; nodrop.row_base = 0; nodrop.scale = 1.f;
-    for (int j0 = 0; j0 < J; j0 += 64) {
-      const int jw = min(64, J - j0);
-      const int Np = jw <= 32 ? 32 : 64;
-      float pv[16];
-#pragma unroll
-      for (int i = 0; i < 16; i += 4) {
-        const float4 p4 = pre(r, j0 + 16 * cs + i);
-        pv[i] = p4.x; pv[i + 1] = p4.y; pv[i + 2] = p4.z; pv[i + 3] = p4.w;
-      }
-      const bool wv = w_vec_ok(W, ldw, col0 + j0);
-      float wr[4 * QW], dummy[4 * QA];
-      w_load_mn(wr, W, ldw, 0, min(32, N), col0 + j0, jw, wv);
-      unsigned first = 1;
-      int slot = 0;
-      for (int n0 = 0; n0 < N; n0 += 32) {
-        const int nw = min(32, N - n0);
-        slot = es.seq & 1;
-        float* xh = sm.XB + slot * 8192;
-        float* wh = sm.WB + slot * 4096;
-        wait(sm, es, slot);
-        w_store_mn(wh, wh + 2048, wr, wv);
-        ASeg sg;
-        sg.ptr = dz; sg.ld = ldd; sg.width = N; sg.kind = SEG_SMEM; sg.wcol = 0;
-        a_store<false>(xh, xh + 4096, dummy, sm, sg, n0, nw, nodrop, false, false);
-        if (n0 + 32 < N) w_load_mn(wr, W, ldw, n0 + 32, min(32, N - n0 - 32), col0 + j0, jw, wv);
-        post(sm, es, slot, TC_OP_NN, Np, (nw + 7) >> 3, first);
-        first = 0;
-      }
-      wait(sm, es, slot ^ 1);
-      wait(sm, es, slot);
-      tc_fence_after();
-      const long long t_epi = MMN_CLOCK();
-      for (int h = 0; h < (Np >> 5); ++h) {
-        const int cb = 32 * h + 16 * cs;
-        if (h) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 p4 = pre(r, j0 + cb + i);
-            pv[i] = p4.x; pv[i + 1] = p4.y; pv[i + 2] = p4.z; pv[i + 3] = p4.w;
-          }
-        }
-        float v[16];
-        acc_load(es, q, cb, v);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) epi(r, j0 + cb + i, v[i], pv[i]);
-      }
-      es.t[5] += MMN_CLOCK() - t_epi;
-    }
-    MMN_WSYNC_N(kWorkers);
-    es.t[2] += MMN_CLOCK() - t_begin;
-  }
-
-  // ------------------------------------------------------------------------------------------------
-  // gW[n][wcol + k] += sum_r dz[r][n] a[r][k]      (both operands MN-major, contraction = the 128 rows)
-  // D[n][k]: lanes = output rows n of one 32-column group of dz (all four lane quarters see the same
-  // group: group stride 0), columns = the 32 k of a chunk.  Staging: XB[0,32K) = dz {hi, lo};
-  // input chunks alternate between WB and XB[32K,64K); accumulator columns alternate with them, so the
-  // epilogue (TMEM -> red.global) of chunk c overlaps the MMAs of chunk c + 1.
-  // ------------------------------------------------------------------------------------------------
-  __device__ static __forceinline__ void gemm_tn(const Smem& sm, State& es, const float* dz, int ldd, int N, const ASeg& sg,
-                                                 const Drop& drop, int rows_valid, float* __restrict__ gW, int ldw) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, cs = warp >> 2;
-    const bool vec_ok = ((ldw & 3) == 0) && ((sg.wcol & 3) == 0) && ((reinterpret_cast<size_t>(gW) & 15) == 0);
-    const bool avec = seg_vec_ok(sg);
-    const long long t_begin = MMN_CLOCK();
-    auto epilogue = [&](int slot, int nb0, int k0) {
-      wait(sm, es, slot);
-      tc_fence_after();
-      const long long t_epi = MMN_CLOCK();
-      constexpr int TC = 16;               // chunk columns per thread
-      float v[16];
-      acc_load(es, q, 32 * slot + TC * cs, v);
-      const int n = nb0 + lane;
-      if (q == 0 && n < N) {
-        const int kc = k0 + TC * cs;
-        float* dst = gW + (long long)n * ldw + sg.wcol + kc;
-#pragma unroll
-        for (int i = 0; i < TC; i += 4) {
-          if (vec_ok && kc + i + 3 < sg.width) {
-            atomicAdd(reinterpret_cast<float4*>(dst + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
-          } else {
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (kc + i + u < sg.width) atomicAdd(dst + i + u, v[i + u]);
-          }
-        }
-      }
-      es.t[6] += MMN_CLOCK() - t_epi;
-    };
-    for (int nb0 = 0; nb0 < N; nb0 += 32) {
-      float ar[4 * QA];
-      a_load(ar, sg, 0, min(KC, sg.width), rows_valid, avec);
-      drain(sm, es);
-      MMN_WSYNC_N(kWorkers);       // every worker is past its reads of the staging buffers / dz tile writes
-      for (int idx = tid; idx < 128 * 8; idx += kWorkers) {      // dz column group -> MN-major A image pair
-        const int rr = idx >> 3, c4 = idx & 7;
-        const float4 v = *reinterpret_cast<const float4*>(dz + rr * ldd + nb0 + 4 * c4);
-        tc_store_quad<true>(sm.XB, sm.XB + 4096, rr, c4, v);
-      }
-      int prev_slot = -1, prev_k0 = 0;
-      for (int k0 = 0; k0 < sg.width; k0 += KC) {
-        const int kw = min(KC, sg.width - k0);
-        const int slot = es.seq & 1;
-        float* ih = slot ? sm.XB + 8192 : sm.WB;
-        wait(sm, es, slot);        // (already collected by the epilogue two chunks ago)
-        a_store<true>(ih, ih + 4096, ar, sm, sg, k0, kw, drop, false, avec);
-        if (k0 + KC < sg.width) a_load(ar, sg, k0 + KC, min(KC, sg.width - k0 - KC), rows_valid, avec);
-        post(sm, es, slot, TC_OP_TN, 32, 16, 1u);
-        if (prev_slot >= 0) epilogue(prev_slot, nb0, prev_k0);
-        prev_slot = slot;
-        prev_k0 = k0;
-      }
-      if (prev_slot >= 0) epilogue(prev_slot, nb0, prev_k0);
-    }
-    MMN_WSYNC_N(kWorkers);
-    es.t[3] += MMN_CLOCK() - t_begin;
-  }
 };
+
 
 // ------------------------------------------------------------------------------------------------
 // self-test of the three operand configurations the engine uses (validated on the GPU by

@@ -239,8 +239,10 @@ struct V2Res {       // a GEMM operand segment that already lives in TMEM
   bool masked;       // dropout applies: staged through an x chunk slot instead of being read in place
 };
 
-template <bool TRAIN>
-__global__ void __launch_bounds__(V2Engine::kBlockThreads, 1) mmn_step_kernel_v2(const StepArgs args) {
+// forward only (test / predict / get_states): round 2 dropped this kernel's backward pass — the FP32-FMA kernel is the fp32
+// train path and the bf16 tile kernel (mmn_nb.cuh) the tensor-core one; see DESIGN.md section 4
+template <int = 0>
+__global__ void __launch_bounds__(V2Engine::kBlockThreads, 1) mmn_forward_kernel_v2(const StepArgs args) {
   using ENG = V2Engine;
   constexpr int TM = 128, NT = ENG::kWorkers;
   const DevPlan& P = *args.plan;
@@ -281,7 +283,6 @@ __global__ void __launch_bounds__(V2Engine::kBlockThreads, 1) mmn_step_kernel_v2
   t.lane_addr = es.tmem + ((unsigned)(32 * t.q) << 16);
 
   const long long n_tiles = (args.n_rows + TM - 1) / TM;
-  float* slotp = TRAIN ? args.stash + (long long)blockIdx.x * args.slot_floats : nullptr;
   Drop nodrop;
   nodrop.enabled = 0; nodrop.seed_mix = 0; nodrop.thr = 0; nodrop.row_base = 0; nodrop.scale = 1.f;
 
@@ -454,14 +455,12 @@ __global__ void __launch_bounds__(V2Engine::kBlockThreads, 1) mmn_step_kernel_v2
           const int N = ly.out_dim, act = ly.act, C = dec.C;
           V2Res rs;
           rs.asel = in_sel; rs.width = in_w; rs.wcol = 0; rs.masked = false;
-          float* stash = TRAIN ? slotp + (long long)(stash_dec_off(P, k) + dec.stash_off + ly.stash_off) * TM : nullptr;
           gemm_fwd(params + ly.w_off, ly.ktot, N, params + ly.b_off, nullptr, 0, 0, nodrop, &rs, 1, no_mid,
                    [&](int h, int nb, float (&v)[16]) {
                      const long long te0 = MMN_CLOCK();
                      act_fwd_n(act, v);
 #pragma unroll
                      for (int i = 0; i < 16; ++i) v[i] = nb + i < N ? v[i] : 0.f;
-                     if (TRAIN) v2_store_row16(stash, N, t.r, nb, N, v);
                      if (!last) {
                        v2_st_pair(t, (out_sel == V2_A_P ? V2_P_HI : V2_Q_HI) + 32 * h, (out_sel == V2_A_P ? V2_P_LO : V2_Q_LO) + 32 * h, v);
                        es.t[9] += MMN_CLOCK() - te0;
@@ -541,7 +540,6 @@ __global__ void __launch_bounds__(V2Engine::kBlockThreads, 1) mmn_step_kernel_v2
         v[i] = c < S ? __ldg(params + P.init_off + c) : 0.f;
       }
       v2_st_pair(t, V2_S_HI + 32 * h, V2_S_LO + 32 * h, v);
-      if (TRAIN) v2_store_row16(slotp + (long long)stash_state_off(P, 0) * TM, S, t.r, 32 * h + 16 * t.cs, S, v);
     }
     tmem_wait_st();
     MMN_WSYNC_N(NT);
@@ -554,14 +552,7 @@ __global__ void __launch_bounds__(V2Engine::kBlockThreads, 1) mmn_step_kernel_v2
       const bool skip = args.skip_flags && args.skip_flags[k - 1] != 0;
       bool pr = false;
       if (!skip) {
-        Drop drop = nodrop;
-        if (TRAIN && args.training && enc.p_drop > 0.f && enc.L[0].has_state) {
-          drop.enabled = 1;
-          drop.seed_mix = args.dropout_seed ^ ((unsigned)e * 0x9E3779B9u);
-          drop.thr = (unsigned)(enc.p_drop * 65536.f);
-          drop.row_base = (unsigned)(args.row_offset + row0);
-          drop.scale = 1.f / (1.f - enc.p_drop);
-        }
+        const Drop drop = nodrop;                 // evaluation mode: no dropout (multimodn.py:267)
         unsigned in_sel = V2_A_P;
         int in_w = 0;
         float sc = 0.f;
@@ -575,7 +566,6 @@ __global__ void __launch_bounds__(V2Engine::kBlockThreads, 1) mmn_step_kernel_v2
           if (j > 0) { rs[nres].asel = in_sel; rs[nres].width = in_w; rs[nres].wcol = 0; rs[nres].masked = false; ++nres; }
           if (ly.has_state) { rs[nres].asel = V2_A_S; rs[nres].width = S; rs[nres].wcol = ly.in_dim; rs[nres].masked = use_drop; ++nres; }
           const int N = ly.out_dim, act = ly.act;
-          float* stash = (TRAIN && !last) ? slotp + (long long)(stash_enc_off(P, k) + ly.stash_off) * TM : nullptr;
           auto mid = [&] {
             if (j == 0) {           // every x chunk of the step has been scanned: fix this step's present mask
               MMN_WSYNC_N(NT);
@@ -589,7 +579,6 @@ __global__ void __launch_bounds__(V2Engine::kBlockThreads, 1) mmn_step_kernel_v2
 #pragma unroll
                      for (int i = 0; i < 16; ++i) v[i] = nb + i < N ? v[i] : 0.f;
                      if (!last) {
-                       if (TRAIN) v2_store_row16(stash, N, t.r, nb, N, v);
                        v2_st_pair(t, (out_sel == V2_A_P ? V2_P_HI : V2_Q_HI) + 32 * h, (out_sel == V2_A_P ? V2_P_LO : V2_Q_LO) + 32 * h, v);
                      } else {
                        // per-row select: missing rows keep their state bit for bit; state-change sum
@@ -610,22 +599,20 @@ __global__ void __launch_bounds__(V2Engine::kBlockThreads, 1) mmn_step_kernel_v2
           in_sel = out_sel;
           in_w = N;
         }
-        sc = warp_sum(sc);
-        if (t.lane == 0 && TRAIN) atomicAdd(&sm.met[met_sc(P, e)], (double)sc);
+        (void)sc;
       }
       // bookkeeping of the step: present mask, counters; stash s_k; reset the NaN flags
       if (t.cs == 0) {
         sm.present[k * TM + t.r] = pr;
         if (pr) { atomicAdd(&sm.cnt[e + 1], 1); sm.tile_any[k] = 1; }
       }
-      if (TRAIN || (args.final_state && k == L)) {
+      if (args.final_state && k == L) {
         for (int h = 0; h < ((S + 31) >> 5); ++h) {
           float so[16], sl[16];
           v2_ld(t, V2_S_HI + 32 * h, so);
           v2_ld(t, V2_S_LO + 32 * h, sl);
 #pragma unroll
           for (int i = 0; i < 16; ++i) so[i] += sl[i];
-          if (TRAIN) v2_store_row16(slotp + (long long)stash_state_off(P, k) * TM, S, t.r, 32 * h + 16 * t.cs, S, so);
           if (args.final_state && k == L && valid) v2_store_row16(args.final_state + row0 * S, S, t.r, 32 * h + 16 * t.cs, S, so);
         }
       }
@@ -642,331 +629,6 @@ __global__ void __launch_bounds__(V2Engine::kBlockThreads, 1) mmn_step_kernel_v2
         for (int i = 0; i < 16; ++i) so[i] += sl[i];
         v2_store_row16(args.final_state + row0 * S, S, t.r, 32 * h + 16 * t.cs, S, so);
       }
-    }
-    if (TRAIN) {
-      // =======================================================================================================
-      // backward: replay the sequence in reverse.  G = dLoss/ds_k lives in TMEM (raw fp32); every dz tile is written
-      // by the epilogue that produces it both to TMEM (hi, lo: A operand of the data-gradient GEMM) and to shared
-      // memory as MN-major images (A operand of the weight-gradient GEMM, source of the bias gradient).
-      // =======================================================================================================
-      float* grads = args.grads;
-      const long long t_bwd0 = MMN_CLOCK();
-      Smem smv1;                        // the staging helpers of mmn_tc.cuh only touch rownan (unused here)
-      smv1.rownan = sm.rownan;
-      {
-        float z[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) z[i] = 0.f;
-        for (int h = 0; h < 2; ++h) v2_st(t, V2_G + 32 * h, z);
-        tmem_wait_st();
-      }
-      // this thread's 16-column slice h of a dz tile -> TMEM operand pair + MN-major image pair of group h
-      auto stage_dz = [&](unsigned hi_col, unsigned lo_col, int h, const float (&v)[16]) {
-        v2_st_pair(t, hi_col + 32 * h, lo_col + 32 * h, v);
-        float* gh = sm.DZ + h * 8192;
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          tc_store_quad<true>(gh, gh + 4096, t.r, 4 * t.cs + u, make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]));
-      };
-      // bias gradient: column sums of the dz images
-      auto colsum_dz = [&](int N, float* __restrict__ gb) {
-        const long long t_c0 = MMN_CLOCK();
-        const int c = tid & 31, part = tid >> 5;        // 8 parts x 16 rows
-        for (int g = 0; g < ((N + 31) >> 5); ++g) {
-          const float* gh = sm.DZ + g * 8192;
-          float sacc = 0.f;
-#pragma unroll 4
-          for (int rr = part * 16; rr < part * 16 + 16; ++rr) {
-            const int o = v2_mn_off(rr, c);
-            sacc += gh[o] + gh[4096 + o];
-          }
-          sm.RED[part * 32 + c] = sacc;
-          MMN_WSYNC_N(NT);
-          if (tid < 32 && 32 * g + tid < N) {
-            float tot = 0.f;
-#pragma unroll
-            for (int pp = 0; pp < 8; ++pp) tot += sm.RED[pp * 32 + tid];
-            atomicAdd(gb + 32 * g + tid, tot);
-          }
-          MMN_WSYNC_N(NT);
-        }
-        es.t[11] += MMN_CLOCK() - t_c0;
-      };
-      // weight gradient of one K-segment: gW[n][wcol + k] += sum_r dz[r][n] in[r][k]
-      auto tn = [&](int N, const ASeg& sg, const Drop& drop, int rv, float* __restrict__ gW, int ldw) {
-        const bool vec_ok = ((ldw & 3) == 0) && ((sg.wcol & 3) == 0) && ((reinterpret_cast<size_t>(gW) & 15) == 0);
-        const bool avec = seg_vec_ok(sg);
-        const long long t_t0 = MMN_CLOCK();
-        auto epilogue = [&](int slot, int g, int k0) {
-          ENG::wait(sm, es, slot);
-          tc_fence_after();
-          float v[16];
-          v2_ld(t, V2_ACC + 32 * slot, v);
-          const int n = 32 * g + t.lane;
-          if (t.q == 0 && n < N) {
-            const int kc = k0 + 16 * t.cs;
-            float* dst = gW + (long long)n * ldw + sg.wcol + kc;
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              if (vec_ok && kc + i + 3 < sg.width) {
-                atomicAdd(reinterpret_cast<float4*>(dst + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
-              } else {
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                  if (kc + i + u < sg.width) atomicAdd(dst + i + u, v[i + u]);
-              }
-            }
-          }
-        };
-        for (int g = 0; g < ((N + 31) >> 5); ++g) {
-          float ar[16];
-          TcEngine::a_load(ar, sg, 0, min(KC, sg.width), rv, avec);
-          int prev_slot = -1, prev_k0 = 0;
-          for (int k0 = 0; k0 < sg.width; k0 += KC) {
-            const int kw = min(KC, sg.width - k0);
-            const int slot = es.seq & 1;
-            float* ih = slot ? sm.IN1 : sm.IN0;
-            ENG::wait(sm, es, slot);
-            TcEngine::a_store<true>(ih, ih + 4096, ar, smv1, sg, k0, kw, drop, false, avec);
-            if (k0 + KC < sg.width) TcEngine::a_load(ar, sg, k0 + KC, min(KC, sg.width - k0 - KC), rv, avec);
-            ENG::post(sm, es, slot, V2_OP_TN | ((unsigned)g << 13));
-            if (prev_slot >= 0) epilogue(prev_slot, g, prev_k0);
-            prev_slot = slot;
-            prev_k0 = k0;
-          }
-          if (prev_slot >= 0) epilogue(prev_slot, g, prev_k0);
-        }
-        es.t[12] += MMN_CLOCK() - t_t0;
-      };
-      // data gradient: ACC[r][j] = sum_n dz[r][n] W[n][col0 + j]; dz = TMEM pair `asel` of width N; J <= 64 outputs;
-      // pre(h) loads this thread's slice of whatever the epilogue needs from global BEFORE the MMAs are awaited
-      auto nn = [&](unsigned asel, int N, const float* __restrict__ W, int ldw, int col0, int J, auto pre, auto epi) {
-        const bool wv = w_vec_ok(W, ldw, col0);
-        const long long t_n0 = MMN_CLOCK();
-        float wr[8];
-        TcEngine::w_load_mn(wr, W, ldw, 0, min(32, N), col0, J, wv);
-        int slot = 0;
-        for (int n0 = 0; n0 < N; n0 += 32) {
-          const int nw = min(32, N - n0);
-          slot = es.seq & 1;
-          ENG::wait(sm, es, slot);
-          float* wh = sm.WB + slot * 4096;
-          TcEngine::w_store_mn(wh, wh + 2048, wr, wv);
-          if (n0 + 32 < N) TcEngine::w_load_mn(wr, W, ldw, n0 + 32, min(32, N - n0 - 32), col0, J, wv);
-          ENG::post(sm, es, slot, ENG::op_ts(true, J, n0 == 0, (nw + 7) >> 3, asel, n0 >> 5));
-        }
-        float pv[2][16];
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-          if (32 * h < J) pre(h, pv[h]);
-        ENG::wait(sm, es, slot ^ 1);
-        ENG::wait(sm, es, slot);
-        tc_fence_after();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (32 * h < J) {
-            float v[16];
-            v2_ld(t, V2_ACC + 32 * h, v);
-            epi(h, 32 * h + 16 * t.cs, v, pv[h]);
-          }
-        }
-        tmem_wait_st();
-        es.t[13] += MMN_CLOCK() - t_n0;
-      };
-      auto sel_hi = [](unsigned sel) { return sel == V2_A_P ? V2_P_HI : sel == V2_A_Q ? V2_Q_HI : V2_T_HI; };
-      auto sel_lo = [](unsigned sel) { return sel == V2_A_P ? V2_P_LO : sel == V2_A_Q ? V2_Q_LO : V2_T_LO; };
-
-      auto decoders_backward = [&](int k) {
-        const float* sk = slotp + (long long)stash_state_off(P, k) * TM;
-        const bool m = sm.present[k * TM + t.r] != 0;
-        for (int d = 0; d < D; ++d) {
-          const DevDecoder& dec = P.dec[d];
-          const int C = dec.C, nl = dec.n_layers;
-          const long long dbase = (long long)(stash_dec_off(P, k) + dec.stash_off) * TM;
-          {   // dz of the last layer from the stashed outputs p: CE-on-outputs gradient through out_act
-            const float* pst = slotp + dbase + (long long)dec.L[nl - 1].stash_off * TM;
-            const ActBwd dact(dec.L[nl - 1].act);
-            float v[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = 0.f;
-            if (t.cs == 0) {
-              float pz[16];
-              float mx = -3.4e38f;
-#pragma unroll
-              for (int c = 0; c < 16; ++c) {
-                pz[c] = c < C ? __ldcg(pst + t.r * C + c) : 0.f;
-                if (c < C) mx = fmaxf(mx, pz[c]);
-              }
-              float se = 0.f;
-#pragma unroll
-              for (int c = 0; c < 16; ++c)
-                if (c < C) se += expf(pz[c] - mx);
-              int y = sm.ys[t.r * D + d];
-              y = y < 0 ? 0 : (y >= C ? C - 1 : y);
-              const float coef = m ? args.c_err : 0.f, inv = 1.f / se;
-#pragma unroll
-              for (int c = 0; c < 16; ++c)
-                if (c < C) v[c] = coef * (expf(pz[c] - mx) * inv - (c == y ? 1.f : 0.f)) * dact(pz[c]);
-            }
-            stage_dz(V2_P_HI, V2_P_LO, 0, v);
-            tmem_wait_st();
-          }
-          unsigned cur = V2_A_P;
-          for (int j = nl - 1; j >= 0; --j) {
-            const DevLayer& ly = dec.L[j];
-            MMN_WSYNC_N(NT);              // the dz images are complete
-            colsum_dz(ly.out_dim, grads + ly.b_off);
-            ASeg seg;
-            seg.kind = SEG_STASH; seg.wcol = 0; seg.width = ly.in_dim; seg.ld = ly.in_dim;
-            seg.ptr = j == 0 ? sk : slotp + dbase + (long long)dec.L[j - 1].stash_off * TM;
-            tn(ly.out_dim, seg, nodrop, TM, grads + ly.w_off, ly.ktot);
-            if (j > 0) {
-              const unsigned other = cur == V2_A_P ? V2_A_Q : V2_A_P;
-              const float* ast = slotp + dbase + (long long)dec.L[j - 1].stash_off * TM;
-              const int J = ly.in_dim;
-              const ActBwd dact(dec.L[j - 1].act);
-              nn(cur, ly.out_dim, params + ly.w_off, ly.ktot, 0, J,
-                 [&](int h, float (&pv)[16]) { v2_load_row16<true>(ast, J, t.r, 32 * h + 16 * t.cs, J, v2_vec_ok(ast, J), pv); },
-                 [&](int h, int jb, float (&v)[16], float (&pv)[16]) {
-#pragma unroll
-                   for (int i = 0; i < 16; ++i) v[i] = jb + i < J ? v[i] * dact(pv[i]) : 0.f;
-                   stage_dz(sel_hi(other), sel_lo(other), h, v);
-                 });
-              cur = other;
-            } else {
-              nn(cur, ly.out_dim, params + ly.w_off, ly.ktot, 0, S,
-                 [&](int, float (&)[16]) {},
-                 [&](int h, int jb, float (&v)[16], float (&)[16]) {
-                   float g[16];
-                   v2_ld(t, V2_G + 32 * h, g);
-#pragma unroll
-                   for (int i = 0; i < 16; ++i) g[i] += jb + i < S ? v[i] : 0.f;
-                   v2_st(t, V2_G + 32 * h, g);
-                 });
-            }
-          }
-        }
-      };
-
-      for (int k = L; k >= 1; --k) {
-        if (!sm.tile_any[k]) continue;       // no row of this tile took the step: s_k == s_{k-1}, nothing flows
-        const int e = args.seq_enc[k - 1], pos = args.seq_pos[k - 1];
-        const DevEncoder& enc = P.enc[e];
-        decoders_backward(k);
-        const float* sk = slotp + (long long)stash_state_off(P, k) * TM;
-        const float* skm1 = slotp + (long long)stash_state_off(P, k - 1) * TM;
-        const bool prk = sm.present[k * TM + t.r] != 0;
-        const int nl = enc.n_layers;
-        {   // G += u_k ; dz_last = present ? G * act'(s_k) : 0
-          const ActBwd dact(enc.L[nl - 1].act);
-          const bool sv = v2_vec_ok(sk, S);
-          for (int h = 0; h < ((S + 31) >> 5); ++h) {
-            float g[16], a[16], b[16];
-            v2_load_row16<true>(sk, S, t.r, 32 * h + 16 * t.cs, S, sv, a);
-            v2_load_row16<true>(skm1, S, t.r, 32 * h + 16 * t.cs, S, sv, b);
-            v2_ld(t, V2_G + 32 * h, g);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              g[i] += args.c_sc * (a[i] - b[i]);
-              a[i] = prk ? g[i] * dact(a[i]) : 0.f;
-            }
-            v2_st(t, V2_G + 32 * h, g);
-            stage_dz(V2_T_HI, V2_T_LO, h, a);
-          }
-          tmem_wait_st();
-        }
-        Drop drop = nodrop;
-        if (args.training && enc.p_drop > 0.f && enc.L[0].has_state) {
-          drop.enabled = 1;
-          drop.seed_mix = args.dropout_seed ^ ((unsigned)e * 0x9E3779B9u);
-          drop.thr = (unsigned)(enc.p_drop * 65536.f);
-          drop.row_base = (unsigned)(args.row_offset + row0);
-          drop.scale = 1.f / (1.f - enc.p_drop);
-        }
-        unsigned cur = V2_A_T;
-        const long long ebase = (long long)stash_enc_off(P, k) * TM;
-        for (int j = nl - 1; j >= 0; --j) {
-          const DevLayer& ly = enc.L[j];
-          const bool use_drop = drop.enabled && j == 0;
-          MMN_WSYNC_N(NT);
-          colsum_dz(ly.out_dim, grads + ly.b_off);
-          ASeg seg;
-          seg.wcol = 0; seg.width = ly.in_dim;
-          if (j == 0) {
-            seg.kind = SEG_X; seg.ptr = args.x[pos] + row0 * args.x_ld[pos]; seg.ld = args.x_ld[pos];
-          } else {
-            seg.kind = SEG_STASH; seg.ptr = slotp + ebase + (long long)enc.L[j - 1].stash_off * TM; seg.ld = ly.in_dim;
-          }
-          tn(ly.out_dim, seg, use_drop ? drop : nodrop, j == 0 ? rows_valid : TM, grads + ly.w_off, ly.ktot);
-          if (ly.has_state) {
-            ASeg s2;
-            s2.kind = SEG_STASH; s2.ptr = skm1; s2.ld = S; s2.width = S; s2.wcol = ly.in_dim;
-            tn(ly.out_dim, s2, use_drop ? drop : nodrop, TM, grads + ly.w_off, ly.ktot);
-          }
-          const unsigned other = cur == V2_A_P ? V2_A_Q : V2_A_P;
-          if (ly.has_state) {
-            // carry into G: present rows take dz W_s (through the dropout mask), absent rows keep G; then remove u_k
-            const int in_dim = ly.in_dim;
-            const bool sv = v2_vec_ok(sk, S);
-            nn(cur, ly.out_dim, params + ly.w_off, ly.ktot, in_dim, S,
-               [&](int h, float (&pv)[16]) {
-                 float b[16];
-                 v2_load_row16<true>(sk, S, t.r, 32 * h + 16 * t.cs, S, sv, pv);
-                 v2_load_row16<true>(skm1, S, t.r, 32 * h + 16 * t.cs, S, sv, b);
-#pragma unroll
-                 for (int i = 0; i < 16; ++i) pv[i] = args.c_sc * (pv[i] - b[i]);
-               },
-               [&](int h, int jb, float (&v)[16], float (&pv)[16]) {
-                 float g[16];
-                 v2_ld(t, V2_G + 32 * h, g);
-#pragma unroll
-                 for (int i = 0; i < 16; ++i) {
-                   float carry = v[i];
-                   if (use_drop)
-                     carry = mmn_dropout_keep(drop.seed_mix, drop.row_base + (unsigned)t.r, (unsigned)(in_dim + jb + i), drop.thr)
-                                 ? carry * drop.scale : 0.f;
-                   const float gn = prk ? carry : g[i];
-                   g[i] = jb + i < S ? gn - pv[i] : 0.f;
-                 }
-                 v2_st(t, V2_G + 32 * h, g);
-               });
-          }
-          if (j > 0) {
-            const float* ast = slotp + ebase + (long long)enc.L[j - 1].stash_off * TM;
-            const int J = ly.in_dim;
-            const ActBwd dact(enc.L[j - 1].act);
-            nn(cur, ly.out_dim, params + ly.w_off, ly.ktot, 0, J,
-               [&](int h, float (&pv)[16]) { v2_load_row16<true>(ast, J, t.r, 32 * h + 16 * t.cs, J, v2_vec_ok(ast, J), pv); },
-               [&](int h, int jb, float (&v)[16], float (&pv)[16]) {
-#pragma unroll
-                 for (int i = 0; i < 16; ++i) v[i] = jb + i < J ? v[i] * dact(pv[i]) : 0.f;
-                 stage_dz(sel_hi(other), sel_lo(other), h, v);
-               });
-            cur = other;
-          }
-        }
-      }
-      decoders_backward(0);
-      // tile backward of state.py:30: column sums of G
-      MMN_WSYNC_N(NT);
-      {
-        float* plain = sm.DZ;              // [128][64] scratch
-        for (int h = 0; h < 2; ++h) {
-          float g[16];
-          v2_ld(t, V2_G + 32 * h, g);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) plain[t.r * 64 + 32 * h + 16 * t.cs + i] = g[i];
-        }
-        MMN_WSYNC_N(NT);
-        const int c = tid & 63, part = tid >> 6;      // 4 parts x 32 rows
-        float sacc = 0.f;
-        for (int rr = part * 32; rr < part * 32 + 32; ++rr) sacc += plain[rr * 64 + c];
-        sm.RED[part * 64 + c] = sacc;
-        MMN_WSYNC_N(NT);
-        if (tid < 64 && tid < S) atomicAdd(grads + P.init_off + tid, sm.RED[tid] + sm.RED[64 + tid] + sm.RED[128 + tid] + sm.RED[192 + tid]);
-        MMN_WSYNC_N(NT);
-      }
-      es.t[14] += MMN_CLOCK() - t_bwd0;
     }
   }
 
@@ -994,10 +656,6 @@ __global__ void __launch_bounds__(V2Engine::kBlockThreads, 1) mmn_step_kernel_v2
       else v = sm.met[i] * args.inv_rows_global / (double)S;
       if (v != 0.0) atomicAdd(args.metrics + i, v);
     }
-  }
-  if (TRAIN && args.grads) {
-    for (int e = tid; e < E; e += NT)
-      if (sm.cnt[e + 1]) atomicAdd(args.grads + P.n_params + e, (float)sm.cnt[e + 1]);
   }
 }
 

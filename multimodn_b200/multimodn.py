@@ -38,7 +38,7 @@ from . import _lib
 from .decoders.multimod_decoder import MultiModDecoder
 from .encoders.multimod_encoder import MultiModEncoder
 from .history import MultiModNHistory
-from .metrics import get_performance_metrics, performance_metrics  # noqa: F401  (re-exported like the reference)
+from .metrics import get_performance_metrics, performance_metrics, to_host  # noqa: F401  (re-exported like the reference)
 from .plan import PackedModel
 from .state import InitState, TrainableInitState
 
@@ -557,15 +557,17 @@ class MultiModN(nn.Module):
         # end-of-test metric suite on the last-encoder outputs (multimodn.py:411-419)
         results = [[] for _ in range(rt.D)]
         if outs:
-            out_all = torch.cat(outs).cpu()
-            tgt_all = torch.cat(tgts).cpu()
+            # device-side: the (N, sum C) outputs stay in HBM; sort-based curves / AUROC / F1 are torch CUDA
+            # ops there and only the result tuple is copied to the host
+            out_all = torch.cat(outs)
+            tgt_all = torch.cat(tgts)
             col = 0
             for d, dec in enumerate(rt.packed.decoders):
                 o = out_all[:, col:col + dec.n_classes]
                 col += dec.n_classes
                 o = o / o.sum(dim=1, keepdim=True)                          # :415
                 pred = torch.max(o, dim=1)[1]                               # :416
-                results[d] = get_performance_metrics(tgt_all[:, d], pred, o[:, 1] if dec.n_classes > 1 else o[:, 0])
+                results[d] = to_host(get_performance_metrics(tgt_all[:, d], pred, o[:, 1] if dec.n_classes > 1 else o[:, 0]))
         return results
 
     # -- inference (multimodn.py:422-458) --------------------------------------------------------

@@ -10,17 +10,10 @@ def test_parity_case(emu, name):
     run_parity_case(name, "cpu")
 
 
-@pytest.mark.parametrize("name", ["multi_tile_ragged", "mnar_rows", "dropout_mnar", "mlp_kind_wide_hidden"])
-def test_parity_case_tc_engine(emu, monkeypatch, name):
-    """the tcgen05 engine's staging / command protocol against the emulator's functional UMMA model"""
-    monkeypatch.setenv("MMN_ENGINE", "tc")
+@pytest.mark.parametrize("name", ["multi_tile_ragged", "mnar_rows", "mlp_kind_wide_hidden"])
+def test_forward_engine_is_tmem_resident_where_the_model_qualifies(emu, name):
+    """run_parity_case's predict / get_states / test legs go through the TMEM-resident forward kernel on the emulator's
+    tcgen05 / TMEM model"""
     model = run_parity_case(name, "cpu")
-    assert emu.dll.mmn_plan_engine(model.runtime().plan) == 1
-
-
-@pytest.mark.parametrize("name", ["multi_tile_ragged", "mnar_rows", "dropout_mnar", "mlp_kind_wide_hidden"])
-def test_parity_case_tmem_resident_engine(emu, monkeypatch, name):
-    """training through the TMEM-resident kernel (forward + backward) on the emulator's tcgen05 / TMEM model"""
-    monkeypatch.setenv("MMN_ENGINE", "tc2")
-    model = run_parity_case(name, "cpu")
-    assert emu.dll.mmn_plan_engine(model.runtime().plan) == 2
+    assert emu.dll.mmn_plan_engine(model.runtime().plan) == 0
+    assert emu.dll.mmn_plan_forward_engine(model.runtime().plan) == 2

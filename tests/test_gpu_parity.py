@@ -220,55 +220,7 @@ def test_c5_predict_permutation_properties():
         assert (out[first + 1] == alone[first + 1]).all()
 
 
-# ---- both GEMM engines: FP32-FMA is the default; MMN_ENGINE=tc selects the tcgen05 3xTF32 engine -------------
-TC_CASES = ["multi_tile_ragged", "mnar_rows", "mlp_kind_wide_hidden", "dropout_mnar"]
-
-
-@pytest.fixture
-def tc_engine(monkeypatch):
-    monkeypatch.setenv("MMN_ENGINE", "tc")
-
-
-@pytest.mark.parametrize("name", TC_CASES)
-def test_oracle_case_tc_engine(tc_engine, name):
-    model = run_parity_case(name, DEV)
-    from multimodn_b200 import _lib
-    assert _lib.get_lib().dll.mmn_plan_engine(model.runtime().plan) == 1
-
-
-@pytest.mark.parametrize("name,names,mode", [("c2_mimic_full", ["a", "b"], "row"), ("c2_mimic_small", ["a", "b"], "batch"),
-                                             ("zoo", ["a", "b", "c"], "row"), ("missing_row", ["a", "b"], "row")])
-def test_golden_tc_engine(tc_engine, name, names, mode):
-    run_golden(name, names, mode, check_val=name != "zoo", check_predict=name != "missing_row")
-
-
-def test_golden_c1_titanic_two_epochs_tc_engine(tc_engine):
-    test_golden_c1_titanic_two_epochs("fused_adam")
-
-
-# ---- MMN_ENGINE=tc2: training through the TMEM-resident kernel (forward + backward in tensor memory) --------------
-@pytest.fixture
-def tc2_engine(monkeypatch):
-    monkeypatch.setenv("MMN_ENGINE", "tc2")
-
-
-@pytest.mark.parametrize("name", TC_CASES)
-def test_oracle_case_tmem_resident_train(tc2_engine, name):
-    model = run_parity_case(name, DEV)
-    from multimodn_b200 import _lib
-    assert _lib.get_lib().dll.mmn_plan_engine(model.runtime().plan) == 2
-
-
-@pytest.mark.parametrize("name,names,mode", [("c2_mimic_full", ["a", "b"], "row"), ("c2_mimic_small", ["a", "b"], "batch"),
-                                             ("missing_row", ["a", "b"], "row")])
-def test_golden_tmem_resident_train(tc2_engine, name, names, mode):
-    run_golden(name, names, mode, check_predict=name != "missing_row")
-
-
-def test_golden_c1_titanic_two_epochs_tmem_resident(tc2_engine):
-    test_golden_c1_titanic_two_epochs("fused_adam")
-
-
+# ---- engines of fp32 plans: the FP32-FMA kernel trains; forward-only launches use the TMEM-resident tcgen05 kernel -----
 def test_default_engine_is_fma():
     from multimodn_b200 import _lib
     fx = load_golden("c2_mimic_full")
