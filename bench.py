@@ -315,7 +315,7 @@ def run_reference(args, w):
             line["cpu_baseline"]["ref_asis"] = cpu_asis_rate(w, args.asis_rows, max_seconds=30.0)
         except Exception as exc:  # noqa: BLE001
             line["cpu_baseline"]["ref_asis"] = dict(error=f"{type(exc).__name__}: {exc}")
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(w, B, world, **extra):
@@ -577,7 +577,27 @@ class Bench:
 TRAFFIC = {("c2_mimic", "fp32-fma"): 709.7e6 + 252.2e6}
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1 at the
+    first communicator), so fd 1 is pointed at stderr for the whole run and the line goes to a saved copy of the real one."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -680,7 +700,7 @@ def main():
             line["dp_parity"] = parity
         if configs:
             line["configs"] = configs
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -268,6 +268,21 @@ class _Runtime:
             raise IndexError("Target out of bounds: a target lies outside [0, n_classes) of its decoder "
                              "(ignore_index = -100 is not supported by the fused step)")
 
+    def read_back_async(self, metrics: Tensor, tag):
+        """device metrics -> one of two alternating pinned host buffers, without blocking the host; returns
+        (tag, host tensor, event to wait for) — (tag, tensor, None) on a host-memory library"""
+        if self.device.type != "cuda":
+            return tag, metrics.clone(), None
+        if not hasattr(self, "_rb"):
+            self._rb = [torch.empty(self.n_metrics, dtype=torch.float64).pin_memory() for _ in range(2)]
+            self._rb_i = 0
+        host = self._rb[self._rb_i]
+        self._rb_i ^= 1
+        host.copy_(metrics, non_blocking=True)
+        event = torch.cuda.Event()
+        event.record(torch.cuda.current_stream(self.device))
+        return tag, host, event
+
     def assign_grads(self):
         """loss.backward() epilogue (multimodn.py:203): hand each parameter a view of the packed
         gradient; an encoder that took no row keeps ``.grad = None`` (multimodn.py:168-169)."""
@@ -478,6 +493,21 @@ class MultiModN(nn.Module):
         batch_metrics = rt.new_metrics() if log_interval else None
         E, D = rt.E, rt.D
 
+        pending_log = None
+
+        def emit_log(entry):
+            idx, host, event = entry
+            if event is not None:
+                event.synchronize()
+            mats, _, sc = rt.split_metrics(host.numpy())
+            err = mats[0].sum() / (D * (E + 1))                      # :194-196
+            chg = sc.sum() / E
+            loss = err * self.err_penalty + chg * self.state_change_penalty
+            logger(f"Batch {idx + 1}/{n_batches}\n"
+                   f"\tLoss: {loss:.4f}\n"
+                   f"\tErr loss: {err:.4f}\n"
+                   f"\tState change: {chg:.4f}")
+
         for batch_idx, (data, target, encoder_sequence) in enumerate(rt.staged(train_loader)):
             seq = self.get_encoder_iterable(encoder_sequence, shuffle_mode=self.shuffle_mode, train=True)
             optimizer.zero_grad()
@@ -497,16 +527,17 @@ class MultiModN(nn.Module):
             if batch_metrics is not None:
                 epoch_metrics += batch_metrics
                 if batch_idx % log_interval == log_interval - 1:
+                    # multimodn.py:214-220.  The batch's loss is read back asynchronously (pinned buffer + event) and the
+                    # line is emitted once the NEXT batch has been enqueued: same lines, same order, but the device never
+                    # idles behind a host round trip per logged batch
                     bm = batch_metrics.clone()
                     self._allreduce(bm)
-                    mats, _, sc = rt.split_metrics(bm.cpu().numpy())
-                    err = mats[0].sum() / (D * (E + 1))                      # :194-196
-                    chg = sc.sum() / E
-                    loss = err * self.err_penalty + chg * self.state_change_penalty
-                    logger(f"Batch {batch_idx + 1}/{n_batches}\n"
-                           f"\tLoss: {loss:.4f}\n"
-                           f"\tErr loss: {err:.4f}\n"
-                           f"\tState change: {chg:.4f}")
+                    entry = rt.read_back_async(bm, batch_idx)
+                    if pending_log is not None:
+                        emit_log(pending_log)
+                    pending_log = entry
+        if pending_log is not None:
+            emit_log(pending_log)
 
         self._dp_close_epoch(rt)
         if history is not None:
