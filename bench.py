@@ -455,7 +455,9 @@ class Bench:
             # side stream) and reads its loss metrics back D2H (log_interval = 1)
             host = [make_batch(w, B, 500 + 17 * self.rank + i, pin=True) for i in range(3)]
             hist = MultiModNHistory([str(d) for d in range(w["n_decoders"])])
-            Ke = e2e_steps or max(3, min(K, 12))
+            # enough steps that the first batch's un-overlapped H2D copy (one batch ahead is all the staging can hide) is
+            # amortised: ~150 ms of steps, at least min(K, 12), at most 40
+            Ke = e2e_steps or int(min(40, max(3, min(K, 12), 150.0 / max(ms / K, 1e-3))))
             logged = []
 
             def epoch_e2e(n):
