@@ -610,7 +610,13 @@ class MultiModN(nn.Module):
         preds = torch.zeros((rt.E + 1, rt.D, n_rows), dtype=torch.uint8, device=rt.device)
         rt.forward(mb, n_rows, predictions=preds)
         del keep
-        return preds.cpu().numpy().astype(np.float64)
+        if rt.device.type != "cuda":
+            return preds.numpy().astype(np.float64)
+        # the reference returns float64 class ids (multimodn.py:429-430): widen on the device and land in pinned host
+        # memory (torch caches the pinned block), instead of a single-threaded astype over (E+1) D N values on the host
+        host = torch.empty(preds.shape, dtype=torch.float64, pin_memory=True)
+        host.copy_(preds.to(torch.float64))
+        return host.numpy()
 
     def get_states(self, data_loader: DataLoader) -> List[Tensor]:
         """multimodn.py:460-492"""
