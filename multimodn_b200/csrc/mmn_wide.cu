@@ -250,6 +250,48 @@ int mmn_wide_plan_init(mmn_plan* p) {
 }
 
 namespace {
+bool ptr16(const void* p) { return (reinterpret_cast<size_t>(p) & 15) == 0; }
+
+// decoder head, forward: picks the class-count instantiation and the straight-line variant when every row is 16-byte aligned
+template <int C>
+void launch_head_fwd_c(bool fast, unsigned grid, cudaStream_t st, const wide::Mat& h, const wide::bf16* Wb, long long ldk, const float* bias,
+                       int act, long long rows, float* p_out) {
+  if (fast) wide::wide_head_fwd_kernel<C, true><<<grid, 256, 0, st>>>(h, Wb, ldk, bias, act, rows, p_out);
+  else wide::wide_head_fwd_kernel<C, false><<<grid, 256, 0, st>>>(h, Wb, ldk, bias, act, rows, p_out);
+}
+void launch_head_fwd(int C, int n_sms, cudaStream_t st, const wide::Mat& h, const wide::bf16* Wb, long long ldk, const float* bias, int act,
+                     long long rows, float* p_out) {
+  const bool fast = ptr16(h.p) && ptr16(Wb) && (h.ld & 7) == 0 && (ldk & 7) == 0 && (h.width & 7) == 0;
+  const long long per_cta = 8 * wide::kHeadRows;
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((rows + per_cta - 1) / per_cta, 8ll * n_sms));
+  switch (C) {
+    case 1: launch_head_fwd_c<1>(fast, grid, st, h, Wb, ldk, bias, act, rows, p_out); break;
+    case 2: launch_head_fwd_c<2>(fast, grid, st, h, Wb, ldk, bias, act, rows, p_out); break;
+    case 3: launch_head_fwd_c<3>(fast, grid, st, h, Wb, ldk, bias, act, rows, p_out); break;
+    default: launch_head_fwd_c<4>(fast, grid, st, h, Wb, ldk, bias, act, rows, p_out); break;
+  }
+}
+template <int C>
+void launch_head_backward_c(bool fast, dim3 grid, cudaStream_t st, const wide::Mat& dz, const wide::Mat& h, long long rows, float* gW,
+                            long long ldw, float* gb, const wide::bf16* Wb, long long ldk, int act_prev, const wide::Mat& out) {
+  if (fast) wide::wide_head_backward_kernel<C, true><<<grid, 256, 0, st>>>(dz, h, rows, gW, ldw, gb, Wb, ldk, act_prev, out);
+  else wide::wide_head_backward_kernel<C, false><<<grid, 256, 0, st>>>(dz, h, rows, gW, ldw, gb, Wb, ldk, act_prev, out);
+}
+void launch_head_backward(int C, int n_sms, cudaStream_t st, const wide::Mat& dz, const wide::Mat& h, long long rows, float* gW, long long ldw,
+                          float* gb, const wide::bf16* Wb, long long ldk, int act_prev, const wide::Mat& out) {
+  const bool fast = ptr16(h.p) && ptr16(out.p) && ptr16(dz.p) && (h.ld & 7) == 0 && (out.ld & 7) == 0 && (dz.ld & 3) == 0 &&
+                    (h.width & 7) == 0;
+  // one wave: every CTA resident at once (kHeadBwdCtas per SM), each streaming its slice of the rows
+  const long long gx = (h.width + 2047) / 2048;
+  const dim3 grid((unsigned)gx, (unsigned)std::max<long long>(1, std::min<long long>((long long)wide::kHeadBwdCtas(C) * n_sms / gx, rows / 16)));
+  switch (C) {
+    case 1: launch_head_backward_c<1>(fast, grid, st, dz, h, rows, gW, ldw, gb, Wb, ldk, act_prev, out); break;
+    case 2: launch_head_backward_c<2>(fast, grid, st, dz, h, rows, gW, ldw, gb, Wb, ldk, act_prev, out); break;
+    case 3: launch_head_backward_c<3>(fast, grid, st, dz, h, rows, gW, ldw, gb, Wb, ldk, act_prev, out); break;
+    default: launch_head_backward_c<4>(fast, grid, st, dz, h, rows, gW, ldw, gb, Wb, ldk, act_prev, out); break;
+  }
+}
+
 // The whole step.  dry = true only sizes the workspace (no launches).
 template <bool TRAIN>
 int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes, void* stream_, bool dry, size_t* need_out) {
@@ -376,8 +418,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
         if (!dry) {
           if (last && j > 0 && dec.C <= 4) {   // decoder head: skinny, bandwidth-bound kernel instead of a tensor-core tile
             g_wt.begin("head_fwd");
-            wide_head_fwd_kernel<4><<<(unsigned)std::min<long long>((B + 7) / 8, 8 * n_sms), 256, 0, ds>>>(
-                in, wbase + w.w, w.ldk, a.params + ly.b_off, dec.C, ly.act, B, Pout);
+            launch_head_fwd(dec.C, n_sms, ds, in, wbase + w.w, w.ldk, a.params + ly.b_off, ly.act, B, Pout);
             if (launched()) return 1;
           } else if (wide_gemm(n_sms, in.p, in.ld, wbase + w.w, w.ldk, B, ly.out_dim, ly.ktot, e, ds, "gemm fwd")) {
             return 1;
@@ -568,9 +609,8 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
           const Mat nz = j == 1 ? dz0[(size_t)k * D + d] : (j > 1 ? view(dzdec[cur], ly.in_dim) : Mat());
           if (j == dec.n_layers - 1 && j > 0 && dec.C <= 4) {       // decoder head (see decoders_forward)
             g_wt.begin("head_backward");
-            wide_head_backward_kernel<4><<<dim3((unsigned)((ly.in_dim + 2047) / 2048), (unsigned)std::max<long long>(1, std::min<long long>(4 * n_sms, B / 16))),
-                                           256, 0, dstream>>>(dz, in, dec.C, B, a.grads + ly.w_off, ly.ktot, a.grads + ly.b_off,
-                                                              wbase + w.w, w.ldk, dec.L[j - 1].act, nz);
+            launch_head_backward(dec.C, n_sms, dstream, dz, in, B, a.grads + ly.w_off, ly.ktot, a.grads + ly.b_off, wbase + w.w, w.ldk,
+                                 dec.L[j - 1].act, nz);
             if (launched()) return 1;
             dz = nz;
             cur ^= 1;

@@ -36,6 +36,14 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   for (int i = 0; i < 4; ++i) hp[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
   return u;
 }
+// 16-byte read-only load the compiler cannot split or fence behind a branch (the streaming kernels below issue several per
+// thread before the first use)
+__device__ __forceinline__ uint4 ldg16(const void* p) {
+  uint4 v;
+  asm("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<size_t>(p) & 15) == 0; }
 __device__ __forceinline__ void load8(const bf16* p, int n_valid, float (&f)[8]) {      // 8 bf16, zero beyond n_valid
   if (n_valid >= 8 && (reinterpret_cast<size_t>(p) & 15) == 0) {
     unpack8(*reinterpret_cast<const uint4*>(p), f);
@@ -183,8 +191,23 @@ __global__ void __launch_bounds__(256) wide_bias_grad_kernel(const bf16* __restr
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   if (n0 < n_out) {
-#pragma unroll 4
-    for (long long r = r0 + rl; r < r1; r += 32) {
+    long long r = r0 + rl;
+    if (n0 + 8 <= n_out && aligned16(dz + n0) && (ld & 7) == 0) {     // straight-line: 8 loads in flight per thread
+      const bf16* src = dz + n0;
+      for (; r + 7 * 32 < r1; r += 8 * 32) {
+        uint4 u[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) u[j] = ldg16(src + (r + 32 * j) * ld);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v[8];
+          unpack8(u[j], v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += v[i];
+        }
+      }
+    }
+    for (; r < r1; r += 32) {
       float v[8];
       load8(dz + r * ld + n0, n_out - n0, v);
 #pragma unroll
@@ -230,95 +253,156 @@ __global__ void wide_state_out_kernel(Mat s, long long rows, float* out) {
 
 // ---- decoder head: the last Linear of an MLP decoder (out = n_classes <= 32) is far too skinny for a 128 x 256 tensor-core
 // tile; two bandwidth-bound kernels replace its forward and its backward (data + weight gradient) GEMMs ----
-// p[r][c] = act(b[c] + sum_k h[r][k] W[c][k])       one warp per row, fp32 accumulation of bf16 products
-template <int CMAX>
+// p[r][c] = act(b[c] + sum_k h[r][k] W[c][k])       fp32 accumulation of bf16 products.
+// A warp owns kHeadRows consecutive rows at a time and strides over k 256 columns per trip, so each weight chunk is fetched
+// once per kHeadRows rows and kHeadRows 16-byte loads of h are in flight per lane and trip (x2 with the unroll).
+// fast = every row of h and W starts 16-byte aligned and the width is a multiple of 8 (checked by the launcher).
+constexpr int kHeadRows = 4;
+template <int C, bool FAST>
 __global__ void __launch_bounds__(256) wide_head_fwd_kernel(Mat h, const bf16* __restrict__ Wb, long long ldk, const float* __restrict__ bias,
-                                                            int C, int act, long long rows, float* __restrict__ p_out) {
+                                                            int act, long long rows, float* __restrict__ p_out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (long long r = (long long)blockIdx.x * 8 + warp; r < rows; r += (long long)gridDim.x * 8) {
-    float acc[CMAX];
+  for (long long rb = ((long long)blockIdx.x * 8 + warp) * kHeadRows; rb < rows; rb += (long long)gridDim.x * 8 * kHeadRows) {
+    float acc[kHeadRows][C];
+    const bf16* hr[kHeadRows];
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c) acc[c] = 0.f;
-    const bf16* hr = h.p + r * h.ld;
-#pragma unroll 4
-    for (int k0 = lane * 8; k0 < h.width; k0 += 256) {
-      float hv[8];
-      load8(hr + k0, h.width - k0, hv);
+    for (int q = 0; q < kHeadRows; ++q) {
+      hr[q] = h.p + min(rb + q, rows - 1) * h.ld;      // rows past the end re-read the last one; their result is dropped
 #pragma unroll
-      for (int c = 0; c < CMAX; ++c) {
-        if (c < C) {
+      for (int c = 0; c < C; ++c) acc[q][c] = 0.f;
+    }
+    if (FAST) {
+#pragma unroll 2
+      for (int k0 = lane * 8; k0 < h.width; k0 += 256) {
+        uint4 hu[kHeadRows], wu[C];
+#pragma unroll
+        for (int q = 0; q < kHeadRows; ++q) hu[q] = ldg16(hr[q] + k0);
+#pragma unroll
+        for (int c = 0; c < C; ++c) wu[c] = ldg16(Wb + (long long)c * ldk + k0);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          float wv[8];
+          unpack8(wu[c], wv);
+#pragma unroll
+          for (int q = 0; q < kHeadRows; ++q) {
+            float hv[8];
+            unpack8(hu[q], hv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[q][c] = fmaf(hv[i], wv[i], acc[q][c]);
+          }
+        }
+      }
+    } else {
+      for (int k0 = lane * 8; k0 < h.width; k0 += 256) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
           float wv[8];
           load8(Wb + (long long)c * ldk + k0, h.width - k0, wv);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[c] = fmaf(hv[i], wv[i], acc[c]);
+          for (int q = 0; q < kHeadRows; ++q) {
+            float hv[8];
+            load8(hr[q] + k0, h.width - k0, hv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[q][c] = fmaf(hv[i], wv[i], acc[q][c]);
+          }
         }
       }
     }
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c) {
-      if (c < C) {
-        float s = acc[c];
+    for (int q = 0; q < kHeadRows; ++q) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float s = acc[q][c];
 #pragma unroll
         for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) p_out[r * C + c] = wide_act(act, s + bias[c]);
+        if (lane == 0 && rb + q < rows) p_out[(rb + q) * C + c] = wide_act(act, s + bias[c]);
       }
     }
   }
 }
 // The head's whole backward in one pass over its input h:  dW[c][k] += sum_r dz[r][c] h[r][k],  db[c] += sum_r dz[r][c]  and
-// dh[r][k] = act'(h[r][k]) * sum_c dz[r][c] W[c][k].   thread = 8 consecutive k, blockIdx.y = a slice of the rows
-template <int CMAX>
-__global__ void __launch_bounds__(256) wide_head_backward_kernel(Mat dz, Mat h, int C, long long rows, float* gW, long long ldw, float* gb,
-                                                                 const bf16* __restrict__ Wb, long long ldk, int act_prev, Mat out) {
+// dh[r][k] = act'(h[r][k]) * sum_c dz[r][c] W[c][k].   thread = 8 consecutive k, blockIdx.y = a slice of the rows.
+// fast (see above, plus dz and dh rows 16-byte aligned): four rows of h in flight per thread, one 8-byte load of a dz row.
+constexpr int kHeadBwdCtas(int C) { return C <= 2 ? 3 : 2; }      // resident CTAs per SM the register budget is set for
+template <int C> struct DzWord { typedef uint2 type; };      // one row of dz (C <= 4 bf16) in one load
+template <> struct DzWord<1> { typedef unsigned type; };
+template <> struct DzWord<2> { typedef unsigned type; };
+template <int C, bool FAST>
+__global__ void __launch_bounds__(256, kHeadBwdCtas(C)) wide_head_backward_kernel(Mat dz, Mat h, long long rows, float* gW, long long ldw, float* gb,
+                                                                    const bf16* __restrict__ Wb, long long ldk, int act_prev, Mat out) {
   const int k0 = (blockIdx.x * 256 + threadIdx.x) * 8;
   const long long per = (rows + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
-  float acc[CMAX][8], wv[CMAX][8];
+  float acc[C][8], wv[C][8];
 #pragma unroll
-  for (int c = 0; c < CMAX; ++c) {
+  for (int c = 0; c < C; ++c) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[c][i] = wv[c][i] = 0.f;
-    if (c < C && k0 < h.width) load8(Wb + (long long)c * ldk + k0, h.width - k0, wv[c]);
+    if (k0 < h.width) load8(Wb + (long long)c * ldk + k0, h.width - k0, wv[c]);
   }
   if (k0 < h.width) {
     const int nv = min(8, h.width - k0);
-#pragma unroll 4
-    for (long long r = r0; r < r1; ++r) {
-      float hv[8], dh[8];
-      load8(h.p + r * h.ld + k0, nv, hv);
+    // one row: dh and the weight-gradient partial sums
+    auto row = [&](long long r, const float (&hv)[8], const float (&d)[C]) {
+      float dh[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) dh[i] = 0.f;
 #pragma unroll
-      for (int c = 0; c < CMAX; ++c) {
-        if (c < C) {
-          const float d = __bfloat162float(dz.p[r * dz.ld + c]);
+      for (int c = 0; c < C; ++c) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            acc[c][i] = fmaf(d, hv[i], acc[c][i]);
-            dh[i] = fmaf(d, wv[c][i], dh[i]);
-          }
+        for (int i = 0; i < 8; ++i) {
+          acc[c][i] = fmaf(d[c], hv[i], acc[c][i]);
+          dh[i] = fmaf(d[c], wv[c][i], dh[i]);
         }
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) dh[i] *= wide_dact(act_prev, hv[i]);
       bf16* op = out.p + r * out.ld + k0;
-      if (nv == 8 && (reinterpret_cast<size_t>(op) & 15) == 0) {
+      if (FAST) {
+        *reinterpret_cast<uint4*>(op) = pack8(dh);
+      } else if (nv == 8 && aligned16(op)) {
         *reinterpret_cast<uint4*>(op) = pack8(dh);
       } else {
         for (int i = 0; i < nv; ++i) op[i] = __float2bfloat16(dh[i]);
       }
+    };
+    long long r = r0;
+    if (FAST) {
+      for (; r + 4 <= r1; r += 4) {
+        uint4 hu[4];
+        typename DzWord<C>::type du[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          hu[j] = ldg16(h.p + (r + j) * h.ld + k0);
+          du[j] = *reinterpret_cast<const typename DzWord<C>::type*>(dz.p + (r + j) * dz.ld);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float hv[8], d[C];
+          unpack8(hu[j], hv);
+          const bf16* dp = reinterpret_cast<const bf16*>(&du[j]);
+#pragma unroll
+          for (int c = 0; c < C; ++c) d[c] = __bfloat162float(dp[c]);
+          row(r + j, hv, d);
+        }
+      }
+    }
+    for (; r < r1; ++r) {
+      float hv[8], d[C];
+      load8(h.p + r * h.ld + k0, nv, hv);
+#pragma unroll
+      for (int c = 0; c < C; ++c) d[c] = __bfloat162float(dz.p[r * dz.ld + c]);
+      row(r, hv, d);
     }
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c) {
-      if (c < C) {
-        float* dst = gW + (long long)c * ldw + k0;
-        if (k0 + 8 <= h.width && (reinterpret_cast<size_t>(dst) & 15) == 0) {      // two red.global.add.v4.f32
-          atomicAdd(reinterpret_cast<float4*>(dst), make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]));
-          atomicAdd(reinterpret_cast<float4*>(dst) + 1, make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]));
-        } else {
+    for (int c = 0; c < C; ++c) {
+      float* dst = gW + (long long)c * ldw + k0;
+      if (k0 + 8 <= h.width && aligned16(dst)) {      // two red.global.add.v4.f32
+        atomicAdd(reinterpret_cast<float4*>(dst), make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]));
+        atomicAdd(reinterpret_cast<float4*>(dst) + 1, make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]));
+      } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (k0 + i < h.width && acc[c][i] != 0.f) atomicAdd(dst + i, acc[c][i]);
-        }
+        for (int i = 0; i < 8; ++i)
+          if (k0 + i < h.width && acc[c][i] != 0.f) atomicAdd(dst + i, acc[c][i]);
       }
     }
   }
