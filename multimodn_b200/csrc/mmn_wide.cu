@@ -1,6 +1,9 @@
 // mmn_wide.cu — translation unit of the wide regime (precision = bf16): tensor maps, the tcgen05 bf16 GEMM launcher and the
 // layer-wise step orchestration (mmn_wide.cuh, mmn_wide_step.cuh).  CUDA only: not part of the host emulator.
 #include "mmn_kernels.cuh"
+#include <set>
+#include <string>
+
 #include "mmn_wide_step.cuh"
 #include "mmn_host.h"
 
@@ -101,6 +104,12 @@ WideTimers g_wt;
 int wide_gemm(int n_sms, const void* A, long long lda, const void* B, long long ldb, long long M, long long N, long long K,
               const wide::Epi& epi, void* stream, const char* what = "gemm", int a_mn = 0, int b_mn = 0) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (g_wt.on) {       // timers: one category per GEMM kind, epilogue mode and shape
+    static std::set<std::string> names;
+    char buf[128];
+    snprintf(buf, sizeof buf, "%s[epi %d%s %lldx%lldx%lld]", what, epi.mode, epi.accumulate ? "+" : "", M, N, K);
+    what = names.insert(buf).first->c_str();
+  }
   alignas(64) CUtensorMap ma, mb, mb_half;
   if (a_mn ? make_operand_map_mn(&ma, A, M, K, lda) : make_operand_map(&ma, A, M, K, lda, wide::BM)) return 1;
   if (b_mn ? make_operand_map_mn(&mb, B, N, K, ldb) : make_operand_map(&mb, B, N, K, ldb, wide::BN)) return 1;

@@ -27,7 +27,8 @@ namespace wide {
 constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
 constexpr int kThreads = 384;          // warps 0-2: TMA / MMA / TMEM allocator; warps 4-11: epilogue
 constexpr int kStageBytes = (BM + BN) * BK * 2;                  // 48 KB
-constexpr int kSmemBytes = STAGES * kStageBytes + 1024 + 256;      // + alignment slack + barriers
+constexpr int kBiasStageBytes = 2 * BN * 4;                      // the epilogue's bias slice of a tile, double-buffered
+constexpr int kSmemBytes = STAGES * kStageBytes + 1024 + 256 + kBiasStageBytes;      // + alignment slack + barriers + bias
 
 enum {
   EPI_STORE = 0,       // out = act(acc + bias)                                   (forward hidden / decoder layers)
@@ -162,6 +163,7 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   unsigned long long* acc_full = empty + NSTG;      // [2]
   unsigned long long* acc_empty = acc_full + 2;       // [2]
   unsigned* tslot = reinterpret_cast<unsigned*>(acc_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(base + NSTG * STG + 256);      // [2][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned pair_rank = PAIR ? cluster_ctarank() : 0u;
@@ -321,13 +323,59 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       const int cols = nhalf < 0 ? BN : tail_w;          // accumulator columns of this item; each warp pair splits them
       const int r = m0 + 32 * q + lane;
       const bool rv = r < M;
-      mbar_wait(acc_full + acc, acc_phase[acc]);
-      acc_phase[acc] ^= 1u;
-      tc_fence_after();
       const bool skipped = epi.skip && *epi.skip != 0;
       const bool pres = ((epi.present && rv) ? epi.present[r] != 0 : true) && !skipped;
       const bool pair_ok = (r | 1) < M;                // rows r and r ^ 1 both exist: packed transposed stores
-      for (int c0 = half * (cols / 2); c0 < (half + 1) * (cols / 2); c0 += 16) {
+      const int c_beg = half * (cols / 2), c_end = (half + 1) * (cols / 2);
+      // fast paths of the row-wise operands the epilogue reads (16 columns = two 16-byte loads per iteration)
+      const bool aux_fast = epi.aux && rv && (epi.ld_aux & 7) == 0 && (reinterpret_cast<size_t>(epi.aux) & 15) == 0 && (n0 & 7) == 0;
+      const bool old_fast = epi.out_f32 && rv && epi.mode == EPI_ACCUM_F32 && epi.accumulate && splits == 1 && (epi.ld_f32 & 3) == 0 &&
+                            (reinterpret_cast<size_t>(epi.out_f32) & 15) == 0 && (n0 & 3) == 0;
+      uint4 aq0 = make_uint4(0, 0, 0, 0), aq1 = aq0;                       // aux of the iteration about to run, fetched one ahead
+      float4 oq[4] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f),
+                      make_float4(0.f, 0.f, 0.f, 0.f)};                   // old fp32 output, likewise
+      auto fetch = [&](int c0) {
+        const int n = n0 + c0;
+        if (n + 16 > N) return;
+        if (aux_fast) {
+          const uint4* ap = reinterpret_cast<const uint4*>(epi.aux + (long long)r * epi.ld_aux + n);
+          aq0 = ap[0]; aq1 = ap[1];
+        }
+        if (old_fast) {
+          const float4* op4 = reinterpret_cast<const float4*>(epi.out_f32 + (long long)r * epi.ld_f32 + n);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) oq[i] = op4[i];
+        }
+      };
+      // While the tensor cores still work on this tile: the tile's bias slice -> shared memory, the lines of the row-wise
+      // operands -> L2 (they were written a whole pass ago and sit in DRAM), and the first iteration's operands -> registers
+      if (epi.bias) {
+        const int e_tid = (int)threadIdx.x - 128, nb = n0 + e_tid;
+        bias_s[(it & 1) * BN + e_tid] = nb < N ? __ldg(epi.bias + nb) : 0.f;
+      }
+      if (rv && n0 + c_beg < N) {
+        const int n_pf = min(c_end, N - n0) - c_beg;
+        auto l2_prefetch = [&](const char* ptr, int bytes) {
+          for (int o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + o));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + bytes - 1));
+        };
+        if (epi.aux) l2_prefetch(reinterpret_cast<const char*>(epi.aux + (long long)r * epi.ld_aux + n0 + c_beg), n_pf * 2);
+        if (epi.aux2) l2_prefetch(reinterpret_cast<const char*>(epi.aux2 + (long long)r * epi.ld_aux2 + n0 + c_beg), n_pf * 2);
+        if (epi.out_f32 && splits == 1 && (epi.accumulate || epi.mode == EPI_CARRY))
+          l2_prefetch(reinterpret_cast<const char*>(epi.out_f32 + (long long)r * epi.ld_f32 + n0 + c_beg), n_pf * 4);
+      }
+      if (epi.bias) asm volatile("bar.sync 1, 256;" ::: "memory");        // the 8 epilogue warps: bias slice complete
+      const float* bias_t = bias_s + (it & 1) * BN;
+      fetch(c_beg);
+      mbar_wait(acc_full + acc, acc_phase[acc]);
+      acc_phase[acc] ^= 1u;
+      tc_fence_after();
+      for (int c0 = c_beg; c0 < c_end; c0 += 16) {
+        const uint4 a0 = aq0, a1 = aq1;
+        float4 old4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) old4[i] = oq[i];
+        if (c0 + 16 < c_end) fetch(c0 + 16);
         float v[16];
         tmem_ld16(tmem + ((unsigned)(32 * q) << 16) + acc * BN + c0, v);     // warp-collective: outside every branch
         const int n = n0 + c0;
@@ -336,8 +384,7 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         float aux[16];
         if (epi.aux && rv) {
           const __nv_bfloat16* ap = epi.aux + (long long)r * epi.ld_aux + n;
-          if (full16 && ((epi.ld_aux & 7) == 0)) {
-            const uint4 a0 = *reinterpret_cast<const uint4*>(ap), a1 = *reinterpret_cast<const uint4*>(ap + 8);
+          if (full16 && aux_fast) {
             const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&a0);
             const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&a1);
 #pragma unroll
@@ -355,15 +402,10 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         }
         if (epi.mode == EPI_STORE || epi.mode == EPI_SELECT) {
           if (epi.bias) {
-            if (full16 && ((reinterpret_cast<size_t>(epi.bias) & 15) == 0)) {
 #pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(epi.bias + n + i));
-                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += n + i < N ? __ldg(epi.bias + n + i) : 0.f;
+            for (int i = 0; i < 16; i += 4) {
+              const float4 b = *reinterpret_cast<const float4*>(bias_t + c0 + i);
+              v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
             }
           }
           if (epi.act == MMN_ACT_RELU) {
@@ -453,7 +495,7 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             for (int i = 0; i < 16; i += 4) {
               float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
               if (epi.accumulate) {
-                const float4 old = *reinterpret_cast<const float4*>(op + i);
+                const float4 old = old_fast ? old4[i / 4] : *reinterpret_cast<const float4*>(op + i);
                 o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
               }
               *reinterpret_cast<float4*>(op + i) = o;
