@@ -102,8 +102,18 @@ WideTimers g_wt;
 // D[M x N] = A[M x K] . B[N x K]^T
 // a_mn / b_mn = 0: the operand is [M or N rows x K] with K contiguous.  = 1: it is [K rows x M or N] with M / N contiguous.
 int wide_gemm(int n_sms, const void* A, long long lda, const void* B, long long ldb, long long M, long long N, long long K,
-              const wide::Epi& epi, void* stream, const char* what = "gemm", int a_mn = 0, int b_mn = 0) {
+              const wide::Epi& epi_in, void* stream, const char* what = "gemm", int a_mn = 0, int b_mn = 0) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
+  // MMN_WIDE_EPI_DEBUG (development aid, results are wrong): none = drop the accumulators, nostore = compute but do not store
+  static const int epi_debug = [] {
+    const char* v = getenv("MMN_WIDE_EPI_DEBUG");
+    return !v ? 0 : (!strcmp(v, "none") ? 1 : (!strcmp(v, "nostore") ? 2 : (!strcmp(v, "ldonly") ? 3 : (!strcmp(v, "aluonly") ? 4 : 0))));
+  }();
+  wide::Epi epi = epi_in;
+  if (epi_debug == 1) epi.mode = wide::EPI_NONE;
+  if (epi_debug == 3) epi.mode = wide::EPI_NONE + 1;
+  if (epi_debug == 4) epi.mode = wide::EPI_NONE + 2;
+  if (epi_debug == 2) { epi.out = nullptr; epi.out_t = nullptr; epi.out_f32 = nullptr; }
   if (g_wt.on) {       // timers: one category per GEMM kind, epilogue mode and shape
     static std::set<std::string> names;
     char buf[128];
@@ -146,7 +156,8 @@ int wide_gemm(int n_sms, const void* A, long long lda, const void* B, long long 
     double best = 1.0;
     for (int s = 2; s <= 16 && kb / s >= 16; ++s) {
       if ((long long)(s - 1) * ((kb + s - 1) / s) >= kb) continue;                 // no empty split
-      const double cost = (double)((n_tiles * s + n_units - 1) / n_units) / s + 0.03 * (s - 1);
+      // + the extra fp32 atomic passes over the output, measured ~3 % of a K = 8192 tile each
+      const double cost = (double)((n_tiles * s + n_units - 1) / n_units) / s + 0.03 * (s - 1) * 128.0 / (double)kb;
       if (cost < best - 1e-9) { best = cost; best_s = s; }
     }
     return best_s;
@@ -368,18 +379,28 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
   }
   for (int e = 0; e < E; ++e)
     for (int j = 0; j < P.enc[e].n_layers; ++j) maxW = std::max(maxW, P.enc[e].L[j].out_dim);
-  float* Pout = (float*)ar.take(sizeof(float) * (size_t)B * maxC);
+  // Training runs every decoder ONCE over the states of all steps: s_0 .. s_L are the row blocks of one [(L + 1) B x S]
+  // matrix, so each decoder layer is a single GEMM with (L + 1) B rows instead of L + 1 launches that each leave a
+  // partial last wave and pay their own prologue (decoders_forward_all / decoders_backward_all below).
+  const long long R = (long long)(L + 1) * B;
+  float* Pout = (float*)ar.take(sizeof(float) * (size_t)(TRAIN ? R : B) * maxC);
+  auto rows_of = [](const Mat& m, long long r0) {      // the row block starting at r0 (row-major orientation only)
+    Mat v = m;
+    v.p = m.p ? m.p + r0 * m.ld : nullptr;
+    v.t = nullptr;
+    return v;
+  };
   std::vector<Mat> Sk(L + 1);
+  Mat Sall = Mat();
   if (TRAIN) {
-    for (int k = 0; k <= L; ++k) Sk[k] = ar.mat(B, S);
+    Sall = ar.mat(R, S);
+    for (int k = 0; k <= L; ++k) Sk[k] = rows_of(Sall, (long long)k * B);
   } else {
     const Mat s0 = ar.mat(B, S), s1 = ar.mat(B, S);
     for (int k = 0; k <= L; ++k) Sk[k] = (k & 1) ? s1 : s0;
   }
   // per (step, module, layer) activations kept for the backward pass
   std::vector<Mat> enc_in((size_t)(L + 1) * MMN_MAX_LAYERS);
-  std::vector<Mat> dec_h((size_t)(L + 1) * D * MMN_MAX_LAYERS);
-  std::vector<Mat> dec_dz((size_t)(L + 1) * D);
   if (!dry) {
     MMN_CUDA(cudaMemsetAsync(present, 1, (size_t)(L + 1) * B, stream));
     MMN_CUDA(cudaMemsetAsync(sc_sum, 0, sizeof(float) * (size_t)std::max(E, 1), stream));
@@ -396,17 +417,9 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
     return e;
   };
 
-  // ---- decoders on s_k ----
-  // Training: the decoders of step k only need s_k, and so does the encoder of step k + 1 — the decoder chains run on the
-  // plan's side stream (forked after s_k is final, joined before the backward pass) next to the following encoder's GEMMs,
-  // which fills the tails of both and hides the small head / loss kernels.
-  const bool fwd_side = TRAIN && !dry && plan->side_stream && !g_wt.on;
-  const cudaStream_t ds = fwd_side ? (cudaStream_t)plan->side_stream : stream;
+  // ---- decoders on s_k, one step at a time (forward-only calls: the states are not kept) ----
+  const cudaStream_t ds = stream;
   auto decoders_forward = [&](int k, int hist_row, bool is_last_enc, const int* skip) -> int {
-    if (fwd_side) {
-      MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->side_fork, stream));
-      MMN_CUDA(cudaStreamWaitEvent(ds, (cudaEvent_t)plan->side_fork, 0));
-    }
     for (int d = 0; d < D; ++d) {
       const DevDecoder& dec = P.dec[d];
       Mat in = Sk[k];
@@ -419,8 +432,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
         Mat out;
         if (!last) {
           out = ar.mat(B, ly.out_dim);
-          dec_h[((size_t)k * D + d) * MMN_MAX_LAYERS + j] = out;
-          e.out = out.p; e.ld_out = out.ld; e.out_t = out.t; e.ld_out_t = out.ldt;
+          e.out = out.p; e.ld_out = out.ld;
         } else {
           e.out_f32 = Pout; e.ld_f32 = dec.C;
         }
@@ -444,15 +456,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
       la.metrics = a.metrics; la.inv_rows_global = a.inv_rows_global;
       la.predictions = a.predictions ? a.predictions + ((long long)hist_row * D + d) * a.pred_ld : nullptr;
       if (a.last_outputs && is_last_enc) { la.last_outputs = a.last_outputs; la.ld_last = P.sumC; la.out_off = dec.out_off; }
-      if (TRAIN) {
-        la.coef = a.c_err;
-        la.dz = ar.mat(B, dec.C);
-        dec_dz[(size_t)k * D + d] = la.dz;
-      }
       if (!dry) {
-        if (TRAIN) {      // the pitch padding of dz is read by the TMA unit as part of full 16-byte rows: keep it finite
-          MMN_CUDA(cudaMemsetAsync(la.dz.p, 0, (size_t)B * la.dz.ld * 2, ds));
-        }
         g_wt.begin("decoder_loss");
         wide_decoder_loss_kernel<<<(unsigned)((B + 255) / 256), 256, 0, ds>>>(la);
         if (launched()) return 1;
@@ -461,7 +465,10 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
     return 0;
   };
 
-  if (decoders_forward(0, 0, false, nullptr)) return 1;
+  struct StepMeta { int hist_row; bool is_last_enc; const int* skip; };
+  std::vector<StepMeta> meta(L + 1);
+  meta[0] = {0, false, nullptr};
+  if (!TRAIN && decoders_forward(0, 0, false, nullptr)) return 1;
   if (!dry) {
     g_wt.begin("finalize");
     wide_finalize_kernel<<<1, 256, 0, stream>>>(present, B, 0, 0, 0, nullptr, nullptr, S, a.inv_rows_global,
@@ -534,18 +541,69 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
                                                   TRAIN ? a.grads + P.n_params : nullptr);
       if (launched()) return 1;
     }
-    if (decoders_forward(k, e + 1, e == E - 1, skip)) return 1;
+    meta[k] = {e + 1, e == E - 1, skip};
+    if (!TRAIN && decoders_forward(k, e + 1, e == E - 1, skip)) return 1;
     if (!TRAIN) ar.off = scratch_mark;
+  }
+  // ---- training: every decoder, once, over the (L + 1) B state rows ----
+  std::vector<Mat> dec_hall((size_t)D * MMN_MAX_LAYERS);     // hidden activations [R x width] of decoder d, layer j
+  std::vector<Mat> dec_dzall(D);                             // loss gradient [R x C] of decoder d
+  if (TRAIN) {
+    for (int d = 0; d < D; ++d) {
+      const DevDecoder& dec = P.dec[d];
+      Mat in = Sall;
+      for (int j = 0; j < dec.n_layers; ++j) {
+        const DevLayer& ly = dec.L[j];
+        const mmn_plan::WL& w = plan->wide_dec[d][j];
+        const bool last = j == dec.n_layers - 1;
+        Epi e = epi0();
+        e.mode = EPI_STORE; e.act = ly.act; e.bias = a.params + ly.b_off;
+        Mat out = Mat();
+        if (!last) {
+          out = ar.mat(R, ly.out_dim);
+          dec_hall[(size_t)d * MMN_MAX_LAYERS + j] = out;
+          e.out = out.p; e.ld_out = out.ld;
+        } else {
+          e.out_f32 = Pout; e.ld_f32 = dec.C;
+        }
+        if (!dry) {
+          if (last && j > 0 && dec.C <= 4) {   // decoder head: skinny, bandwidth-bound kernel instead of a tensor-core tile
+            g_wt.begin("head_fwd");
+            launch_head_fwd(dec.C, n_sms, stream, in, wbase + w.w, w.ldk, a.params + ly.b_off, ly.act, R, Pout);
+            if (launched()) return 1;
+          } else if (wide_gemm(n_sms, in.p, in.ld, wbase + w.w, w.ldk, R, ly.out_dim, ly.ktot, e, stream, "gemm fwd")) {
+            return 1;
+          }
+        }
+        in = out;
+      }
+      dec_dzall[d] = ar.mat(R, dec.C);
+      // the pitch padding of dz is read by the TMA unit as part of full 16-byte rows: keep it finite
+      if (!dry) MMN_CUDA(cudaMemsetAsync(dec_dzall[d].p, 0, (size_t)R * dec_dzall[d].ld * 2, stream));
+      for (int k = 0; k <= L; ++k) {          // the per-row epilogue differs per step (history row, mask, skip flag)
+        LossArgs la;
+        memset(&la, 0, sizeof la);
+        la.p = Pout + (long long)k * B * dec.C; la.ldp = dec.C; la.C = dec.C; la.act = dec.L[dec.n_layers - 1].act; la.D = D; la.d = d;
+        la.hist_row = meta[k].hist_row; la.n_mat_rows = E + 1; la.rows = B; la.targets = a.targets; la.target_error = a.target_error;
+        la.present = k == 0 ? nullptr : present + (size_t)k * B;
+        la.skip = meta[k].skip;
+        la.metrics = a.metrics; la.inv_rows_global = a.inv_rows_global;
+        la.predictions = a.predictions ? a.predictions + ((long long)meta[k].hist_row * D + d) * a.pred_ld : nullptr;
+        if (a.last_outputs && meta[k].is_last_enc) { la.last_outputs = a.last_outputs; la.ld_last = P.sumC; la.out_off = dec.out_off; }
+        la.coef = a.c_err;
+        la.dz = rows_of(dec_dzall[d], (long long)k * B);
+        if (!dry) {
+          g_wt.begin("decoder_loss");
+          wide_decoder_loss_kernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>(la);
+          if (launched()) return 1;
+        }
+      }
+    }
   }
   if (a.final_state && !dry) {
     g_wt.begin("state_out");
     wide_state_out_kernel<<<(unsigned)std::min<long long>((B * S + 255) / 256, 4096), 256, 0, stream>>>(Sk[L], B, a.final_state);
     if (launched()) return 1;
-  }
-
-  if (fwd_side) {          // join: the backward pass needs every decoder's activations and loss gradient
-    MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->side_done, ds));
-    MMN_CUDA(cudaStreamWaitEvent(stream, (cudaEvent_t)plan->side_done, 0));
   }
 
   if (TRAIN) {
@@ -593,89 +651,86 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
       e.out_f32 = a.grads + ly.w_off; e.ld_f32 = ly.ktot;
       return wide_gemm(n_sms, dz.p, dz.ld, in.p, in.ld, ly.out_dim, ly.ktot, B, e, stream, "gemm wgrad", 1, 1);
     };
-    // Decoders, backward.  Everything except the last step — the first layer's data gradient, which lands in G — depends
-    // only on what the forward pass left behind, so the chains of ALL steps are enqueued up front on the plan's decoder
-    // stream and run next to the encoders' backward GEMMs (part A); the caller's stream adds each step's contribution to G
-    // where the reverse replay needs it (part B), behind that step's event.
+    // Decoders, backward, over the (L + 1) B rows of all steps at once.  On the caller's stream: each decoder's chain from
+    // its head down to the gradient dz_0 of its first layer, then DS (+)= dz_0 . W_0, the decoders' gradient with respect
+    // to every state (row block k is added to G where the reverse replay reaches step k).  The first layers' parameter
+    // gradients only read dz_0 and the states: they run on the plan's decoder stream next to the encoders' backward GEMMs.
     const bool dec_side = !dry && plan->dec_stream && !g_wt.on;
     const cudaStream_t dstream = dec_side ? (cudaStream_t)plan->dec_stream : stream;
-    std::vector<Mat> dz0((size_t)(L + 1) * D);          // dz of every decoder's first layer, kept for part B
-    Mat dzdec[2] = {ar.mat(B, maxW), ar.mat(B, maxW)};  // intermediates of decoders deeper than two layers
-    for (int k = 0; k <= L; ++k)
-      for (int d = 0; d < D; ++d)
-        dz0[(size_t)k * D + d] = P.dec[d].n_layers > 1 ? ar.mat(B, P.dec[d].L[0].out_dim) : dec_dz[(size_t)k * D + d];
-    auto decoders_backward_a = [&](int k) -> int {
-      if (dry) return 0;
-      for (int d = 0; d < D; ++d) {
+    float* DS = (float*)ar.take(sizeof(float) * (size_t)R * S);
+    {
+      bool deep = false;
+      for (int d = 0; d < D; ++d) deep |= P.dec[d].n_layers > 2;
+      Mat dzdec[2];                               // intermediates of decoders deeper than two layers
+      if (deep) { dzdec[0] = ar.mat(R, maxW); dzdec[1] = ar.mat(R, maxW); }
+      std::vector<Mat> dz0(D);                    // dz of every decoder's first layer
+      for (int d = 0; d < D; ++d) dz0[d] = P.dec[d].n_layers > 1 ? ar.mat(R, P.dec[d].L[0].out_dim) : dec_dzall[d];
+      const auto bias_grid = [&](int out_dim) {
+        return dim3((unsigned)((out_dim + 63) / 64), (unsigned)std::max<long long>(1, std::min<long long>(32, R / 256)));
+      };
+      for (int d = 0; d < D && !dry; ++d) {
         const DevDecoder& dec = P.dec[d];
-        Mat dz = dec_dz[(size_t)k * D + d];
+        Mat dz = dec_dzall[d];
         int cur = 0;
-        for (int j = dec.n_layers - 1; j >= 0; --j) {
+        for (int j = dec.n_layers - 1; j >= 1; --j) {
           const DevLayer& ly = dec.L[j];
           const mmn_plan::WL& w = plan->wide_dec[d][j];
-          const Mat in = j == 0 ? Sk[k] : dec_h[((size_t)k * D + d) * MMN_MAX_LAYERS + j - 1];
+          const Mat in = dec_hall[(size_t)d * MMN_MAX_LAYERS + j - 1];
           // dz of the layer below: the kept buffer when that layer is the first one
-          const Mat nz = j == 1 ? dz0[(size_t)k * D + d] : (j > 1 ? view(dzdec[cur], ly.in_dim) : Mat());
-          if (j == dec.n_layers - 1 && j > 0 && dec.C <= 4) {       // decoder head (see decoders_forward)
+          const Mat nz = j == 1 ? dz0[d] : view(dzdec[cur], ly.in_dim);
+          if (j == dec.n_layers - 1 && dec.C <= 4) {       // decoder head (see the forward pass)
             g_wt.begin("head_backward");
-            launch_head_backward(dec.C, n_sms, dstream, dz, in, B, a.grads + ly.w_off, ly.ktot, a.grads + ly.b_off, wbase + w.w, w.ldk,
+            launch_head_backward(dec.C, n_sms, stream, dz, in, R, a.grads + ly.w_off, ly.ktot, a.grads + ly.b_off, wbase + w.w, w.ldk,
                                  dec.L[j - 1].act, nz);
             if (launched()) return 1;
-            dz = nz;
-            cur ^= 1;
-            continue;
-          }
-          g_wt.begin("bias_grad");
-          wide_bias_grad_kernel<<<dim3((unsigned)((ly.out_dim + 63) / 64), (unsigned)std::max<long long>(1, std::min<long long>(32, B / 256))),
-                                  256, 0, dstream>>>(dz.p, dz.ld, B, ly.out_dim, a.grads + ly.b_off);
-          if (launched()) return 1;
-          Epi e = epi0();
-          e.mode = EPI_ACCUM_F32; e.accumulate = 1;
-          e.out_f32 = a.grads + ly.w_off; e.ld_f32 = ly.ktot;
-          if (wide_gemm(n_sms, dz.p, dz.ld, in.p, in.ld, ly.out_dim, ly.ktot, B, e, dstream, "gemm wgrad", 1, 1)) return 1;
-          if (j > 0) {
+          } else {
+            g_wt.begin("bias_grad");
+            wide_bias_grad_kernel<<<bias_grid(ly.out_dim), 256, 0, stream>>>(dz.p, dz.ld, R, ly.out_dim, a.grads + ly.b_off);
+            if (launched()) return 1;
+            Epi e = epi0();
+            e.mode = EPI_ACCUM_F32; e.accumulate = 1;
+            e.out_f32 = a.grads + ly.w_off; e.ld_f32 = ly.ktot;
+            if (wide_gemm(n_sms, dz.p, dz.ld, in.p, in.ld, ly.out_dim, ly.ktot, R, e, stream, "gemm wgrad", 1, 1)) return 1;
             Epi ed = epi0();
             ed.mode = EPI_DACT; ed.act = dec.L[j - 1].act;
             ed.aux = in.p; ed.ld_aux = in.ld;
             ed.out = nz.p; ed.ld_out = nz.ld;
-            if (wide_gemm(n_sms, dz.p, dz.ld, wbase + w.wt, w.ldo, B, ly.in_dim, ly.out_dim, ed, dstream, "gemm dgrad")) return 1;
-            dz = nz;
-            cur ^= 1;
+            if (wide_gemm(n_sms, dz.p, dz.ld, wbase + w.wt, w.ldo, R, ly.in_dim, ly.out_dim, ed, stream, "gemm dgrad")) return 1;
           }
+          dz = nz;
+          cur ^= 1;
         }
-      }
-      if (dec_side) MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->dec_done[k], dstream));
-      return 0;
-    };
-    auto decoders_backward_b = [&](int k) -> int {       // G += dz_0 . W_0 for every decoder of step k
-      if (dry) return 0;
-      if (dec_side) MMN_CUDA(cudaStreamWaitEvent(stream, (cudaEvent_t)plan->dec_done[k], 0));
-      for (int d = 0; d < D; ++d) {
-        const DevLayer& ly = P.dec[d].L[0];
-        const mmn_plan::WL& w = plan->wide_dec[d][0];
+        // DS (+)= dz_0 . W_0
+        const DevLayer& l0 = dec.L[0];
+        const mmn_plan::WL& w0 = plan->wide_dec[d][0];
         Epi e = epi0();
-        e.mode = EPI_ACCUM_F32; e.accumulate = 1;
-        e.out_f32 = G; e.ld_f32 = S;
-        if (dgrad(dz0[(size_t)k * D + d], ly, w, 0, S, e, "gemm dgrad")) return 1;
+        e.mode = EPI_ACCUM_F32; e.accumulate = d > 0;
+        e.out_f32 = DS; e.ld_f32 = S;
+        if (wide_gemm(n_sms, dz0[d].p, dz0[d].ld, wbase + w0.wt, w0.ldo, R, S, l0.out_dim, e, stream, "gemm dgrad")) return 1;
       }
-      return 0;
-    };
-    auto decoders_backward = [&](int k) -> int {
-      if (!dec_side && decoders_backward_a(k)) return 1;
-      return decoders_backward_b(k);
-    };
-    if (dec_side) {            // every step's part A, in the order part B will ask for them
-      MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->dec_fork, stream));
-      MMN_CUDA(cudaStreamWaitEvent(dstream, (cudaEvent_t)plan->dec_fork, 0));
-      for (int k = L; k >= 0; --k)
-        if (decoders_backward_a(k)) return 1;
+      if (!dry) {
+        if (dec_side) {
+          MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->dec_fork, stream));
+          MMN_CUDA(cudaStreamWaitEvent(dstream, (cudaEvent_t)plan->dec_fork, 0));
+        }
+        for (int d = 0; d < D; ++d) {             // first layers: bias and weight gradients, contraction over all R rows
+          const DevLayer& l0 = P.dec[d].L[0];
+          g_wt.begin("bias_grad");
+          wide_bias_grad_kernel<<<bias_grid(l0.out_dim), 256, 0, dstream>>>(dz0[d].p, dz0[d].ld, R, l0.out_dim, a.grads + l0.b_off);
+          if (launched()) return 1;
+          Epi e = epi0();
+          e.mode = EPI_ACCUM_F32; e.accumulate = 1;
+          e.out_f32 = a.grads + l0.w_off; e.ld_f32 = l0.ktot;
+          if (wide_gemm(n_sms, dz0[d].p, dz0[d].ld, Sall.p, Sall.ld, l0.out_dim, l0.ktot, R, e, dstream, "gemm wgrad", 1, 1)) return 1;
+        }
+        if (dec_side) MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->dec_done[0], dstream));
+      }
     }
     for (int k = L; k >= 1; --k) {
       const int e = a.seq_enc[k - 1];
       const DevEncoder& enc = P.enc[e];
       const int* skip = a.skip_flags ? a.skip_flags + (k - 1) : nullptr;
       unsigned char* pres = present + (size_t)k * B;
-      if (decoders_backward(k)) return 1;
       const int nl = enc.n_layers;
       int cur = 0;
       Mat dz = view(dzbuf[cur], S);
@@ -683,7 +738,8 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
       if (!dry) {
         if (join_side()) return 1;
         g_wt.begin("state_grad");
-        wide_state_grad_kernel<<<tgrid(B, S), tb, 0, stream>>>(G, Sk[k], Sk[k - 1], pres, skip, a.c_sc, enc.L[nl - 1].act, B, dz);
+        wide_state_grad_kernel<<<tgrid(B, S), tb, 0, stream>>>(G, DS + (size_t)k * B * S, Sk[k], Sk[k - 1], pres, skip, a.c_sc,
+                                                               enc.L[nl - 1].act, B, dz);
         if (launched()) return 1;
       }
       for (int j = nl - 1; j >= 0; --j) {
@@ -726,12 +782,12 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
         ev_done |= 1u << e;
       }
     }
-    if (decoders_backward(0)) return 1;
     if (!dry) {
       if (join_side()) return 1;
       g_wt.begin("colsum_f32");
-      wide_colsum_f32_kernel<<<dim3((unsigned)((S + 31) / 32), 16), 256, 0, stream>>>(G, B, S, a.grads + P.init_off);
+      wide_colsum_f32_kernel<<<dim3((unsigned)((S + 31) / 32), 16), 256, 0, stream>>>(G, DS, B, S, a.grads + P.init_off);
       if (launched()) return 1;
+      if (dec_side) MMN_CUDA(cudaStreamWaitEvent(stream, (cudaEvent_t)plan->dec_done[0], 0));      // the decoders' parameter gradients
       for (int i = 0; i < plan->n_grad_events; ++i)      // decoders, initial state, encoders that took no step
         if (i == E || !(ev_done & (1u << i))) MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->grad_events[i], stream));
     }

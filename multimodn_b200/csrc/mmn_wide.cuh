@@ -28,7 +28,8 @@ constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
 constexpr int kThreads = 384;          // warps 0-2: TMA / MMA / TMEM allocator; warps 4-11: epilogue
 constexpr int kStageBytes = (BM + BN) * BK * 2;                  // 48 KB
 constexpr int kBiasStageBytes = 2 * BN * 4;                      // the epilogue's bias slice of a tile, double-buffered
-constexpr int kSmemBytes = STAGES * kStageBytes + 1024 + 256 + kBiasStageBytes;      // + alignment slack + barriers + bias
+constexpr int kEpiStageBytes = 8 * 32 * 64;                      // per epilogue warp: 32 rows x 64 bytes of output being transposed
+constexpr int kSmemBytes = STAGES * kStageBytes + 1024 + 256 + kBiasStageBytes + kEpiStageBytes;   // + alignment slack, barriers, bias
 
 enum {
   EPI_STORE = 0,       // out = act(acc + bias)                                   (forward hidden / decoder layers)
@@ -37,6 +38,7 @@ enum {
   EPI_ACCUM_F32 = 3,   // out_f32 (+)= acc                                         (weight gradient; state gradient G += ...)
   EPI_CARRY = 4,       // out_f32 = (present[r] ? acc : out_f32) - c_sc (aux - aux2)   (state carry through an encoder; the
                        //                                                          state-change term changes sign for s_{k-1})
+  EPI_NONE = 5,        // accumulators dropped (MMN_WIDE_EPI_DEBUG=none: main-loop-only timing, development aid)
 };
 
 struct Epi {
@@ -147,6 +149,194 @@ __device__ __forceinline__ float wide_dact(int act, float a) {      // derivativ
   }
 }
 
+// ---- the epilogue of one warp on an interior tile: every row and column exists and every row of every operand starts on a
+// 16-byte boundary, so the loop over 16-column groups is straight-line per mode (the generic loop in the kernel spends ~260
+// instructions per group on mode / bounds / alignment decisions and, with two epilogue warps per scheduler, that issue
+// latency — not memory — is what a tile's epilogue costs).  Row-wise operands are fetched one group ahead. ----
+__device__ __forceinline__ void unpack16(const uint4& a0, const uint4& a1, float (&f)[16]) {
+  const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&a0);
+  const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&a1);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f0 = __bfloat1622float2(h0[i]), f1 = __bfloat1622float2(h1[i]);
+    f[2 * i] = f0.x; f[2 * i + 1] = f0.y; f[8 + 2 * i] = f1.x; f[8 + 2 * i + 1] = f1.y;
+  }
+}
+__device__ __forceinline__ void store16_bf16(__nv_bfloat16* op, const float (&v)[16]) {
+  uint4 o[2];
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  reinterpret_cast<uint4*>(op)[0] = o[0];
+  reinterpret_cast<uint4*>(op)[1] = o[1];
+}
+// Stores go through a per-warp staging buffer (32 rows x 64 bytes, 16-byte chunks XOR-swizzled by (row / 2) % 4 so that
+// both the row-wise writes and the 4-lanes-per-row reads are bank-conflict free): a thread owns one accumulator ROW, and a
+// direct store makes every warp instruction touch 32 lines with half-filled 32-byte sectors — measured 8.6 us of a 35 us
+// K = 1024 GEMM.  Staged, one instruction writes 8 rows x 64 contiguous bytes (full sectors).
+template <int MODE>
+__device__ __forceinline__ void epi_lean(const Epi& epi, unsigned taddr, int c_beg, int c_end, long long r, int n0, bool pres,
+                                         const float* bias_t, bool atomic, unsigned long long* acc_full_bar, unsigned parity,
+                                         char* stg, float& sc) {
+  constexpr bool kAux = MODE == EPI_SELECT || MODE == EPI_DACT || MODE == EPI_CARRY;
+  constexpr bool kAux2 = MODE == EPI_CARRY;
+  const int lane = threadIdx.x & 31;
+  const long long rbase = r - lane;                       // first row of this warp's 32
+  const bool f32_out = MODE == EPI_CARRY || (MODE == EPI_ACCUM_F32 && epi.out_f32);
+  const __nv_bfloat16* const aux_row = kAux ? epi.aux + r * epi.ld_aux + n0 : nullptr;
+  const __nv_bfloat16* const aux2_row = kAux2 ? epi.aux2 + r * epi.ld_aux2 + n0 : nullptr;
+  // staging: this lane's row on the write side, (row rr + 8 j, chunk rc) on the read side
+  char* const my_row = stg + lane * 64;
+  const unsigned wsw = (unsigned)(lane >> 1) & 3u;
+  const int rr = lane >> 2, rc = lane & 3;
+  auto st_chunk = [&](int ch, const uint4& val) { *reinterpret_cast<uint4*>(my_row + (((unsigned)ch ^ wsw) << 4)) = val; };
+  auto ld_chunk = [&](int j) {
+    const int row = rr + 8 * j;
+    return *reinterpret_cast<const uint4*>(stg + row * 64 + (((unsigned)rc ^ ((unsigned)(row >> 1) & 3u)) << 4));
+  };
+  // fp32 output, read side: the four rows this lane stores to, whether they take the old value (accumulation; carry: rows the
+  // encoder did not touch), and that old value fetched one group ahead
+  float* f32_t[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool add_old[4] = {false, false, false, false};
+  if (f32_out) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      f32_t[j] = epi.out_f32 + (rbase + rr + 8 * j) * epi.ld_f32 + n0 + rc * 4;
+      const bool pres_j = __shfl_sync(0xffffffffu, pres ? 1 : 0, rr + 8 * j) != 0;
+      add_old[j] = MODE == EPI_CARRY ? !pres_j : (epi.accumulate && !atomic);
+    }
+  }
+  __nv_bfloat16* bf_t[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (!f32_out) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bf_t[j] = epi.out + (rbase + rr + 8 * j) * epi.ld_out + n0 + rc * 8;
+  }
+  const int act = epi.act;
+  const float scale = epi.scale;
+  uint4 aq[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)}, bq[2] = {aq[0], aq[0]};
+  float4 oq[4] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f),
+                  make_float4(0.f, 0.f, 0.f, 0.f)};
+  auto fetch = [&](int c0) {
+    if (kAux) { aq[0] = reinterpret_cast<const uint4*>(aux_row + c0)[0]; aq[1] = reinterpret_cast<const uint4*>(aux_row + c0)[1]; }
+    if (kAux2) { bq[0] = reinterpret_cast<const uint4*>(aux2_row + c0)[0]; bq[1] = reinterpret_cast<const uint4*>(aux2_row + c0)[1]; }
+    if (f32_out) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (add_old[j]) oq[j] = *reinterpret_cast<const float4*>(f32_t[j] + c0);
+    }
+  };
+  fetch(c_beg);
+  mbar_wait(acc_full_bar, parity);
+  tc_fence_after();
+  for (int c0 = c_beg; c0 < c_end; c0 += 16) {
+    const uint4 a0 = aq[0], a1 = aq[1], b0 = bq[0], b1 = bq[1];
+    const float4 old0 = oq[0], old1 = oq[1], old2 = oq[2], old3 = oq[3];
+    if (c0 + 16 < c_end) fetch(c0 + 16);
+    float v[16];
+    tmem_ld16(taddr + c0, v);
+    if (MODE == EPI_STORE || MODE == EPI_SELECT) {
+      if (epi.bias) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(bias_t + c0 + i);
+          v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+        }
+      }
+      if (act == MMN_ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+      } else if (act == MMN_ACT_SIGMOID) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __fdividef(1.f, 1.f + __expf(-v[i]));
+      } else if (act == MMN_ACT_TANH) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
+      }
+      if (MODE == EPI_SELECT) {
+        float aux[16];
+        unpack16(a0, a1, aux);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          // what the next layer reads is the bf16-rounded state: measure the change on that
+          const float nw = pres ? __bfloat162float(__float2bfloat16(v[i])) : aux[i];
+          const float df = nw - aux[i];
+          sc = fmaf(df, df, sc);
+          v[i] = nw;
+        }
+      }
+    } else if (MODE == EPI_DACT) {
+      float aux[16];
+      unpack16(a0, a1, aux);
+      if (act == MMN_ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = aux[i] > 0.f ? v[i] : 0.f;
+      } else if (act == MMN_ACT_SIGMOID) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= aux[i] * (1.f - aux[i]);
+      } else if (act == MMN_ACT_TANH) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= 1.f - aux[i] * aux[i];
+      }
+    } else if (MODE == EPI_ACCUM_F32) {
+      if (scale != 1.f) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= scale;
+      }
+    } else {      // EPI_CARRY: the part that does not depend on the old value; absent rows contribute 0 here and keep G below
+      if (epi.drop_thr) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          v[i] = mmn_dropout_keep(epi.drop_seed, epi.drop_row_base + (unsigned)r, epi.drop_col_base + (unsigned)(n0 + c0 + i), epi.drop_thr)
+                     ? v[i] * scale : 0.f;
+      } else if (scale != 1.f) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= scale;
+      }
+      float aux[16], b[16];
+      unpack16(a0, a1, aux);
+      unpack16(b0, b1, b);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = (pres ? v[i] : 0.f) - epi.c_sc * (aux[i] - b[i]);
+    }
+    if (f32_out) {
+      // 16 fp32 = this row's 64 staged bytes; flushed every group
+#pragma unroll
+      for (int i = 0; i < 4; ++i) st_chunk(i, make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]), __float_as_uint(v[4 * i + 2]),
+                                                         __float_as_uint(v[4 * i + 3])));
+      __syncwarp();
+      const float4 olds[4] = {old0, old1, old2, old3};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 u = ld_chunk(j);
+        float4 o = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+        float* dst = f32_t[j] + c0;
+        if (MODE == EPI_ACCUM_F32 && atomic) {
+          atomicAdd(reinterpret_cast<float4*>(dst), o);
+        } else {
+          if (add_old[j]) { o.x += olds[j].x; o.y += olds[j].y; o.z += olds[j].z; o.w += olds[j].w; }
+          *reinterpret_cast<float4*>(dst) = o;
+        }
+      }
+      __syncwarp();
+    } else {
+      // 16 bf16 = half of this row's 64 staged bytes; flushed every second group
+      uint4 o[2];
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      const int odd = ((c0 - c_beg) >> 4) & 1;
+      st_chunk(2 * odd, o[0]);
+      st_chunk(2 * odd + 1, o[1]);
+      if (odd) {
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(bf_t[j] + (c0 - 16)) = ld_chunk(j);
+        __syncwarp();
+      }
+    }
+  }
+}
+
 // PAIR = true: launched as clusters of two CTAs working on one 256 x 256 output tile (K-major operands, no split-K);
 // each CTA stages 16 KB of A + 16 KB of B per k-step instead of 16 + 32 and the ring is 6 stages deep.
 constexpr int kPairStages = 6, kPairStageBytes = (BM + BN / 2) * BK * 2;       // 32 KB
@@ -164,6 +354,7 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   unsigned long long* acc_empty = acc_full + 2;       // [2]
   unsigned* tslot = reinterpret_cast<unsigned*>(acc_empty + 2);
   float* bias_s = reinterpret_cast<float*>(base + NSTG * STG + 256);      // [2][BN]
+  char* epi_stage = base + NSTG * STG + 256 + kBiasStageBytes;            // [8 warps][32 rows][64 bytes]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned pair_rank = PAIR ? cluster_ctarank() : 0u;
@@ -326,6 +517,38 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       const bool skipped = epi.skip && *epi.skip != 0;
       const bool pres = ((epi.present && rv) ? epi.present[r] != 0 : true) && !skipped;
       const bool pair_ok = (r | 1) < M;                // rows r and r ^ 1 both exist: packed transposed stores
+      if (epi.mode >= EPI_NONE) {
+        mbar_wait(acc_full + acc, acc_phase[acc]);
+        acc_phase[acc] ^= 1u;
+        tc_fence_after();
+        if (epi.mode == EPI_NONE + 1) {            // ldonly: the TMEM reads of a real epilogue, nothing else
+          float keep = 0.f;
+          for (int c0 = half * (cols / 2); c0 < (half + 1) * (cols / 2); c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem + ((unsigned)(32 * q) << 16) + acc * BN + c0, v);
+            keep += v[0];
+          }
+          if (keep == 1.2345e-30f && epi.sc_sum) *epi.sc_sum = keep;
+        } else if (epi.mode == EPI_NONE + 2) {     // aluonly: about the arithmetic of a real epilogue on dummy registers
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = (float)(lane + i);
+          for (int c0 = half * (cols / 2); c0 < (half + 1) * (cols / 2); c0 += 16) {
+#pragma unroll
+            for (int rep = 0; rep < 3; ++rep)
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], 1.0001f, (float)c0);
+          }
+          float keep = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) keep += v[i];
+          if (keep == 1.2345e-30f && epi.sc_sum) *epi.sc_sum = keep;
+        }
+        tc_fence_before();
+        if (PAIR) mbar_arrive_leader(acc_empty + acc);
+        else mbar_arrive(acc_empty + acc);
+        continue;
+      }
       const int c_beg = half * (cols / 2), c_end = (half + 1) * (cols / 2);
       // fast paths of the row-wise operands the epilogue reads (16 columns = two 16-byte loads per iteration)
       const bool aux_fast = epi.aux && rv && (epi.ld_aux & 7) == 0 && (reinterpret_cast<size_t>(epi.aux) & 15) == 0 && (n0 & 7) == 0;
@@ -366,6 +589,35 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       }
       if (epi.bias) asm volatile("bar.sync 1, 256;" ::: "memory");        // the 8 epilogue warps: bias slice complete
       const float* bias_t = bias_s + (it & 1) * BN;
+      {
+        auto al16 = [](const void* p_) { return (reinterpret_cast<size_t>(p_) & 15) == 0; };
+        const bool lean = m0 + BM <= M && n0 + c_end <= N && !epi.out_t && (!epi.out || ((epi.ld_out & 7) == 0 && al16(epi.out))) &&
+                          (!epi.out_f32 || ((epi.ld_f32 & 3) == 0 && al16(epi.out_f32))) &&
+                          (!epi.aux || ((epi.ld_aux & 7) == 0 && al16(epi.aux))) && (!epi.aux2 || ((epi.ld_aux2 & 7) == 0 && al16(epi.aux2))) &&
+                          (epi.mode != EPI_CARRY || (epi.out_f32 && epi.aux && epi.aux2)) &&
+                          ((epi.mode != EPI_SELECT && epi.mode != EPI_DACT) || epi.aux) &&
+                          // one output: bf16 for activations / layer gradients, fp32 for accumulations and the carry
+                          (epi.mode == EPI_CARRY || (epi.mode == EPI_ACCUM_F32 ? (epi.out != nullptr) != (epi.out_f32 != nullptr)
+                                                                               : (epi.out && !epi.out_f32))) &&
+                          ((c_end - c_beg) & 31) == 0;
+        if (lean) {            // uniform over the CTA
+          const unsigned taddr = tmem + ((unsigned)(32 * q) << 16) + acc * BN;
+          const unsigned parity = acc_phase[acc];
+          acc_phase[acc] ^= 1u;
+          char* stg = epi_stage + (warp - 4) * (32 * 64);
+          switch (epi.mode) {
+            case EPI_STORE: epi_lean<EPI_STORE>(epi, taddr, c_beg, c_end, r, n0, pres, bias_t, splits > 1, acc_full + acc, parity, stg, sc); break;
+            case EPI_SELECT: epi_lean<EPI_SELECT>(epi, taddr, c_beg, c_end, r, n0, pres, bias_t, splits > 1, acc_full + acc, parity, stg, sc); break;
+            case EPI_DACT: epi_lean<EPI_DACT>(epi, taddr, c_beg, c_end, r, n0, pres, bias_t, splits > 1, acc_full + acc, parity, stg, sc); break;
+            case EPI_ACCUM_F32: epi_lean<EPI_ACCUM_F32>(epi, taddr, c_beg, c_end, r, n0, pres, bias_t, splits > 1, acc_full + acc, parity, stg, sc); break;
+            default: epi_lean<EPI_CARRY>(epi, taddr, c_beg, c_end, r, n0, pres, bias_t, splits > 1, acc_full + acc, parity, stg, sc); break;
+          }
+          tc_fence_before();
+          if (PAIR) mbar_arrive_leader(acc_empty + acc);
+          else mbar_arrive(acc_empty + acc);
+          continue;
+        }
+      }
       fetch(c_beg);
       mbar_wait(acc_full + acc, acc_phase[acc]);
       acc_phase[acc] ^= 1u;

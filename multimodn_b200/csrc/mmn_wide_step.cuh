@@ -157,9 +157,11 @@ __global__ void __launch_bounds__(256) wide_input_state_kernel(Mat s, long long 
 __global__ void __launch_bounds__(256) wide_init_state_kernel(const float* __restrict__ init, long long rows, Mat s) {
   tile64_emit([&](long long, int c, int nv, float (&v)[8]) { load8(init + c, nv, v); }, rows, s.width, s.p, s.ld, s.t, s.ldt, 0);
 }
-// G += u_k ; dz = present ? G * act'(s_k) : 0      (u_k = c_sc (s_k - s_{k-1}))
-__global__ void __launch_bounds__(256) wide_state_grad_kernel(float* G, Mat sk, Mat skm1, const unsigned char* present, const int* skip,
-                                                              float c_sc, int act, long long rows, Mat dz) {
+// G += add_k + u_k ; dz = present ? G * act'(s_k) : 0      (u_k = c_sc (s_k - s_{k-1}); add_k = the decoders' gradient
+// with respect to s_k when it was computed for all steps at once, else null)
+__global__ void __launch_bounds__(256) wide_state_grad_kernel(float* G, const float* __restrict__ add, Mat sk, Mat skm1,
+                                                              const unsigned char* present, const int* skip, float c_sc, int act,
+                                                              long long rows, Mat dz) {
   const bool skipped = skip && *skip != 0;
   tile64_emit([&](long long r, int c, int nv, float (&v)[8]) {
     float a[8], b[8], g[8];
@@ -167,6 +169,12 @@ __global__ void __launch_bounds__(256) wide_state_grad_kernel(float* G, Mat sk, 
     load8(skm1.p + r * skm1.ld + c, nv, b);
     float* gp = G + r * sk.width + c;
     load8(gp, nv, g);
+    if (add) {
+      float d[8];
+      load8(add + r * sk.width + c, nv, d);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] += d[i];
+    }
     const bool live = present[r] && !skipped;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -226,13 +234,14 @@ __global__ void __launch_bounds__(256) wide_bias_grad_kernel(const bf16* __restr
   }
 }
 // column sums of the fp32 state gradient -> gradient of state_value (tile backward, state.py:30)
-__global__ void wide_colsum_f32_kernel(const float* __restrict__ G, long long rows, int S, float* out) {
+__global__ void wide_colsum_f32_kernel(const float* __restrict__ G, const float* __restrict__ add, long long rows, int S, float* out) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int part = threadIdx.x >> 5, parts = blockDim.x >> 5;
   __shared__ float red[8][32];
   float s = 0.f;
   if (c < S)
-    for (long long r = part + (long long)blockIdx.y * parts; r < rows; r += (long long)parts * gridDim.y) s += G[r * S + c];
+    for (long long r = part + (long long)blockIdx.y * parts; r < rows; r += (long long)parts * gridDim.y)
+      s += G[r * S + c] + (add ? add[r * S + c] : 0.f);
   red[part][threadIdx.x & 31] = s;
   __syncthreads();
   if (part == 0 && c < S) {
