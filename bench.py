@@ -466,9 +466,23 @@ class Bench:
             epoch_e2e(3)
             ems = self.timed(lambda i: epoch_e2e(Ke) if i == 0 else None, 1)
             assert len(logged) == 3 + Ke
+            # the ceiling the host side sets: the same pinned batches copied by every rank at once with nothing else running
+            # (all ranks share the host's DRAM and PCIe root complexes); an e2e step cannot be shorter than this copy
+            dst = [[torch.empty_like(t, device=dev) for t in xs] + [torch.empty_like(y, device=dev)] for xs, y in host[:1]][0]
+
+            def copy_only(i):
+                xs, y = host[i % 3]
+                for d, t in zip(dst, list(xs) + [y]):
+                    d.copy_(t, non_blocking=True)
+
+            copy_only(0)
+            cms = self.timed(copy_only, 6) / 6
+            del dst
             out["e2e"] = dict(value=B * world * Ke / (ems * 1e-3), unit="samples/s", h2d_bytes_per_step=bytes_in,
                               d2h_bytes_per_step=rt.n_metrics * 8, steps=Ke, ms_per_step=ems / Ke,
                               h2d_gbs_per_rank=bytes_in / (ems / Ke * 1e-3) / 1e9,
+                              h2d_ceiling=dict(gbs_per_rank=bytes_in / (cms * 1e-3) / 1e9, ms_per_step=cms,
+                                               note="copy-only time of one step's inputs, all ranks copying at once"),
                               call="MultiModN.train_epoch(loader of pinned host batches, FusedAdam, CrossEntropyLoss, history, log_interval=1)")
             del host
         del resident, model, opt, rt

@@ -580,21 +580,27 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
       dec_dzall[d] = ar.mat(R, dec.C);
       // the pitch padding of dz is read by the TMA unit as part of full 16-byte rows: keep it finite
       if (!dry) MMN_CUDA(cudaMemsetAsync(dec_dzall[d].p, 0, (size_t)R * dec_dzall[d].ld * 2, stream));
-      for (int k = 0; k <= L; ++k) {          // the per-row epilogue differs per step (history row, mask, skip flag)
-        LossArgs la;
-        memset(&la, 0, sizeof la);
-        la.p = Pout + (long long)k * B * dec.C; la.ldp = dec.C; la.C = dec.C; la.act = dec.L[dec.n_layers - 1].act; la.D = D; la.d = d;
-        la.hist_row = meta[k].hist_row; la.n_mat_rows = E + 1; la.rows = B; la.targets = a.targets; la.target_error = a.target_error;
-        la.present = k == 0 ? nullptr : present + (size_t)k * B;
-        la.skip = meta[k].skip;
+      {          // the per-row epilogue of every step in one launch (history row, mask and skip flag differ per step)
+        LossSteps ls;
+        memset(&ls, 0, sizeof ls);
+        LossArgs& la = ls.base;
+        la.p = Pout; la.ldp = dec.C; la.C = dec.C; la.act = dec.L[dec.n_layers - 1].act; la.D = D; la.d = d;
+        la.n_mat_rows = E + 1; la.rows = B; la.targets = a.targets; la.target_error = a.target_error;
         la.metrics = a.metrics; la.inv_rows_global = a.inv_rows_global;
-        la.predictions = a.predictions ? a.predictions + ((long long)meta[k].hist_row * D + d) * a.pred_ld : nullptr;
-        if (a.last_outputs && meta[k].is_last_enc) { la.last_outputs = a.last_outputs; la.ld_last = P.sumC; la.out_off = dec.out_off; }
+        la.predictions = a.predictions; ls.pred_ld = a.pred_ld;
+        if (a.last_outputs) { la.last_outputs = a.last_outputs; la.ld_last = P.sumC; la.out_off = dec.out_off; }
         la.coef = a.c_err;
-        la.dz = rows_of(dec_dzall[d], (long long)k * B);
+        la.dz = dec_dzall[d];
+        ls.n_steps = L + 1;
+        for (int k = 0; k <= L; ++k) {
+          ls.step[k].hist_row = meta[k].hist_row;
+          ls.step[k].is_last = meta[k].is_last_enc ? 1 : 0;
+          ls.step[k].present = k == 0 ? nullptr : present + (size_t)k * B;
+          ls.step[k].skip = meta[k].skip;
+        }
         if (!dry) {
           g_wt.begin("decoder_loss");
-          wide_decoder_loss_kernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>(la);
+          wide_decoder_loss_steps_kernel<<<dim3((unsigned)((B + 255) / 256), (unsigned)(L + 1)), 256, 0, stream>>>(ls);
           if (launched()) return 1;
         }
       }

@@ -438,7 +438,7 @@ struct LossArgs {
 };
 // per-row decoder epilogue (multimodn.py:144-157,179-191): first-max arg-max, CE on the outputs, counters, and the
 // gradient of the loss through the output activation
-__global__ void wide_decoder_loss_kernel(const LossArgs a) {
+__device__ __forceinline__ void decoder_loss_rows(const LossArgs& a) {
   const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const bool rv = r < a.rows;
   const bool skipped = a.skip && *a.skip != 0;
@@ -507,6 +507,28 @@ __global__ void wide_decoder_loss_kernel(const LossArgs a) {
     for (int j = 0; j < 5; ++j)
       if (tc[j]) atomicAdd(a.metrics + (j + 1) * stride + at, (double)tc[j]);
   }
+}
+__global__ void wide_decoder_loss_kernel(const LossArgs a) { decoder_loss_rows(a); }
+// The same epilogue for one decoder after EVERY step in one launch (training: the decoder ran once over all steps' states):
+// blockIdx.y = step k, whose rows are the k-th block of `rows` rows of p / dz.
+struct LossSteps {
+  LossArgs base;                           // p, dz: step 0; hist_row / present / skip / predictions / last_outputs: per step below
+  int n_steps;
+  long long pred_ld;                       // predictions: [(E + 1) x D x pred_ld], base.predictions = the array's start (or null)
+  struct Step { int hist_row, is_last; const unsigned char* present; const int* skip; } step[MMN_MAX_ENCODERS + 1];
+};
+__global__ void wide_decoder_loss_steps_kernel(const __grid_constant__ LossSteps s) {
+  const int k = blockIdx.y;
+  LossArgs a = s.base;
+  a.p += (long long)k * a.rows * a.ldp;
+  a.dz.p += (long long)k * a.rows * a.dz.ld;
+  a.dz.t = nullptr;
+  a.hist_row = s.step[k].hist_row;
+  a.present = s.step[k].present;
+  a.skip = s.step[k].skip;
+  a.predictions = s.base.predictions ? s.base.predictions + ((long long)a.hist_row * a.D + a.d) * s.pred_ld : nullptr;
+  if (!s.step[k].is_last) a.last_outputs = nullptr;
+  decoder_loss_rows(a);
 }
 // per-step bookkeeping: present-row counts, state-change means, the gradient buffer's "encoder took a row" tail
 __global__ void wide_finalize_kernel(const unsigned char* present, long long rows, int k, int hist_row, int e, const int* skip,

@@ -199,3 +199,67 @@ def test_wide_test_epoch_history_and_outputs():
     fin = acc.finalize()
     assert_close(hist.loss["val"][0], fin["loss"], rtol=1e-4, what="val loss")
     np.testing.assert_allclose(np.nan_to_num(hist.accuracy["val"][0]), np.nan_to_num(fin["accuracy"]), atol=0.01)
+
+
+def test_wide_full_config4_at_8192_rows():
+    """BASELINE configs[3] complete (4 encoders 1024/1024/768/768 -> 2048 -> 2048 -> state 1024, 2 decoders 1024 -> 2048 -> 2,
+    MNAR missingness) at its per-GPU batch of 8192 rows.  The oracle cannot run 8192 rows of this model in test time, so:
+      * per-row results (predictions after every step, final states) of the 8192-row calls are compared with the bf16 oracle
+        on a 512-row sample of the same batch -- rows are independent in the forward pass;
+      * the 8192-row gradient / metric vector equals the sum of its sixteen 512-row shards normalised by the global batch
+        (the data-parallel contract), and the first shard alone, run through train_epoch, agrees with the bf16 oracle's
+        gradient of those 512 rows."""
+    from oracle.spec_io import config_spec, CONFIGS
+    feats, D, B, n = CONFIGS["c4_wide"]["features"], CONFIGS["c4_wide"]["n_decoders"], 8192, 512
+    spec = config_spec("c4_wide", 5)
+    rng = np.random.default_rng(2024)
+    data, y = synthetic_batch(rng, feats, D, B, mnar=True)
+    err, scp = 0.8, 0.6
+    model = model_from_spec(spec, err, scp, DEV, "row", precision="bf16")
+    rt = model.runtime()
+    from multimodn_b200 import _lib
+    assert _lib.get_lib().dll.mmn_plan_engine(rt.plan) == 3
+    ospec = dict(O.cast_spec(spec, np.float32), precision="bf16")
+
+    # forward, per row
+    pred = model.predict([torch.from_numpy(x) for x in data])
+    loader = [([torch.from_numpy(x).to(DEV) for x in data], torch.from_numpy(y).to(DEV))]
+    states = torch.stack(model.get_states(loader)).cpu().numpy().reshape(B, -1)
+    idx = np.sort(rng.choice(B, n, replace=False))
+    ofwd = O.forward(ospec, [x[idx] for x in data], y[idx], None, "row")
+    assert pred.shape == (len(feats) + 1, D, B)
+    assert (pred[:, :, idx] != ofwd["predictions"]).mean() <= 0.005
+    assert_close(states[idx], ofwd["final_state"].reshape(n, -1), rtol=8e-3, what="states of the sampled rows vs bf16 oracle")
+
+    # backward: the full batch == the sum of its shards; one shard == the oracle
+    dev = [torch.from_numpy(x).to(DEV) for x in data]
+    ty = torch.from_numpy(y).to(DEV)
+    seq = [(i, i) for i in range(len(feats))]
+
+    def run(shards):
+        acc_g, acc_m = torch.zeros_like(rt.gflat), rt.new_metrics()
+        for r in range(shards):
+            m = B // shards
+            rt.step_counter = 0
+            mb, keep, rows = rt.prepare_batch([t[r * m:(r + 1) * m] for t in dev], ty[r * m:(r + 1) * m], seq, "row", (shards, r, None))
+            rt.train_step(mb, rows, err, 0.01 * scp, True, acc_m)
+            acc_g += rt.gflat
+        return acc_g.cpu().numpy(), acc_m.cpu().numpy()
+
+    g1, m1 = run(1)
+    g16, m16 = run(B // n)
+    P = rt.packed.n_params
+    assert np.isfinite(g1).all()
+    assert_close(g16[:P], g1[:P], rtol=2e-3, what="sum of 16 shards == the 8192-row step (gradients)")
+    assert (g16[P:] == g1[P:]).all()
+    assert_close(m16, m1, rtol=1e-5, what="sum of 16 shards == the 8192-row step (metrics)")
+    # one 512-row shard through the public API (normalised by its own size) against the oracle
+    sl = slice(0, n)
+    tap = GradTap(model.parameters())
+    model.train_epoch([([t[sl] for t in dev], ty[sl])], tap, CrossEntropyLoss(), MultiModNHistory(["a", "b"]))
+    got, _ = tapped_flat(model, tap)
+    _, _, grads, _ = O.train_step(ospec, [x[sl] for x in data], y[sl], err, 0.01 * scp, missing_mode="row")
+    want = flat_grads(grads).astype(np.float64)
+    cos = float(got @ want / (np.linalg.norm(got) * np.linalg.norm(want)))
+    assert cos >= 0.9999, cos
+    assert_close(got, want, rtol=2e-3, what="first 512-row shard vs bf16 oracle (gradients)")
