@@ -60,6 +60,20 @@ int make_operand_map_mn(CUtensorMap* m, const void* base, long long mn, long lon
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for an MN-major %lld x %lld operand, pitch %lld", (int)r, k_rows, mn, ld);
   return 0;
 }
+// Every kernel of the wide step is launched with programmatic stream serialisation (see pdl_entry in mmn_wide.cuh);
+// MMN_WIDE_PDL=0 launches them fully serialised.
+static const bool g_pdl = !(getenv("MMN_WIDE_PDL") && !strcmp(getenv("MMN_WIDE_PDL"), "0"));
+template <typename... KArgs, typename... Args>
+void wide_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // errors surface through cudaGetLastError at the call site
+}
 long long g_wide_launches = 0;       // kernels launched by the wide path (bench.py's gpu_launches)
 // MMN_WIDE_TIMERS=1: CUDA events around every launch of a step, summed per category and printed (development aid)
 struct WideTimers {
@@ -180,10 +194,12 @@ int wide_gemm(int n_sms, const void* A, long long lda, const void* B, long long 
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(wide::kThreads); cfg.dynamicSmemBytes = wide::kSmemBytes;
     cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 2;
     g_wt.begin(what);
     MMN_CUDA(cudaLaunchKernelEx(&cfg, wide::mmn_wide_gemm_kernel<true>, ma, mb_quarter, mb_half, (int)M, (int)N, (int)K, psplits, a_mn, b_mn,
                                 pair_tail, epi));
@@ -197,7 +213,7 @@ int wide_gemm(int n_sms, const void* A, long long lda, const void* B, long long 
   const int tail_halves = splits == 1 ? pick_tail_div(tiles, grid, false) : 1;
   if (tail_halves > 1 && !b_mn && make_operand_map(&mb_half, B, N, K, ldb, wide::BN / tail_halves)) return 1;
   g_wt.begin(what);
-  wide::mmn_wide_gemm_kernel<false><<<grid, wide::kThreads, wide::kSmemBytes, (cudaStream_t)stream>>>(ma, mb, mb_half, (int)M, (int)N, (int)K, splits, a_mn, b_mn, tail_halves, epi);
+  wide_launch(wide::mmn_wide_gemm_kernel<false>, dim3(grid), dim3(wide::kThreads), wide::kSmemBytes, (cudaStream_t)stream, ma, mb, mb_half, (int)M, (int)N, (int)K, splits, a_mn, b_mn, tail_halves, epi);
   g_wt.end();
   MMN_CUDA(cudaGetLastError());
   ++g_wide_launches;
@@ -276,14 +292,16 @@ bool ptr16(const void* p) { return (reinterpret_cast<size_t>(p) & 15) == 0; }
 template <int C>
 void launch_head_fwd_c(bool fast, unsigned grid, cudaStream_t st, const wide::Mat& h, const wide::bf16* Wb, long long ldk, const float* bias,
                        int act, long long rows, float* p_out) {
-  if (fast) wide::wide_head_fwd_kernel<C, true><<<grid, 256, 0, st>>>(h, Wb, ldk, bias, act, rows, p_out);
-  else wide::wide_head_fwd_kernel<C, false><<<grid, 256, 0, st>>>(h, Wb, ldk, bias, act, rows, p_out);
+  if (fast) wide_launch(wide::wide_head_fwd_kernel<C, true>, dim3(grid), dim3(256), 0, st, h, Wb, ldk, bias, act, rows, p_out);
+  else wide_launch(wide::wide_head_fwd_kernel<C, false>, dim3(grid), dim3(256), 0, st, h, Wb, ldk, bias, act, rows, p_out);
 }
 void launch_head_fwd(int C, int n_sms, cudaStream_t st, const wide::Mat& h, const wide::bf16* Wb, long long ldk, const float* bias, int act,
                      long long rows, float* p_out) {
   const bool fast = ptr16(h.p) && ptr16(Wb) && (h.ld & 7) == 0 && (ldk & 7) == 0 && (h.width & 7) == 0;
   const long long per_cta = 8 * wide::kHeadRows;
-  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((rows + per_cta - 1) / per_cta, 8ll * n_sms));
+  // one resident wave (3 CTAs of 256 threads per SM at the kernel's 80 registers): the grid-stride loop then gives every warp
+  // the same number of row groups instead of a second, mostly empty wave
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((rows + per_cta - 1) / per_cta, 3ll * n_sms));
   switch (C) {
     case 1: launch_head_fwd_c<1>(fast, grid, st, h, Wb, ldk, bias, act, rows, p_out); break;
     case 2: launch_head_fwd_c<2>(fast, grid, st, h, Wb, ldk, bias, act, rows, p_out); break;
@@ -294,8 +312,8 @@ void launch_head_fwd(int C, int n_sms, cudaStream_t st, const wide::Mat& h, cons
 template <int C>
 void launch_head_backward_c(bool fast, dim3 grid, cudaStream_t st, const wide::Mat& dz, const wide::Mat& h, long long rows, float* gW,
                             long long ldw, float* gb, const wide::bf16* Wb, long long ldk, int act_prev, const wide::Mat& out) {
-  if (fast) wide::wide_head_backward_kernel<C, true><<<grid, 256, 0, st>>>(dz, h, rows, gW, ldw, gb, Wb, ldk, act_prev, out);
-  else wide::wide_head_backward_kernel<C, false><<<grid, 256, 0, st>>>(dz, h, rows, gW, ldw, gb, Wb, ldk, act_prev, out);
+  if (fast) wide_launch(wide::wide_head_backward_kernel<C, true>, dim3(grid), dim3(256), 0, st, dz, h, rows, gW, ldw, gb, Wb, ldk, act_prev, out);
+  else wide_launch(wide::wide_head_backward_kernel<C, false>, dim3(grid), dim3(256), 0, st, dz, h, rows, gW, ldw, gb, Wb, ldk, act_prev, out);
 }
 void launch_head_backward(int C, int n_sms, cudaStream_t st, const wide::Mat& dz, const wide::Mat& h, long long rows, float* gW, long long ldw,
                           float* gb, const wide::bf16* Wb, long long ldk, int act_prev, const wide::Mat& out) {
@@ -364,7 +382,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
     // the job table travels through the head of the workspace (re-sent every call: params may move between calls)
     MMN_CUDA(cudaMemcpyAsync(cast_jobs_dev, &jobs, sizeof(CastJob) * n_jobs, cudaMemcpyHostToDevice, stream));
     g_wt.begin("cast_weight");
-    wide_cast_weights_kernel<<<dim3((unsigned)((max_k + 63) / 64), (unsigned)((max_out + 63) / 64), (unsigned)n_jobs), 256, 0, stream>>>(
+    wide_launch(wide_cast_weights_kernel, dim3((unsigned)((max_k + 63) / 64), (unsigned)((max_out + 63) / 64), (unsigned)n_jobs), dim3(256), 0, stream, 
         (const CastJobs*)cast_jobs_dev);
     if (launched()) return 1;
   }
@@ -405,7 +423,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
     MMN_CUDA(cudaMemsetAsync(present, 1, (size_t)(L + 1) * B, stream));
     MMN_CUDA(cudaMemsetAsync(sc_sum, 0, sizeof(float) * (size_t)std::max(E, 1), stream));
     g_wt.begin("init_state");
-    wide_init_state_kernel<<<tgrid(B, S), tb, 0, stream>>>(a.params + P.init_off, B, Sk[0]);
+    wide_launch(wide_init_state_kernel, dim3(tgrid(B, S)), tb, 0, stream, a.params + P.init_off, B, Sk[0]);
     if (launched()) return 1;
   }
   const size_t scratch_mark = ar.off;
@@ -458,7 +476,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
       if (a.last_outputs && is_last_enc) { la.last_outputs = a.last_outputs; la.ld_last = P.sumC; la.out_off = dec.out_off; }
       if (!dry) {
         g_wt.begin("decoder_loss");
-        wide_decoder_loss_kernel<<<(unsigned)((B + 255) / 256), 256, 0, ds>>>(la);
+        wide_launch(wide_decoder_loss_kernel, dim3((unsigned)((B + 255) / 256)), dim3(256), 0, ds, la);
         if (launched()) return 1;
       }
     }
@@ -471,7 +489,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
   if (!TRAIN && decoders_forward(0, 0, false, nullptr)) return 1;
   if (!dry) {
     g_wt.begin("finalize");
-    wide_finalize_kernel<<<1, 256, 0, stream>>>(present, B, 0, 0, 0, nullptr, nullptr, S, a.inv_rows_global,
+    wide_launch(wide_finalize_kernel, dim3(1), dim3(256), 0, stream, present, B, 0, 0, 0, nullptr, nullptr, S, a.inv_rows_global,
                                                 a.metrics ? a.metrics + met_present(P, 0) : nullptr, nullptr, nullptr);
     if (launched()) return 1;
   }
@@ -495,11 +513,11 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
     enc_in[(size_t)k * MMN_MAX_LAYERS + 0] = in;
     if (!dry) {
       g_wt.begin("input_x");
-      wide_input_x_kernel<<<tgrid(B, enc.F), tb, 0, stream>>>(a.x[pos], a.x_ld[pos], B, enc.F, in, pres, drop);
+      wide_launch(wide_input_x_kernel, dim3(tgrid(B, enc.F)), tb, 0, stream, a.x[pos], a.x_ld[pos], B, enc.F, in, pres, drop);
       if (launched()) return 1;
       if (enc.L[0].has_state) {
         g_wt.begin("input_state");
-        wide_input_state_kernel<<<tgrid(B, S), tb, 0, stream>>>(Sk[k - 1], B, in, enc.L[0].in_dim, drop);
+        wide_launch(wide_input_state_kernel, dim3(tgrid(B, S)), tb, 0, stream, Sk[k - 1], B, in, enc.L[0].in_dim, drop);
         if (launched()) return 1;
       }
     }
@@ -527,7 +545,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
         if (wide_gemm(n_sms, in.p, in.ld, wbase + w.w, w.ldk, B, ly.out_dim, ly.ktot, ep, stream)) return 1;
         if (!last && enc.L[j + 1].has_state) {
           g_wt.begin("input_state");
-          wide_input_state_kernel<<<tgrid(B, S), tb, 0, stream>>>(Sk[k - 1], B, next, enc.L[j + 1].in_dim, nodrop);
+          wide_launch(wide_input_state_kernel, dim3(tgrid(B, S)), tb, 0, stream, Sk[k - 1], B, next, enc.L[j + 1].in_dim, nodrop);
           if (launched()) return 1;
         }
       }
@@ -535,7 +553,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
     }
     if (!dry) {
       g_wt.begin("finalize");
-      wide_finalize_kernel<<<1, 256, 0, stream>>>(pres, B, k, e + 1, e, skip, TRAIN ? sc_sum + e : nullptr, S, a.inv_rows_global,
+      wide_launch(wide_finalize_kernel, dim3(1), dim3(256), 0, stream, pres, B, k, e + 1, e, skip, TRAIN ? sc_sum + e : nullptr, S, a.inv_rows_global,
                                                   a.metrics ? a.metrics + met_present(P, 0) : nullptr,
                                                   (TRAIN && a.metrics) ? a.metrics + met_sc(P, 0) : nullptr,
                                                   TRAIN ? a.grads + P.n_params : nullptr);
@@ -600,7 +618,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
         }
         if (!dry) {
           g_wt.begin("decoder_loss");
-          wide_decoder_loss_steps_kernel<<<dim3((unsigned)((B + 255) / 256), (unsigned)(L + 1)), 256, 0, stream>>>(ls);
+          wide_launch(wide_decoder_loss_steps_kernel, dim3((unsigned)((B + 255) / 256), (unsigned)(L + 1)), dim3(256), 0, stream, ls);
           if (launched()) return 1;
         }
       }
@@ -608,7 +626,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
   }
   if (a.final_state && !dry) {
     g_wt.begin("state_out");
-    wide_state_out_kernel<<<(unsigned)std::min<long long>((B * S + 255) / 256, 4096), 256, 0, stream>>>(Sk[L], B, a.final_state);
+    wide_launch(wide_state_out_kernel, dim3((unsigned)std::min<long long>((B * S + 255) / 256, 4096)), dim3(256), 0, stream, Sk[L], B, a.final_state);
     if (launched()) return 1;
   }
 
@@ -642,14 +660,14 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
       if (use_side) {
         MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->side_fork, stream));
         MMN_CUDA(cudaStreamWaitEvent(side, (cudaEvent_t)plan->side_fork, 0));
-        wide_bias_grad_kernel<<<bgrid, 256, 0, side>>>(dz.p, dz.ld, B, ly.out_dim, a.grads + ly.b_off);
+        wide_launch(wide_bias_grad_kernel, dim3(bgrid), dim3(256), 0, side, dz.p, dz.ld, B, ly.out_dim, a.grads + ly.b_off);
         MMN_CUDA(cudaGetLastError());
         ++g_wide_launches;
         MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->side_done, side));
         side_pending = true;
       } else {
         g_wt.begin("bias_grad");
-        wide_bias_grad_kernel<<<bgrid, 256, 0, stream>>>(dz.p, dz.ld, B, ly.out_dim, a.grads + ly.b_off);
+        wide_launch(wide_bias_grad_kernel, dim3(bgrid), dim3(256), 0, stream, dz.p, dz.ld, B, ly.out_dim, a.grads + ly.b_off);
         if (launched()) return 1;
       }
       Epi e = epi0();
@@ -691,7 +709,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
             if (launched()) return 1;
           } else {
             g_wt.begin("bias_grad");
-            wide_bias_grad_kernel<<<bias_grid(ly.out_dim), 256, 0, stream>>>(dz.p, dz.ld, R, ly.out_dim, a.grads + ly.b_off);
+            wide_launch(wide_bias_grad_kernel, dim3(bias_grid(ly.out_dim)), dim3(256), 0, stream, dz.p, dz.ld, R, ly.out_dim, a.grads + ly.b_off);
             if (launched()) return 1;
             Epi e = epi0();
             e.mode = EPI_ACCUM_F32; e.accumulate = 1;
@@ -722,7 +740,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
         for (int d = 0; d < D; ++d) {             // first layers: bias and weight gradients, contraction over all R rows
           const DevLayer& l0 = P.dec[d].L[0];
           g_wt.begin("bias_grad");
-          wide_bias_grad_kernel<<<bias_grid(l0.out_dim), 256, 0, dstream>>>(dz0[d].p, dz0[d].ld, R, l0.out_dim, a.grads + l0.b_off);
+          wide_launch(wide_bias_grad_kernel, dim3(bias_grid(l0.out_dim)), dim3(256), 0, dstream, dz0[d].p, dz0[d].ld, R, l0.out_dim, a.grads + l0.b_off);
           if (launched()) return 1;
           Epi e = epi0();
           e.mode = EPI_ACCUM_F32; e.accumulate = 1;
@@ -744,7 +762,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
       if (!dry) {
         if (join_side()) return 1;
         g_wt.begin("state_grad");
-        wide_state_grad_kernel<<<tgrid(B, S), tb, 0, stream>>>(G, DS + (size_t)k * B * S, Sk[k], Sk[k - 1], pres, skip, a.c_sc,
+        wide_launch(wide_state_grad_kernel, dim3(tgrid(B, S)), tb, 0, stream, G, DS + (size_t)k * B * S, Sk[k], Sk[k - 1], pres, skip, a.c_sc,
                                                                enc.L[nl - 1].act, B, dz);
         if (launched()) return 1;
       }
@@ -791,7 +809,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
     if (!dry) {
       if (join_side()) return 1;
       g_wt.begin("colsum_f32");
-      wide_colsum_f32_kernel<<<dim3((unsigned)((S + 31) / 32), 16), 256, 0, stream>>>(G, DS, B, S, a.grads + P.init_off);
+      wide_launch(wide_colsum_f32_kernel, dim3((unsigned)((S + 31) / 32), 16), dim3(256), 0, stream, G, DS, B, S, a.grads + P.init_off);
       if (launched()) return 1;
       if (dec_side) MMN_CUDA(cudaStreamWaitEvent(stream, (cudaEvent_t)plan->dec_done[0], 0));      // the decoders' parameter gradients
       for (int i = 0; i < plan->n_grad_events; ++i)      // decoders, initial state, encoders that took no step

@@ -124,6 +124,15 @@ __device__ __forceinline__ void tmem_dealloc_pair(unsigned taddr, unsigned ncols
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
+// Programmatic dependent launch: every kernel of the wide step lets its successor in the stream be scheduled at once
+// (launch_dependents) and waits for its own predecessor to have completed and flushed (wait) before it touches global memory.
+// The successor's CTAs then start as this grid's CTAs retire — launch latency and the GEMM's prologue (barrier init, TMEM
+// allocation, descriptor prefetch) hide behind the predecessor's tail.  Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_entry() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 struct Pipe {
   int stage;
   unsigned phase;
@@ -391,6 +400,7 @@ mmn_wide_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   else __syncthreads();
   tc_fence_after();
   const unsigned tmem = *tslot;
+  pdl_entry();            // everything above touched only shared and tensor memory
 
   if (warp == 0) {
     // ===== TMA producer =====

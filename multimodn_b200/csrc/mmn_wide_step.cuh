@@ -120,6 +120,7 @@ struct CastJob { const float* W; bf16* Wb; bf16* WbT; int out, ktot; long long l
 constexpr int kMaxCastJobs = (MMN_MAX_ENCODERS + MMN_MAX_DECODERS) * MMN_MAX_LAYERS;
 struct CastJobs { CastJob job[kMaxCastJobs]; };
 __global__ void __launch_bounds__(256) wide_cast_weights_kernel(const CastJobs* __restrict__ jobs) {
+  pdl_entry();
   const CastJob j = jobs->job[blockIdx.z];
   if ((int)blockIdx.x * 64 >= j.ktot || (int)blockIdx.y * 64 >= j.out) return;
   tile64_emit([&](long long r, int c, int nv, float (&v)[8]) { load8(j.W + r * j.ktot + c, nv, v); }, j.out, j.ktot, j.Wb, j.ldk,
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(256) wide_cast_weights_kernel(const CastJobs* 
 // features of one modality -> columns [0, F) of the first layer's input; NaN -> 0 and the row is marked absent
 __global__ void __launch_bounds__(256) wide_input_x_kernel(const float* __restrict__ x, long long x_ld, long long rows, int F, Mat in,
                                                            unsigned char* present, Drop drop) {
+  pdl_entry();
   tile64_emit([&](long long r, int c, int nv, float (&v)[8]) {
     load8(x + r * x_ld + c, nv, v);
     bool nan = false;
@@ -144,6 +146,7 @@ __global__ void __launch_bounds__(256) wide_input_x_kernel(const float* __restri
 }
 // the running state -> columns [colofs, colofs + S) of a layer input (torch.cat([x, state]), mlp_encoder.py:41,78)
 __global__ void __launch_bounds__(256) wide_input_state_kernel(Mat s, long long rows, Mat in, int colofs, Drop drop) {
+  pdl_entry();
   tile64_emit([&](long long r, int c, int nv, float (&v)[8]) {
     load8(s.p + r * s.ld + c, nv, v);
     if (drop.enabled) {
@@ -155,6 +158,7 @@ __global__ void __launch_bounds__(256) wide_input_state_kernel(Mat s, long long 
 }
 // s_0 = tile(state_value) (state.py:29-32)
 __global__ void __launch_bounds__(256) wide_init_state_kernel(const float* __restrict__ init, long long rows, Mat s) {
+  pdl_entry();
   tile64_emit([&](long long, int c, int nv, float (&v)[8]) { load8(init + c, nv, v); }, rows, s.width, s.p, s.ld, s.t, s.ldt, 0);
 }
 // G += add_k + u_k ; dz = present ? G * act'(s_k) : 0      (u_k = c_sc (s_k - s_{k-1}); add_k = the decoders' gradient
@@ -162,6 +166,7 @@ __global__ void __launch_bounds__(256) wide_init_state_kernel(const float* __res
 __global__ void __launch_bounds__(256) wide_state_grad_kernel(float* G, const float* __restrict__ add, Mat sk, Mat skm1,
                                                               const unsigned char* present, const int* skip, float c_sc, int act,
                                                               long long rows, Mat dz) {
+  pdl_entry();
   const bool skipped = skip && *skip != 0;
   tile64_emit([&](long long r, int c, int nv, float (&v)[8]) {
     float a[8], b[8], g[8];
@@ -191,6 +196,7 @@ __global__ void __launch_bounds__(256) wide_state_grad_kernel(float* G, const fl
 }
 // bias gradient: gb[n] += sum_r dz[r][n]          CTA = 64 columns x a slice of the rows; thread = 8 columns, every 32nd row
 __global__ void __launch_bounds__(256) wide_bias_grad_kernel(const bf16* __restrict__ dz, long long ld, long long rows, int n_out, float* gb) {
+  pdl_entry();
   __shared__ float red[32][65];
   const int chunk = threadIdx.x & 7, rl = threadIdx.x >> 3;
   const int n0 = blockIdx.x * 64 + chunk * 8;
@@ -235,6 +241,7 @@ __global__ void __launch_bounds__(256) wide_bias_grad_kernel(const bf16* __restr
 }
 // column sums of the fp32 state gradient -> gradient of state_value (tile backward, state.py:30)
 __global__ void wide_colsum_f32_kernel(const float* __restrict__ G, const float* __restrict__ add, long long rows, int S, float* out) {
+  pdl_entry();
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int part = threadIdx.x >> 5, parts = blockDim.x >> 5;
   __shared__ float red[8][32];
@@ -252,6 +259,7 @@ __global__ void wide_colsum_f32_kernel(const float* __restrict__ G, const float*
 }
 // bf16 state -> fp32 final_state
 __global__ void wide_state_out_kernel(Mat s, long long rows, float* out) {
+  pdl_entry();
   const long long n = rows * s.width;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / s.width;
@@ -268,8 +276,9 @@ __global__ void wide_state_out_kernel(Mat s, long long rows, float* out) {
 // fast = every row of h and W starts 16-byte aligned and the width is a multiple of 8 (checked by the launcher).
 constexpr int kHeadRows = 4;
 template <int C, bool FAST>
-__global__ void __launch_bounds__(256) wide_head_fwd_kernel(Mat h, const bf16* __restrict__ Wb, long long ldk, const float* __restrict__ bias,
+__global__ void __launch_bounds__(256, 3) wide_head_fwd_kernel(Mat h, const bf16* __restrict__ Wb, long long ldk, const float* __restrict__ bias,
                                                             int act, long long rows, float* __restrict__ p_out) {
+  pdl_entry();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (long long rb = ((long long)blockIdx.x * 8 + warp) * kHeadRows; rb < rows; rb += (long long)gridDim.x * 8 * kHeadRows) {
     float acc[kHeadRows][C];
@@ -339,6 +348,7 @@ template <> struct DzWord<2> { typedef unsigned type; };
 template <int C, bool FAST>
 __global__ void __launch_bounds__(256, kHeadBwdCtas(C)) wide_head_backward_kernel(Mat dz, Mat h, long long rows, float* gW, long long ldw, float* gb,
                                                                     const bf16* __restrict__ Wb, long long ldk, int act_prev, Mat out) {
+  pdl_entry();
   const int k0 = (blockIdx.x * 256 + threadIdx.x) * 8;
   const long long per = (rows + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
   float acc[C][8], wv[C][8];
@@ -508,7 +518,8 @@ __device__ __forceinline__ void decoder_loss_rows(const LossArgs& a) {
       if (tc[j]) atomicAdd(a.metrics + (j + 1) * stride + at, (double)tc[j]);
   }
 }
-__global__ void wide_decoder_loss_kernel(const LossArgs a) { decoder_loss_rows(a); }
+__global__ void wide_decoder_loss_kernel(const LossArgs a) {
+  pdl_entry(); decoder_loss_rows(a); }
 // The same epilogue for one decoder after EVERY step in one launch (training: the decoder ran once over all steps' states):
 // blockIdx.y = step k, whose rows are the k-th block of `rows` rows of p / dz.
 struct LossSteps {
@@ -518,6 +529,7 @@ struct LossSteps {
   struct Step { int hist_row, is_last; const unsigned char* present; const int* skip; } step[MMN_MAX_ENCODERS + 1];
 };
 __global__ void wide_decoder_loss_steps_kernel(const __grid_constant__ LossSteps s) {
+  pdl_entry();
   const int k = blockIdx.y;
   LossArgs a = s.base;
   a.p += (long long)k * a.rows * a.ldp;
@@ -534,6 +546,7 @@ __global__ void wide_decoder_loss_steps_kernel(const __grid_constant__ LossSteps
 __global__ void wide_finalize_kernel(const unsigned char* present, long long rows, int k, int hist_row, int e, const int* skip,
                                      const float* sc_sum, int S, double inv_rows_global, double* met_present, double* met_sc,
                                      float* grad_tail) {
+  pdl_entry();
   __shared__ unsigned red[8];
   unsigned n = 0;
   const bool skipped = skip && *skip != 0;
