@@ -684,9 +684,9 @@ def main():
                 continue
             ww = WORKLOADS[name]
             guarded(name, lambda ww=ww: bench.train(ww, ww["batch"], Ks, 3, e2e=name in ("c2_mimic", "c3_mnar", "c4_wide"),
-                                                    e2e_steps=6))
+                                                    e2e_steps=12 if name == "c2_mimic" else 6))
         c2 = WORKLOADS["c2_mimic"]
-        guarded("c2_mimic_bf16", lambda: bench.train(c2, c2["batch"], Ks, 3, precision="bf16", e2e=True, e2e_steps=6))
+        guarded("c2_mimic_bf16", lambda: bench.train(c2, c2["batch"], Ks, 3, precision="bf16", e2e=True, e2e_steps=12))
         c1 = WORKLOADS["c1_titanic"]
         guarded("c1_titanic_bf16", lambda: bench.train(c1, c1["batch"], Ks, 3, precision="bf16", e2e=False))
         guarded("c5_sweep", lambda: bench.predict_sweep(WORKLOADS["c3_mnar"], 1 << 20))
