@@ -160,10 +160,14 @@ enum { MMN_ENGINE_FMA = 0, MMN_ENGINE_TC = 1 /* reserved */, MMN_ENGINE_TC2 = 2,
 int32_t mmn_plan_engine(const mmn_plan* plan);           /* engine of mmn_train_step */
 
 /* Data-parallel overlap (the gradient all-reduce "issued per encoder block in reverse order to overlap with
- * the remaining backward").  events: E + 1 cudaEvent_t handles owned by the caller (n = 0 clears).  Every mmn_train_step
- * then records events[e] on its stream as soon as encoder e's parameter gradients are final and events[E] when the whole
- * gradient buffer is (decoders, initial state, present counts; encoders outside the sequence).  Layer-wise (bf16) plans
- * record them between their launches; the single-launch fp32 kernels record all of them after the launch. */
+ * the remaining backward").  events: cudaEvent_t handles owned by the caller (n = 0 clears).  n = E + 1: every
+ * mmn_train_step records events[e] as soon as encoder e's parameter gradients are final and events[E] when the whole
+ * gradient buffer is (decoders, initial state, present counts; encoders outside the sequence).  n = E + 2 adds
+ * events[E + 1] = every decoder's parameter gradients are final (layer-wise plans finish them before the encoders').
+ * n = E + 2 + (number of encoder Linear layers) adds one event per encoder layer, in (encoder, layer) order: that
+ * layer's weight and bias gradients are final — the last block to finish is then one layer, not one encoder.
+ * Events are recorded on streams ordered with the caller's stream; wait on them from any stream.  Layer-wise (bf16)
+ * plans record them between their launches; the single-launch fp32 kernels record all of them after the launch. */
 int mmn_plan_set_grad_events(mmn_plan* plan, void* const* events, int32_t n);
 int32_t mmn_plan_forward_engine(const mmn_plan* plan);   /* engine of mmn_forward */
 

@@ -216,7 +216,12 @@ extern "C" int64_t mmn_grad_count(const mmn_plan* plan) { return plan ? plan->ho
 
 extern "C" int mmn_plan_set_grad_events(mmn_plan* plan, void* const* events, int32_t n) {
   if (!plan) return fail("mmn_plan_set_grad_events: null plan");
-  if (n != 0 && n != plan->host.E + 1) return fail("mmn_plan_set_grad_events: expected %d events (one per encoder + one), got %d", plan->host.E + 1, n);
+  const int E = plan->host.E;
+  int n_layers = 0;
+  for (int e = 0; e < E; ++e) n_layers += plan->host.enc[e].n_layers;
+  if (n != 0 && n != E + 1 && n != E + 2 && n != E + 2 + n_layers)
+    return fail("mmn_plan_set_grad_events: expected %d (one per encoder + one), %d (+ decoders) or %d (+ one per encoder layer) events, got %d",
+                E + 1, E + 2, E + 2 + n_layers, n);
   if (n && !events) return fail("mmn_plan_set_grad_events: null event array");
   for (int i = 0; i < n; ++i) {
     if (!events[i]) return fail("mmn_plan_set_grad_events: event %d is null", i);

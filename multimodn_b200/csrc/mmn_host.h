@@ -42,8 +42,14 @@ struct mmn_plan {
   void* nb_dev = nullptr;
   void* nb_arena = nullptr;
   // optional cudaEvent_t handles recorded by mmn_train_step as gradient blocks become final (mmn_plan_set_grad_events)
-  void* grad_events[MMN_MAX_ENCODERS + 1] = {};
+  // layout: [0, E) encoder e complete; E = everything; E + 1 = decoders; E + 2 + (layers before (e, j)) = encoder e's layer j
+  void* grad_events[MMN_MAX_ENCODERS + 2 + MMN_MAX_ENCODERS * MMN_MAX_LAYERS] = {};
   int n_grad_events = 0;
+  int grad_layer_event(int e, int j) const {        // index of the per-layer event, -1 if the caller did not ask for them
+    int at = host.E + 2;
+    for (int i = 0; i < e; ++i) at += host.enc[i].n_layers;
+    return at + j < n_grad_events ? at + j : -1;
+  }
 };
 
 int mmn_fail(const char* fmt, ...);       // records the calling thread's error message, returns 1

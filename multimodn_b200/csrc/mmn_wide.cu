@@ -339,6 +339,14 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
   const long long B = a.n_rows;
   const int S = P.S, E = P.E, D = P.D, L = a.seq_len;
   const int n_sms = plan->n_sms;
+  // The GEMMs are persistent (one CTA or CTA pair per SM) and statically scheduled.  In a data-parallel step the NCCL kernels
+  // of the gradient all-reduce run beside the backward GEMMs; each of their CTAs takes an SM for the length of a collective,
+  // the GEMM CTAs that should have run there start a whole collective later and the GEMM takes almost twice as long.
+  // Backward GEMMs launched after the first gradient-ready event therefore leave SMs free for the collectives
+  // (profiles/dp_overlap_probe.sh on 2 GPUs: 148 SMs 3.86 ms/step, 136 3.79, 128 3.71, 124 3.94; MMN_WIDE_COMM_SMS overrides).
+  static const int comm_sms_env = getenv("MMN_WIDE_COMM_SMS") ? atoi(getenv("MMN_WIDE_COMM_SMS")) : 128;
+  const int comm_sms = plan->n_grad_events > 0 && comm_sms_env > 1 && comm_sms_env < n_sms ? (comm_sms_env & ~1) : n_sms;
+  int gemm_sms = n_sms;            // SMs the next GEMM may use
   Arena ar(dry ? nullptr : ws);
   ar.want_t = false;         // weight gradients read dZ and the layer inputs in place (MN-major operands)
   bf16* const wbase = (bf16*)plan->wide_w;
@@ -360,8 +368,8 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
   // when the sub-block starts on a 16-byte boundary but measured 10 % slower on config 4, so it is not used.
   auto needs_wt = [](const DevLayer&) { return true; };
   auto dgrad = [&](const Mat& dz, const DevLayer& l, const mmn_plan::WL& w, int col0, int n, const Epi& e, const char* what) -> int {
-    if (needs_wt(l)) return wide_gemm(n_sms, dz.p, dz.ld, wbase + w.wt + (long long)col0 * w.ldo, w.ldo, B, n, l.out_dim, e, stream, what);
-    return wide_gemm(n_sms, dz.p, dz.ld, wbase + w.w + col0, w.ldk, B, n, l.out_dim, e, stream, what, 0, 1);
+    if (needs_wt(l)) return wide_gemm(gemm_sms, dz.p, dz.ld, wbase + w.wt + (long long)col0 * w.ldo, w.ldo, B, n, l.out_dim, e, stream, what);
+    return wide_gemm(gemm_sms, dz.p, dz.ld, wbase + w.w + col0, w.ldk, B, n, l.out_dim, e, stream, what, 0, 1);
   };
 
   void* cast_jobs_dev = ar.take(sizeof(CastJobs));
@@ -459,7 +467,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
             g_wt.begin("head_fwd");
             launch_head_fwd(dec.C, n_sms, ds, in, wbase + w.w, w.ldk, a.params + ly.b_off, ly.act, B, Pout);
             if (launched()) return 1;
-          } else if (wide_gemm(n_sms, in.p, in.ld, wbase + w.w, w.ldk, B, ly.out_dim, ly.ktot, e, ds, "gemm fwd")) {
+          } else if (wide_gemm(gemm_sms, in.p, in.ld, wbase + w.w, w.ldk, B, ly.out_dim, ly.ktot, e, ds, "gemm fwd")) {
             return 1;
           }
         }
@@ -542,7 +550,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
         ep.sc_sum = TRAIN ? sc_sum + e : nullptr;
       }
       if (!dry) {
-        if (wide_gemm(n_sms, in.p, in.ld, wbase + w.w, w.ldk, B, ly.out_dim, ly.ktot, ep, stream)) return 1;
+        if (wide_gemm(gemm_sms, in.p, in.ld, wbase + w.w, w.ldk, B, ly.out_dim, ly.ktot, ep, stream)) return 1;
         if (!last && enc.L[j + 1].has_state) {
           g_wt.begin("input_state");
           wide_launch(wide_input_state_kernel, dim3(tgrid(B, S)), tb, 0, stream, Sk[k - 1], B, next, enc.L[j + 1].in_dim, nodrop);
@@ -589,7 +597,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
             g_wt.begin("head_fwd");
             launch_head_fwd(dec.C, n_sms, stream, in, wbase + w.w, w.ldk, a.params + ly.b_off, ly.act, R, Pout);
             if (launched()) return 1;
-          } else if (wide_gemm(n_sms, in.p, in.ld, wbase + w.w, w.ldk, R, ly.out_dim, ly.ktot, e, stream, "gemm fwd")) {
+          } else if (wide_gemm(gemm_sms, in.p, in.ld, wbase + w.w, w.ldk, R, ly.out_dim, ly.ktot, e, stream, "gemm fwd")) {
             return 1;
           }
         }
@@ -673,7 +681,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
       Epi e = epi0();
       e.mode = EPI_ACCUM_F32; e.accumulate = 1;
       e.out_f32 = a.grads + ly.w_off; e.ld_f32 = ly.ktot;
-      return wide_gemm(n_sms, dz.p, dz.ld, in.p, in.ld, ly.out_dim, ly.ktot, B, e, stream, "gemm wgrad", 1, 1);
+      return wide_gemm(gemm_sms, dz.p, dz.ld, in.p, in.ld, ly.out_dim, ly.ktot, B, e, stream, "gemm wgrad", 1, 1);
     };
     // Decoders, backward, over the (L + 1) B rows of all steps at once.  On the caller's stream: each decoder's chain from
     // its head down to the gradient dz_0 of its first layer, then DS (+)= dz_0 . W_0, the decoders' gradient with respect
@@ -714,12 +722,12 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
             Epi e = epi0();
             e.mode = EPI_ACCUM_F32; e.accumulate = 1;
             e.out_f32 = a.grads + ly.w_off; e.ld_f32 = ly.ktot;
-            if (wide_gemm(n_sms, dz.p, dz.ld, in.p, in.ld, ly.out_dim, ly.ktot, R, e, stream, "gemm wgrad", 1, 1)) return 1;
+            if (wide_gemm(gemm_sms, dz.p, dz.ld, in.p, in.ld, ly.out_dim, ly.ktot, R, e, stream, "gemm wgrad", 1, 1)) return 1;
             Epi ed = epi0();
             ed.mode = EPI_DACT; ed.act = dec.L[j - 1].act;
             ed.aux = in.p; ed.ld_aux = in.ld;
             ed.out = nz.p; ed.ld_out = nz.ld;
-            if (wide_gemm(n_sms, dz.p, dz.ld, wbase + w.wt, w.ldo, R, ly.in_dim, ly.out_dim, ed, stream, "gemm dgrad")) return 1;
+            if (wide_gemm(gemm_sms, dz.p, dz.ld, wbase + w.wt, w.ldo, R, ly.in_dim, ly.out_dim, ed, stream, "gemm dgrad")) return 1;
           }
           dz = nz;
           cur ^= 1;
@@ -730,8 +738,9 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
         Epi e = epi0();
         e.mode = EPI_ACCUM_F32; e.accumulate = d > 0;
         e.out_f32 = DS; e.ld_f32 = S;
-        if (wide_gemm(n_sms, dz0[d].p, dz0[d].ld, wbase + w0.wt, w0.ldo, R, S, l0.out_dim, e, stream, "gemm dgrad")) return 1;
+        if (wide_gemm(gemm_sms, dz0[d].p, dz0[d].ld, wbase + w0.wt, w0.ldo, R, S, l0.out_dim, e, stream, "gemm dgrad")) return 1;
       }
+      gemm_sms = comm_sms;         // from here on collectives may be in flight
       if (!dry) {
         if (dec_side) {
           MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->dec_fork, stream));
@@ -745,9 +754,11 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
           Epi e = epi0();
           e.mode = EPI_ACCUM_F32; e.accumulate = 1;
           e.out_f32 = a.grads + l0.w_off; e.ld_f32 = l0.ktot;
-          if (wide_gemm(n_sms, dz0[d].p, dz0[d].ld, Sall.p, Sall.ld, l0.out_dim, l0.ktot, R, e, dstream, "gemm wgrad", 1, 1)) return 1;
+          if (wide_gemm(gemm_sms, dz0[d].p, dz0[d].ld, Sall.p, Sall.ld, l0.out_dim, l0.ktot, R, e, dstream, "gemm wgrad", 1, 1)) return 1;
         }
         if (dec_side) MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->dec_done[0], dstream));
+        // every decoder's parameter gradients are final (heads and deeper layers were finished on the caller's stream before the fork)
+        if (plan->n_grad_events > E + 1) MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->grad_events[E + 1], dstream));
       }
     }
     for (int k = L; k >= 1; --k) {
@@ -771,6 +782,10 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
         const mmn_plan::WL& w = plan->wide_enc[e][j];
         const Mat in = enc_in[(size_t)k * MMN_MAX_LAYERS + j];
         if (layer_param_grads(ly, dz, in)) return 1;
+        if (!dry && plan->grad_layer_event(e, j) >= 0) {      // this layer's weight and bias gradients are final
+          if (join_side()) return 1;                          // (the bias sums ran beside the GEMM and are long done)
+          MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->grad_events[plan->grad_layer_event(e, j)], stream));
+        }
         if (ly.has_state && !dry) {
           // carry into G: present rows take dz W_s (through the dropout mask), absent rows keep G; u_k is removed in the same epilogue
           Epi ep = epi0();
@@ -812,8 +827,12 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
       wide_launch(wide_colsum_f32_kernel, dim3((unsigned)((S + 31) / 32), 16), dim3(256), 0, stream, G, DS, B, S, a.grads + P.init_off);
       if (launched()) return 1;
       if (dec_side) MMN_CUDA(cudaStreamWaitEvent(stream, (cudaEvent_t)plan->dec_done[0], 0));      // the decoders' parameter gradients
-      for (int i = 0; i < plan->n_grad_events; ++i)      // decoders, initial state, encoders that took no step
+      for (int i = 0; i < std::min(plan->n_grad_events, E + 1); ++i)      // everything; encoders that took no step
         if (i == E || !(ev_done & (1u << i))) MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->grad_events[i], stream));
+      for (int e = 0; e < E; ++e)                        // layers of encoders that took no step
+        for (int j = 0; j < P.enc[e].n_layers; ++j)
+          if (!(ev_done & (1u << e)) && plan->grad_layer_event(e, j) >= 0)
+            MMN_CUDA(cudaEventRecord((cudaEvent_t)plan->grad_events[plan->grad_layer_event(e, j)], stream));
     }
   }
   g_wt.report();

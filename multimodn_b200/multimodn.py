@@ -101,13 +101,20 @@ class _Runtime:
             pass
 
     def enable_grad_events(self):
-        """E + 1 CUDA events the library records as gradient blocks become final (mmn_plan_set_grad_events)."""
-        events = [torch.cuda.Event() for _ in range(self.E + 1)]
+        """CUDA events the library records as gradient blocks become final (mmn_plan_set_grad_events): one per encoder, one
+        for the whole buffer, one for the decoders and one per encoder layer (``grad_layer_events[e][j]``)."""
+        n_layers = [len(m.layers) for m in self.packed.encoders]
+        n = self.E + 2 + sum(n_layers)
+        events = [torch.cuda.Event() for _ in range(n)]
         for ev in events:
             ev.record(torch.cuda.current_stream(self.device))      # creates the underlying cudaEvent_t
-        handles = (C.c_void_p * (self.E + 1))(*[ev.cuda_event for ev in events])
-        self.lib.check(self.lib.dll.mmn_plan_set_grad_events(self.plan, handles, self.E + 1))
+        handles = (C.c_void_p * n)(*[ev.cuda_event for ev in events])
+        self.lib.check(self.lib.dll.mmn_plan_set_grad_events(self.plan, handles, n))
         self.grad_events = events
+        self.grad_layer_events, at = [], self.E + 2
+        for k in n_layers:
+            self.grad_layer_events.append(events[at:at + k])
+            at += k
         self.comm_stream = torch.cuda.Stream(self.device)
 
     # ------------------------------------------------------------------------------------------
@@ -373,11 +380,13 @@ class MultiModN(nn.Module):
 
     def _allreduce_grads(self, rt, seq):
         """Gradient all-reduce of one train step.  Fused single-launch plans: one collective over the packed buffer.
-        Layer-wise (bf16) plans: one collective per encoder block on a side stream behind the block's gradient-ready
-        event, so that it overlaps the remaining backward GEMMs.  The collectives are issued in an order
-        that does not depend on the rank-local sequence (descending encoder id = the order the default sequence finishes
-        them; an encoder outside the sequence waits for the end-of-step event), so ranks that disagree on the sequence
-        still pair their collectives — the disagreement itself is reported by ``_dp_note`` / ``check_data_parallel``."""
+        Layer-wise (bf16) plans: one collective per gradient block on a side stream behind the block's gradient-ready
+        event, so that it overlaps the remaining backward GEMMs: first the decoders (finished before the
+        encoders' backward), then every encoder layer in the order the default sequence finishes them (descending encoder
+        id, last layer first) — the block left exposed at the end of the step is one layer — then the initial state and the
+        counters.  The order does not depend on the rank-local sequence (an encoder outside the sequence waits for the
+        end-of-step event), so ranks that disagree on the sequence still pair their collectives — the disagreement itself
+        is reported by ``_dp_note`` / ``check_data_parallel``."""
         if not (self._dp and self._dp[0] > 1):
             return
         if not rt.grad_events:
@@ -388,12 +397,16 @@ class MultiModN(nn.Module):
         in_seq = {e for _, e in seq}
         all_ids = list(range(rt.E - 1, -1, -1))
         with torch.cuda.stream(comm):
+            dec = rt.packed.decoder_range()
+            comm.wait_event(rt.grad_events[rt.E + 1])
+            torch.distributed.all_reduce(rt.gflat[dec[0]:dec[1]], group=self._dp[2])
             for e in all_ids:
-                comm.wait_event(rt.grad_events[e if e in in_seq else rt.E])
-                lo, hi = rt.packed.encoder_range(e)
-                torch.distributed.all_reduce(rt.gflat[lo:hi], group=self._dp[2])
+                ranges = rt.packed.encoder_layer_ranges(e)
+                for j in range(len(ranges) - 1, -1, -1):
+                    comm.wait_event(rt.grad_layer_events[e][j] if e in in_seq else rt.grad_events[rt.E])
+                    torch.distributed.all_reduce(rt.gflat[ranges[j][0]:ranges[j][1]], group=self._dp[2])
             comm.wait_event(rt.grad_events[rt.E])
-            for lo, hi in rt.packed.complement_ranges(all_ids, rt.n_grads):
+            for lo, hi in rt.packed.complement_ranges(all_ids, rt.n_grads, also=[dec]):
                 torch.distributed.all_reduce(rt.gflat[lo:hi], group=self._dp[2])
         main.wait_stream(comm)
 

@@ -191,9 +191,18 @@ class PackedModel:
         offs = [(off, off + p.numel()) for p, off, owner in self.slots if owner == e]
         return min(lo for lo, _ in offs), max(hi for _, hi in offs)
 
-    def complement_ranges(self, encoders, total: int):
-        """what is left of [0, total) once the blocks of `encoders` are removed, as a list of [lo, hi)"""
-        taken = sorted(self.encoder_range(e) for e in encoders)
+    def encoder_layer_ranges(self, e: int):
+        """[lo, hi) of every Linear layer (weight and bias, adjacent in the packed buffer) of encoder e, in layer order"""
+        return [(l.w_off, l.b_off + l.linear.bias.numel()) for l in self.encoders[e].layers]
+
+    def decoder_range(self):
+        """[lo, hi) of all decoders' parameters (packed behind the last encoder)"""
+        offs = [(l.w_off, l.b_off + l.linear.bias.numel()) for m in self.decoders for l in m.layers]
+        return min(lo for lo, _ in offs), max(hi for _, hi in offs)
+
+    def complement_ranges(self, encoders, total: int, also=()):
+        """what is left of [0, total) once the blocks of `encoders` (and the ranges in `also`) are removed, as a list of [lo, hi)"""
+        taken = sorted([self.encoder_range(e) for e in encoders] + list(also))
         out, at = [], 0
         for lo, hi in taken:
             if lo > at:
