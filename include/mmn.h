@@ -169,6 +169,12 @@ int32_t mmn_plan_engine(const mmn_plan* plan);           /* engine of mmn_train_
  * Events are recorded on streams ordered with the caller's stream; wait on them from any stream.  Layer-wise (bf16)
  * plans record them between their launches; the single-launch fp32 kernels record all of them after the launch. */
 int mmn_plan_set_grad_events(mmn_plan* plan, void* const* events, int32_t n);
+/* Layer-wise (bf16) plans: SMs the backward GEMMs may use while gradient collectives are in flight (between the first
+ * gradient-ready event of a step and its end).  The GEMMs are persistent and statically scheduled: a collective's CTAs that
+ * take SMs from a running GEMM make it wait a whole collective for its last tiles, so a data-parallel caller leaves the
+ * collective its SMs up front (NCCL on B200: ~20 CTAs on 2 GPUs, 24 NVLS channels on 8).  0 = all SMs (default without
+ * grad events); with grad events the default is 128.  Ignored by the single-launch engines. */
+int mmn_plan_set_comm_sms(mmn_plan* plan, int32_t n_sms);
 int32_t mmn_plan_forward_engine(const mmn_plan* plan);   /* engine of mmn_forward */
 
 int64_t mmn_metrics_count(const mmn_plan* plan);            /* doubles in mmn_outputs.metrics */

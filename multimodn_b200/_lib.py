@@ -62,7 +62,7 @@ PRECISIONS = {"fp32": 0, "bf16": 1}      # MMN_PRECISION_*
 EXPORTS = ("mmn_last_error", "mmn_abi_version", "mmn_plan_create", "mmn_plan_destroy", "mmn_metrics_count",
            "mmn_grad_count", "mmn_workspace_bytes", "mmn_scan_missing", "mmn_forward", "mmn_train_step",
            "mmn_adam_step", "mmn_selftest_umma", "mmn_selftest_protocol", "mmn_plan_engine", "mmn_plan_forward_engine",
-           "mmn_selftest_gemm_bf16", "mmn_selftest_gemm_bf16_mn", "mmn_wide_launch_count", "mmn_plan_set_grad_events",
+           "mmn_selftest_gemm_bf16", "mmn_selftest_gemm_bf16_mn", "mmn_wide_launch_count", "mmn_plan_set_grad_events", "mmn_plan_set_comm_sms",
            "mmn_selftest_fma_peak")
 
 
@@ -118,6 +118,7 @@ class Library:
         d.mmn_wide_launch_count.restype = C.c_int64
         d.mmn_selftest_fma_peak.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]
         d.mmn_plan_set_grad_events.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32]
+        d.mmn_plan_set_comm_sms.argtypes = [C.c_void_p, C.c_int32]
         if d.mmn_abi_version() != ABI_VERSION:
             raise MMNError(f"{path}: ABI version {d.mmn_abi_version()} != {ABI_VERSION}; rebuild the library")
 

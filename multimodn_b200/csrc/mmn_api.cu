@@ -231,6 +231,13 @@ extern "C" int mmn_plan_set_grad_events(mmn_plan* plan, void* const* events, int
   return 0;
 }
 
+extern "C" int mmn_plan_set_comm_sms(mmn_plan* plan, int32_t n_sms) {
+  if (!plan) return fail("mmn_plan_set_comm_sms: null plan");
+  if (n_sms < 0) return fail("mmn_plan_set_comm_sms: negative SM count");
+  plan->comm_sms = n_sms;
+  return 0;
+}
+
 extern "C" int32_t mmn_plan_engine(const mmn_plan* plan) { return plan ? plan->engine : -1; }
 extern "C" int32_t mmn_plan_forward_engine(const mmn_plan* plan) { return plan ? plan->fwd_engine : -1; }
 

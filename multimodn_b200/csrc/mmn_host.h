@@ -45,6 +45,7 @@ struct mmn_plan {
   // layout: [0, E) encoder e complete; E = everything; E + 1 = decoders; E + 2 + (layers before (e, j)) = encoder e's layer j
   void* grad_events[MMN_MAX_ENCODERS + 2 + MMN_MAX_ENCODERS * MMN_MAX_LAYERS] = {};
   int n_grad_events = 0;
+  int comm_sms = 0;                 // mmn_plan_set_comm_sms; 0 = default
   int grad_layer_event(int e, int j) const {        // index of the per-layer event, -1 if the caller did not ask for them
     int at = host.E + 2;
     for (int i = 0; i < e; ++i) at += host.enc[i].n_layers;

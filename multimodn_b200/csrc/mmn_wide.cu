@@ -343,9 +343,11 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
   // of the gradient all-reduce run beside the backward GEMMs; each of their CTAs takes an SM for the length of a collective,
   // the GEMM CTAs that should have run there start a whole collective later and the GEMM takes almost twice as long.
   // Backward GEMMs launched after the first gradient-ready event therefore leave SMs free for the collectives
-  // (profiles/dp_overlap_probe.sh on 2 GPUs: 148 SMs 3.86 ms/step, 136 3.79, 128 3.71, 124 3.94; MMN_WIDE_COMM_SMS overrides).
-  static const int comm_sms_env = getenv("MMN_WIDE_COMM_SMS") ? atoi(getenv("MMN_WIDE_COMM_SMS")) : 128;
-  const int comm_sms = plan->n_grad_events > 0 && comm_sms_env > 1 && comm_sms_env < n_sms ? (comm_sms_env & ~1) : n_sms;
+  // (mmn_plan_set_comm_sms; profiles/dp_overlap_probe.sh on 2 GPUs: 148 SMs 3.82 ms/step, 136 3.72, 128 3.65, 120 3.80; 8 GPUs, NVLS with
+  // 24 channels: 148 4.05, 112 3.96; MMN_WIDE_COMM_SMS overrides).
+  static const int comm_sms_env = getenv("MMN_WIDE_COMM_SMS") ? atoi(getenv("MMN_WIDE_COMM_SMS")) : 0;
+  const int comm_sms_want = comm_sms_env ? comm_sms_env : (plan->comm_sms ? plan->comm_sms : 128);
+  const int comm_sms = plan->n_grad_events > 0 && comm_sms_want > 1 && comm_sms_want < n_sms ? (comm_sms_want & ~1) : n_sms;
   int gemm_sms = n_sms;            // SMs the next GEMM may use
   Arena ar(dry ? nullptr : ws);
   ar.want_t = false;         // weight gradients read dZ and the layer inputs in place (MN-major operands)

@@ -28,6 +28,7 @@ import random
 from typing import Callable, Iterable, List, Optional, Tuple, Union
 
 import numpy as np
+import os
 import torch
 import torch.nn as nn
 from torch import Tensor
@@ -372,6 +373,9 @@ class MultiModN(nn.Module):
         dist.broadcast(rt.flat, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         if self._dp[0] > 1 and rt.layerwise and self.device.type == "cuda":
             rt.enable_grad_events()
+            # SMs the backward GEMMs leave to the collectives' kernels (mmn_plan_set_comm_sms): measured on B200, NCCL 2.28 —
+            # 2 GPUs (P2P rings) 128 of 148, 8 GPUs (NVLS, 24 channels) 112
+            rt.lib.check(rt.lib.dll.mmn_plan_set_comm_sms(rt.plan, 128 if self._dp[0] <= 2 else 112))
         return self
 
     def _allreduce(self, tensor):
@@ -400,7 +404,15 @@ class MultiModN(nn.Module):
             dec = rt.packed.decoder_range()
             comm.wait_event(rt.grad_events[rt.E + 1])
             torch.distributed.all_reduce(rt.gflat[dec[0]:dec[1]], group=self._dp[2])
+            # one collective per encoder layer shortens the exposed tail (one layer instead of one encoder) but triples the
+            # number of collectives; MMN_DP_BLOCKS=layer|encoder overrides the choice below
+            per_layer = os.environ.get("MMN_DP_BLOCKS", "layer" if self._dp[0] <= 2 else "encoder") != "encoder"
             for e in all_ids:
+                if not per_layer:       # one collective per encoder (fewer launches, a longer exposed tail)
+                    comm.wait_event(rt.grad_events[e if e in in_seq else rt.E])
+                    lo, hi = rt.packed.encoder_range(e)
+                    torch.distributed.all_reduce(rt.gflat[lo:hi], group=self._dp[2])
+                    continue
                 ranges = rt.packed.encoder_layer_ranges(e)
                 for j in range(len(ranges) - 1, -1, -1):
                     comm.wait_event(rt.grad_layer_events[e][j] if e in in_seq else rt.grad_events[rt.E])
