@@ -28,6 +28,10 @@ struct mmn_plan {
   struct WL { long long w, wt; int ldk, ldo; };
   WL wide_enc[MMN_MAX_ENCODERS][MMN_MAX_LAYERS];
   WL wide_dec[MMN_MAX_DECODERS][MMN_MAX_LAYERS];
+  // > 0: the transposed first-layer images of all decoders sit side by side in one [S x dec_cat_k] matrix (pitch dec_cat_k;
+  // decoder d's columns start at dec_cat_col[d]), so sum_d dz0_d . W0_d is one GEMM with K = dec_cat_k
+  int dec_cat_k = 0;
+  int dec_cat_col[MMN_MAX_DECODERS] = {};
   // layer-wise plans: an internal side stream (forked from / joined to the caller's stream with events) on which the small
   // bias-gradient reductions run concurrently with the weight-gradient GEMMs
   void* side_stream = nullptr;

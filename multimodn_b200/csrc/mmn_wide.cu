@@ -263,6 +263,25 @@ int mmn_wide_plan_init(mmn_plan* p) {
   }
   for (int d = 0; d < P.D; ++d)
     for (int j = 0; j < P.dec[d].n_layers; ++j) place(P.dec[d].L[j], p->wide_dec[d][j]);
+  // The decoders' data gradients with respect to the state, sum_d dz0_d . W0_d, as ONE GEMM: the transposed first-layer
+  // images W0_d^T [S x h_d] side by side (K-concatenation).  Needs a hidden layer in every decoder (dz0_d is then a buffer of
+  // ours, written as a column block of one matrix) and 16-byte aligned column blocks.
+  bool cat = P.D >= 2;
+  int cat_k = 0;
+  for (int d = 0; d < P.D; ++d) {
+    cat = cat && P.dec[d].n_layers >= 2 && P.dec[d].L[0].out_dim % 8 == 0 && P.dec[d].L[0].ktot == P.S;
+    p->dec_cat_col[d] = cat_k;
+    cat_k += P.dec[d].L[0].out_dim;
+  }
+  if (cat) {
+    p->dec_cat_k = cat_k;
+    const long long base = off;
+    off += ((long long)P.S * cat_k + 127) & ~127ll;
+    for (int d = 0; d < P.D; ++d) {
+      p->wide_dec[d][0].wt = base + p->dec_cat_col[d];
+      p->wide_dec[d][0].ldo = cat_k;
+    }
+  }
   p->wide_elems = off;
   cudaStream_t side;
   cudaEvent_t fork, done;
@@ -698,7 +717,18 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
       Mat dzdec[2];                               // intermediates of decoders deeper than two layers
       if (deep) { dzdec[0] = ar.mat(R, maxW); dzdec[1] = ar.mat(R, maxW); }
       std::vector<Mat> dz0(D);                    // dz of every decoder's first layer
-      for (int d = 0; d < D; ++d) dz0[d] = P.dec[d].n_layers > 1 ? ar.mat(R, P.dec[d].L[0].out_dim) : dec_dzall[d];
+      const bool cat = plan->dec_cat_k > 0;       // column blocks of one matrix: the data gradient below is a single GEMM
+      Mat dz0cat = Mat();
+      if (cat) dz0cat = ar.mat(R, plan->dec_cat_k);
+      for (int d = 0; d < D; ++d) {
+        if (cat) {
+          dz0[d] = dz0cat;
+          dz0[d].p = dz0cat.p ? dz0cat.p + plan->dec_cat_col[d] : nullptr;
+          dz0[d].width = P.dec[d].L[0].out_dim;
+        } else {
+          dz0[d] = P.dec[d].n_layers > 1 ? ar.mat(R, P.dec[d].L[0].out_dim) : dec_dzall[d];
+        }
+      }
       const auto bias_grid = [&](int out_dim) {
         return dim3((unsigned)((out_dim + 63) / 64), (unsigned)std::max<long long>(1, std::min<long long>(32, R / 256)));
       };
@@ -734,6 +764,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
           dz = nz;
           cur ^= 1;
         }
+        if (cat) continue;
         // DS (+)= dz_0 . W_0
         const DevLayer& l0 = dec.L[0];
         const mmn_plan::WL& w0 = plan->wide_dec[d][0];
@@ -741,6 +772,14 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
         e.mode = EPI_ACCUM_F32; e.accumulate = d > 0;
         e.out_f32 = DS; e.ld_f32 = S;
         if (wide_gemm(gemm_sms, dz0[d].p, dz0[d].ld, wbase + w0.wt, w0.ldo, R, S, l0.out_dim, e, stream, "gemm dgrad")) return 1;
+      }
+      if (cat && !dry) {         // DS = [dz0_0 | dz0_1 | ...] . [W0_0; W0_1; ...]
+        Epi e = epi0();
+        e.mode = EPI_ACCUM_F32; e.accumulate = 0;
+        e.out_f32 = DS; e.ld_f32 = S;
+        if (wide_gemm(gemm_sms, dz0cat.p, dz0cat.ld, wbase + plan->wide_dec[0][0].wt, plan->dec_cat_k, R, S, plan->dec_cat_k, e, stream,
+                      "gemm dgrad"))
+          return 1;
       }
       gemm_sms = comm_sms;         // from here on collectives may be in flight
       if (!dry) {
