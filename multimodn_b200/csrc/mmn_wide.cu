@@ -516,7 +516,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
   std::vector<StepMeta> meta(L + 1);
   meta[0] = {0, false, nullptr};
   if (!TRAIN && decoders_forward(0, 0, false, nullptr)) return 1;
-  if (!dry) {
+  if (!dry && !TRAIN) {          // (training: the bookkeeping of all steps is one launch after the walk)
     g_wt.begin("finalize");
     wide_launch(wide_finalize_kernel, dim3(1), dim3(256), 0, stream, present, B, 0, 0, 0, nullptr, nullptr, S, a.inv_rows_global,
                                                 a.metrics ? a.metrics + met_present(P, 0) : nullptr, nullptr, nullptr);
@@ -541,12 +541,15 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
     Mat in = ar.mat(B, enc.L[0].ktot);
     enc_in[(size_t)k * MMN_MAX_LAYERS + 0] = in;
     if (!dry) {
-      g_wt.begin("input_x");
-      wide_launch(wide_input_x_kernel, dim3(tgrid(B, enc.F)), tb, 0, stream, a.x[pos], a.x_ld[pos], B, enc.F, in, pres, drop);
-      if (launched()) return 1;
-      if (enc.L[0].has_state) {
-        g_wt.begin("input_state");
-        wide_launch(wide_input_state_kernel, dim3(tgrid(B, S)), tb, 0, stream, Sk[k - 1], B, in, enc.L[0].in_dim, drop);
+      if (enc.L[0].has_state) {         // features and state side by side: one launch
+        g_wt.begin("input_x");
+        const dim3 gx = tgrid(B, enc.F), gs = tgrid(B, S);
+        wide_launch(wide_input_xs_kernel, dim3(gx.x + gs.x, gx.y), tb, 0, stream, a.x[pos], a.x_ld[pos], B, enc.F, Sk[k - 1], in,
+                    enc.L[0].in_dim, pres, drop);
+        if (launched()) return 1;
+      } else {
+        g_wt.begin("input_x");
+        wide_launch(wide_input_x_kernel, dim3(tgrid(B, enc.F)), tb, 0, stream, a.x[pos], a.x_ld[pos], B, enc.F, in, pres, drop);
         if (launched()) return 1;
       }
     }
@@ -580,7 +583,7 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
       }
       in = next;
     }
-    if (!dry) {
+    if (!dry && !TRAIN) {
       g_wt.begin("finalize");
       wide_launch(wide_finalize_kernel, dim3(1), dim3(256), 0, stream, pres, B, k, e + 1, e, skip, TRAIN ? sc_sum + e : nullptr, S, a.inv_rows_global,
                                                   a.metrics ? a.metrics + met_present(P, 0) : nullptr,
@@ -591,6 +594,22 @@ int wide_step(const mmn_plan* plan, const StepArgs& a, void* ws, size_t ws_bytes
     meta[k] = {e + 1, e == E - 1, skip};
     if (!TRAIN && decoders_forward(k, e + 1, e == E - 1, skip)) return 1;
     if (!TRAIN) ar.off = scratch_mark;
+  }
+  if (TRAIN && !dry) {           // per-step bookkeeping (present-row counts, state-change means), all steps in one launch
+    FinalizeSteps fs;
+    memset(&fs, 0, sizeof fs);
+    fs.present = present; fs.rows = B; fs.sc_sum = sc_sum; fs.S = S; fs.inv_rows_global = a.inv_rows_global;
+    fs.met_present = a.metrics ? a.metrics + met_present(P, 0) : nullptr;
+    fs.met_sc = a.metrics ? a.metrics + met_sc(P, 0) : nullptr;
+    fs.grad_tail = a.grads + P.n_params;
+    for (int k = 0; k <= L; ++k) {
+      fs.step[k].hist_row = meta[k].hist_row;
+      fs.step[k].e = k == 0 ? 0 : a.seq_enc[k - 1];
+      fs.step[k].skip = meta[k].skip;
+    }
+    g_wt.begin("finalize");
+    wide_launch(wide_finalize_steps_kernel, dim3((unsigned)(L + 1)), dim3(256), 0, stream, fs);
+    if (launched()) return 1;
   }
   // ---- training: every decoder, once, over the (L + 1) B state rows ----
   std::vector<Mat> dec_hall((size_t)D * MMN_MAX_LAYERS);     // hidden activations [R x width] of decoder d, layer j

@@ -67,11 +67,11 @@ __device__ __forceinline__ void load8(const float* p, int n_valid, float (&f)[8]
 // Launch: 256 threads, grid (ceil(width / 64), ceil(rows / 64)).
 template <typename F>
 __device__ __forceinline__ void tile64_emit(F value8, long long rows, int width, bf16* dst, long long ld, bf16* dst_t, long long ldt,
-                                            int colofs) {
+                                            int colofs, int col_tile = -1) {
   __shared__ __align__(16) bf16 tile[64][72];
   const int t = threadIdx.x;
   const long long r0 = (long long)blockIdx.y * 64;
-  const int c0 = blockIdx.x * 64;
+  const int c0 = (col_tile < 0 ? (int)blockIdx.x : col_tile) * 64;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int rr = (t >> 3) + 32 * i, cc = (t & 7) * 8;
@@ -155,6 +155,36 @@ __global__ void __launch_bounds__(256) wide_input_state_kernel(Mat s, long long 
         v[i] = mmn_dropout_keep(drop.seed_mix, drop.row_base + (unsigned)r, (unsigned)(colofs + c + i), drop.thr) ? v[i] * drop.scale : 0.f;
     }
   }, rows, s.width, in.p, in.ld, in.t, in.ldt, colofs);
+}
+// both parts of an encoder's first-layer input in one launch: column tiles [0, ceil(F / 64)) stage the features, the rest the state
+__global__ void __launch_bounds__(256) wide_input_xs_kernel(const float* __restrict__ x, long long x_ld, long long rows, int F, Mat s,
+                                                            Mat in, int colofs, unsigned char* present, Drop drop) {
+  pdl_entry();
+  const int x_tiles = (F + 63) / 64;
+  if ((int)blockIdx.x < x_tiles) {
+    tile64_emit([&](long long r, int c, int nv, float (&v)[8]) {
+      load8(x + r * x_ld + c, nv, v);
+      bool nan = false;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (v[i] != v[i]) { nan = true; v[i] = 0.f; }
+      if (nan) present[r] = 0;
+      if (drop.enabled) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          v[i] = mmn_dropout_keep(drop.seed_mix, drop.row_base + (unsigned)r, (unsigned)(c + i), drop.thr) ? v[i] * drop.scale : 0.f;
+      }
+    }, rows, F, in.p, in.ld, in.t, in.ldt, 0);
+  } else {
+    tile64_emit([&](long long r, int c, int nv, float (&v)[8]) {
+      load8(s.p + r * s.ld + c, nv, v);
+      if (drop.enabled) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          v[i] = mmn_dropout_keep(drop.seed_mix, drop.row_base + (unsigned)r, (unsigned)(colofs + c + i), drop.thr) ? v[i] * drop.scale : 0.f;
+      }
+    }, rows, s.width, in.p, in.ld, in.t, in.ldt, colofs, (int)blockIdx.x - x_tiles);
+  }
 }
 // s_0 = tile(state_value) (state.py:29-32)
 __global__ void __launch_bounds__(256) wide_init_state_kernel(const float* __restrict__ init, long long rows, Mat s) {
@@ -543,10 +573,9 @@ __global__ void wide_decoder_loss_steps_kernel(const __grid_constant__ LossSteps
   decoder_loss_rows(a);
 }
 // per-step bookkeeping: present-row counts, state-change means, the gradient buffer's "encoder took a row" tail
-__global__ void wide_finalize_kernel(const unsigned char* present, long long rows, int k, int hist_row, int e, const int* skip,
-                                     const float* sc_sum, int S, double inv_rows_global, double* met_present, double* met_sc,
-                                     float* grad_tail) {
-  pdl_entry();
+__device__ __forceinline__ void finalize_step(const unsigned char* present, long long rows, int k, int hist_row, int e, const int* skip,
+                                              const float* sc_sum, int S, double inv_rows_global, double* met_present, double* met_sc,
+                                              float* grad_tail) {
   __shared__ unsigned red[8];
   unsigned n = 0;
   const bool skipped = skip && *skip != 0;
@@ -564,6 +593,25 @@ __global__ void wide_finalize_kernel(const unsigned char* present, long long row
       if (grad_tail && tot) atomicAdd(grad_tail + e, (float)tot);
     }
   }
+}
+__global__ void wide_finalize_kernel(const unsigned char* present, long long rows, int k, int hist_row, int e, const int* skip,
+                                     const float* sc_sum, int S, double inv_rows_global, double* met_present, double* met_sc,
+                                     float* grad_tail) {
+  pdl_entry();
+  finalize_step(present, rows, k, hist_row, e, skip, sc_sum, S, inv_rows_global, met_present, met_sc, grad_tail);
+}
+// every step of a training call in one launch: blockIdx.x = step k (present: [(L + 1) x rows], sc_sum: one float per encoder)
+struct FinalizeSteps {
+  const unsigned char* present; long long rows;
+  const float* sc_sum; int S; double inv_rows_global;
+  double* met_present; double* met_sc; float* grad_tail;
+  struct Step { int hist_row, e; const int* skip; } step[MMN_MAX_ENCODERS + 1];
+};
+__global__ void wide_finalize_steps_kernel(const __grid_constant__ FinalizeSteps s) {
+  pdl_entry();
+  const int k = blockIdx.x;
+  finalize_step(s.present + (long long)k * s.rows, s.rows, k, s.step[k].hist_row, s.step[k].e, s.step[k].skip,
+                k > 0 && s.sc_sum ? s.sc_sum + s.step[k].e : nullptr, s.S, s.inv_rows_global, s.met_present, s.met_sc, s.grad_tail);
 }
 
 }  // namespace wide
