@@ -129,3 +129,36 @@ def test_shuffle_mode_under_data_parallel_uses_one_order(tmp_path):
     a, b = np.load(out + ".0.npz"), np.load(out + ".1.npz")
     assert str(a["msg"]) == "ok" and str(b["msg"]) == "ok"
     assert (a["params"] == b["params"]).all()
+
+
+def test_gradient_blocks_partition_the_packed_buffer():
+    """the blocks `_allreduce_grads` reduces one by one on layer-wise plans — the decoders, every encoder layer, the rest —
+    cover the packed gradient buffer exactly once (alignment padding aside), whichever granularity is used"""
+    from oracle.spec_io import random_spec
+    from model_utils import model_from_spec
+    from multimodn_b200.plan import PackedModel
+    rng = np.random.default_rng(3)
+    spec = random_spec(rng, 12, [5, 9, 7], enc_kind="mimic", enc_hidden=(10, 6), dropout=0.0, n_decoders=3, dec_hidden=(8,), n_classes=2)
+    model = model_from_spec(spec, 1.0, 0.3, "cpu", "row")
+    packed = PackedModel(model.init_state.state_value, model.encoders, model.decoders, 12)
+    E, total = len(model.encoders), packed.n_params + len(model.encoders)
+    ids = list(range(E))
+    dec = packed.decoder_range()
+    for per_layer in (True, False):
+        covered = np.zeros(total, dtype=np.int32)
+        covered[dec[0]:dec[1]] += 1
+        for e in ids:
+            blocks = packed.encoder_layer_ranges(e) if per_layer else [packed.encoder_range(e)]
+            lo_e, hi_e = packed.encoder_range(e)
+            for lo, hi in blocks:
+                assert lo_e <= lo < hi <= hi_e
+                covered[lo:hi] += 1
+        for lo, hi in packed.complement_ranges(ids, total, also=[dec]):
+            covered[lo:hi] += 1
+        assert covered.max() == 1
+        # every parameter (and the per-encoder counters behind them) is in exactly one block; only alignment padding is not
+        used = np.zeros(total, dtype=bool)
+        for p, off, _ in packed.slots:
+            used[off:off + p.numel()] = True
+        used[packed.n_params:] = True
+        assert (covered[used] == 1).all()
