@@ -4,14 +4,17 @@
 //   D[M x N] = A[M x K] . B[N x K]^T        A, B bf16, K contiguous (K-major); fp32 accumulation in tensor memory
 //
 // One kernel shape serves forward (A = activations, B = W), data gradient (A = dZ, B = W^T copy) and weight gradient
-// (A = dZ^T, B = X^T: the contraction runs over the batch rows) because every epilogue that produces an activation or a
-// dZ writes it in both orientations (row-major and transposed).
+// (A = dZ, B = X, both read in place as MN-major operands: the contraction runs over the batch rows).
 //
 //   warp 0   TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B boxes of 64 bf16 x 128 / 256 rows) into a 4-stage ring
-//   warp 1   MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M128 N256 K16, 4 per stage; tcgen05.commit frees the stage
+//            (6 stages of 32 KB when two CTAs share a 256 x 256 tile, PAIR)
+//   warp 1   MMA issuer: tcgen05.mma.cta_group::1 / ::2 .kind::f16, N256 K16, 4 per stage; tcgen05.commit frees the stage
 //   warp 2   TMEM allocator (512 columns = two 128 x 256 fp32 accumulators: the epilogue of tile i overlaps tile i+1)
 //   warps 4-11 epilogue (two per TMEM lane quarter, 128 columns each): tcgen05.ld 16 columns at a time -> bias /
-//            activation / select / derivative -> row-major stores + lane-pair-packed transposed stores
+//            activation / select / derivative / accumulation.  Interior tiles run epi_lean<MODE> (one straight-line loop
+//            per mode, bias slice in shared memory, row operands prefetched, stores transposed through a swizzled per-warp
+//            staging buffer so that each store instruction writes 8 rows x 64 contiguous bytes); edge tiles and the
+//            transposed-copy output of the self-test run the generic loop below it.
 //
 // Out-of-range rows / columns / k are zero-filled by the TMA unit, so M, N, K need no padding (row pitches: 16 bytes).
 #pragma once
